@@ -1,0 +1,16 @@
+"""convofusion_b200 -- B200-native (sm_100a) implementation of ConvoFusion's sampling hot path.
+
+Public surface (mirrors the reference's operator surface):
+  Denoiser, ConvoFusionVae            drop-in modules (identical state_dict keys and call signatures)
+  DDIMScheduler, DDPMScheduler        diffusers-0.14-compatible scheduler mirrors
+  ConvoFusionSampler                  test_diffusion_forward / unbounded synthesis orchestration
+All arithmetic runs in lib/libconvofusion_b200.so (hand-written CUDA, C ABI in include/convofusion_b200.h).
+"""
+from .modules import ConvoFusionVae, Denoiser
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .conditioning import AudioConvEncoder, T5TextEncoder, TextAudioController, TextAudioMotionFuser
+from .sampler import ConvoFusionSampler, default_denoiser, default_scheduler, default_vae
+
+__all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
+           "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
+           "default_denoiser", "default_vae", "default_scheduler"]

@@ -1,0 +1,107 @@
+// Shared helpers for the convofusion_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include "../../include/convofusion_b200.h"
+
+namespace cfb {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;
+
+#define CFB_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      cfb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return CFB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define CFB_CHECK(cond, ...)                                                             \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      cfb::set_error(__VA_ARGS__);                                                       \
+      return CFB_ERR_INVALID;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define CFB_TRY(expr)                                                                    \
+  do {                                                                                   \
+    int _s = (expr);                                                                     \
+    if (_s != CFB_OK) return _s;                                                         \
+  } while (0)
+
+// Every kernel launch goes through this so gpu_launches is an honest count.
+#define CFB_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    ++cfb::g_launches;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      cfb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return CFB_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case CFB_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact-erf GELU (F.gelu default)
+    case CFB_ACT_SILU: return v / (1.0f + expf(-v));
+    case CFB_ACT_RELU: return v > 0.f ? v : 0.f;
+    case CFB_ACT_LEAKY01: return v > 0.f ? v : 0.1f * v;
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- epilogue description shared by the SIMT and tcgen05 GEMMs -------------------
+struct Epilogue {
+  const float* bias;   // [bias_period, N] (period 1 = ordinary bias) or nullptr
+  int bias_period;     // rows r use bias[(r % period) * N + n]
+  int act;             // cfb_act applied after bias
+  int accumulate;      // out += value (float out only): residual update
+  int out_bf16;        // element type of out
+  void* out;
+  int ldo;
+  int replicate;       // write `replicate` copies, copy c at out + c * rep_stride elements
+  long long rep_stride;
+};
+
+// GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.
+int gemm_simt(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw, int M, int N, int K,
+              int a_act, const Epilogue& ep, cudaStream_t st);
+bool gemm_tc_supported(int M, int N, int K, int lda, int ldw);
+int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,
+            cudaStream_t st);
+extern int g_gemm_backend;
+
+// y = act(A W^T + b) dispatch: bf16 operands use tcgen05 when allowed, everything else SIMT.
+int gemm(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw, int M, int N, int K,
+         int a_act, const Epilogue& ep, cudaStream_t st);
+
+}  // namespace cfb

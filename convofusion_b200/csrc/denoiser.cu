@@ -1,0 +1,370 @@
+// Denoiser handle: one evaluation (cfb_denoiser_forward) and the whole guided sampling loop
+// (cfb_sample) as a sequence of the kernels in gemm_*.cu / rowops.cu / attention.cu / sched.cu.
+//
+// Data layout in HBM (R = n_batch * n_tokens query rows, batch-major like the reference's
+// batch-first [BG,16,128] sample; d = 512):
+//   h        float [R, d]      residual stream (always fp32)
+//   a        T     [R, d]      current GEMM A operand (LayerNorm / modulation output, attention output)
+//   qkv      T     [R, 3d]     self-attention projections
+//   qx       T     [R, 5d]     folded cross-attention queries, overwritten in place by P.mem_hat
+//   f        T     [R, ff]     GELU(linear1)
+//   mem_c    float [Rm, d]     cond + stream embedding + PE for every memory slot (built once per call)
+//   mem_hat  T     [Rm, d]     LayerNorm-without-affine of (mem_c + time_emb(t)), rebuilt every step
+//   temb / tbmod float [S, d] / [S, L*2*2d]   time embedding and TimeBlock (scale|shift) for all S steps
+// T = float (fp32 parity mode) or bf16 (tensor-core mode).
+#include "common.cuh"
+#include "kernels.cuh"
+#include <vector>
+#include <cstring>
+
+namespace cfb {
+
+int init_gemm_tc_kernels();
+int init_attention_kernels();
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes, unsigned* epoch) {
+    if (bytes <= cap) return CFB_OK;
+    if (p) CFB_CUDA(cudaFree(p));
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    CFB_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    if (epoch) ++*epoch;
+    return CFB_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+}  // namespace cfb
+
+using namespace cfb;
+
+struct cfb_denoiser {
+  cfb_denoiser_weights w;
+  std::vector<cfb_denoiser_layer> layers;
+  int d, lat, ntok, L, H, ff, prec;
+  unsigned epoch = 0;
+  DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
+      preseq, slots, masks;
+  // cached CUDA graph of one sampling step
+  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphKey {
+    unsigned epoch; int n_clips, n_branch, n_steps, kind, clip, preseq_len; float scale;
+    int n_slots[CFB_N_STREAMS], len[CFB_N_STREAMS]; bool has_mask[CFB_N_STREAMS];
+    const void *noise, *record, *att[CFB_N_STREAMS];
+  } graph_key;
+  bool graph_valid = false;
+  size_t graph_nodes = 0;   // kernel nodes in the captured step (for the launch counter)
+};
+
+namespace {
+
+struct MemLayout {
+  int row_base[CFB_N_STREAMS];
+  int total_rows;
+  int slot_off[CFB_N_STREAMS];   // element offsets into h->slots
+  int mask_off[CFB_N_STREAMS];   // byte offsets into h->masks
+};
+
+template <typename T>
+int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaStream_t st) {
+  // denoiser.py:183-187,316-326: latent_embd + body/hand embedding + SineBH positional encoding
+  const int rows = n_in * h->ntok;
+  CFB_TRY(cast_rows<T>(latents, h->xin.as<T>(), (long long)rows * h->lat, st));
+  Epilogue ep{};
+  ep.bias = h->w.tok_bias; ep.bias_period = h->ntok; ep.out = h->h.p; ep.ldo = h->d;
+  ep.replicate = replicate; ep.rep_stride = (long long)rows * h->d;
+  return gemm(h->xin.p, sizeof(T) == 2, h->lat, h->w.w_embed, sizeof(T) == 2, h->lat, rows, h->d, h->lat, 0, ep, st);
+}
+
+template <typename T>
+int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
+               float* eps_out, cudaStream_t st) {
+  const int R = n_batch * h->ntok, d = h->d;
+  const int tb = sizeof(T) == 2;
+  float* hres = h->h.as<float>();
+  T* a = h->a.as<T>();
+  T* qkv = h->qkv.as<T>();
+  T* qx = h->qx.as<T>();
+  T* f = h->f.as<T>();
+  const long long mod_stride = (long long)h->L * 2 * 2 * d;
+  auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
+    Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
+  };
+  auto lin_res = [&](const void* A, int K, const void* W, const float* b) {
+    Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
+    return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
+  };
+  for (int l = 0; l < h->L; ++l) {
+    const cfb_denoiser_layer& w = h->layers[l];
+    const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
+    const float* mod2 = mod1 + 2 * d;
+    // self-attention block (cross_attention.py:568-572)
+    CFB_TRY(ln_rows<T>(hres, w.ln1_g, w.ln1_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin_T(a, d, w.w_in, w.b_in, qkv, 3 * d, 0));
+    CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
+    CFB_TRY(lin_res(a, d, w.w_so, w.b_so));
+    // time_block1 (:575)
+    CFB_TRY(ln_rows<T>(hres, w.tb1_g, w.tb1_b, mod1, step_ptr, mod_stride, a, R, d, st));
+    CFB_TRY(lin_res(a, d, w.w_tb1, w.b_tb1));
+    // five cross-attentions + att_fuser (:578-652), folded
+    CFB_TRY(ln_rows<T>(hres, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
+    for (int x = 0; x < CFB_N_STREAMS; ++x)
+      ca.att[x] = att_base && att_base[x] ? att_base[x] + (size_t)l * h->ntok * ca.len[x] : nullptr;
+    CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), qx, ca, n_batch, h->ntok, d, st));
+    CFB_TRY(lin_res(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu));
+    // time_block2 (:655)
+    CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+    CFB_TRY(lin_res(a, d, w.w_tb2, w.b_tb2));
+    // feed-forward (:659-661)
+    CFB_TRY(ln_rows<T>(hres, w.ln3_g, w.ln3_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU));
+    CFB_TRY(lin_res(f, h->ff, w.w_ff2, w.b_ff2));
+  }
+  // decoder.norm + latent_proj (cross_attention.py:238-239, denoiser.py:382)
+  CFB_TRY(ln_rows<T>(hres, h->w.lnf_g, h->w.lnf_b, nullptr, nullptr, 0, a, R, d, st));
+  Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
+  return gemm(a, tb, d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
+}
+
+// time embedding + TimeBlock (scale|shift) tables for S timesteps already in h->tsteps (float)
+int prep_time(cfb_denoiser* h, int S, cudaStream_t st) {
+  const int d = h->d;
+  const int nmod = h->L * 2 * 2 * d;
+  CFB_TRY(h->tsin.reserve((size_t)S * d * 4, &h->epoch));
+  CFB_TRY(h->t1.reserve((size_t)S * d * 4, &h->epoch));
+  CFB_TRY(h->temb.reserve((size_t)S * d * 4, &h->epoch));
+  CFB_TRY(h->tbmod.reserve((size_t)S * nmod * 4, &h->epoch));
+  CFB_TRY(time_sinusoid(h->tsteps.as<float>(), h->tsin.as<float>(), S, d, st));   // denoiser.py:195-196
+  Epilogue e1{}; e1.bias = h->w.b_t1; e1.bias_period = 1; e1.act = CFB_ACT_SILU; e1.out = h->t1.p; e1.ldo = d; e1.replicate = 1;
+  CFB_TRY(gemm_simt(h->tsin.p, 0, d, h->w.w_t1, 0, d, S, d, d, 0, e1, st));       // embeddings.py:298-305
+  Epilogue e2{}; e2.bias = h->w.b_t2; e2.bias_period = 1; e2.out = h->temb.p; e2.ldo = d; e2.replicate = 1;
+  CFB_TRY(gemm_simt(h->t1.p, 0, d, h->w.w_t2, 0, d, S, d, d, 0, e2, st));
+  Epilogue e3{}; e3.bias = h->w.b_tbmod; e3.bias_period = 1; e3.out = h->tbmod.p; e3.ldo = nmod; e3.replicate = 1;
+  return gemm_simt(h->temb.p, 0, d, h->w.w_tbmod, 0, d, S, nmod, d, CFB_ACT_SILU, e3, st);  // cross_attention.py:433
+}
+
+int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
+  const size_t R = (size_t)n_batch * h->ntok, es = h->prec == CFB_BF16 ? 2 : 4, d = h->d;
+  CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
+  CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
+  CFB_TRY(h->qkv.reserve(R * 3 * d * es, &h->epoch));
+  CFB_TRY(h->qx.reserve(R * CFB_N_STREAMS * d * es, &h->epoch));
+  CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
+  CFB_TRY(h->xin.reserve((size_t)n_in * h->ntok * h->lat * es, &h->epoch));
+  CFB_TRY(h->eps.reserve(R * h->lat * 4, &h->epoch));
+  return CFB_OK;
+}
+
+// Validate the memory description, build mem_c, stage slots/masks in handle-owned buffers.
+int prep_memory(cfb_denoiser* h, const cfb_memory* mem, int n_batch, MemLayout* ml, CrossArgs* ca, cudaStream_t st) {
+  int rows = 0, slot_elems = 0, mask_bytes = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    CFB_CHECK(mem->cond[x] != nullptr && mem->n_slots[x] > 0 && mem->len[x] > 0, "memory stream %d is empty", x);
+    CFB_CHECK(mem->len[x] <= h->w.pe_len, "memory stream %d: %d tokens exceed the positional table (%d)", x, mem->len[x], h->w.pe_len);
+    CFB_CHECK(mem->slot[x] != nullptr || mem->n_slots[x] == n_batch, "memory stream %d: %d slots for %d batch entries and no slot table", x, mem->n_slots[x], n_batch);
+    ml->row_base[x] = rows; rows += mem->n_slots[x] * mem->len[x];
+    ml->slot_off[x] = slot_elems; slot_elems += n_batch;
+    ml->mask_off[x] = mask_bytes; mask_bytes += (mem->n_slots[x] * mem->len[x] + 15) & ~15;
+  }
+  ml->total_rows = rows;
+  const size_t es = h->prec == CFB_BF16 ? 2 : 4;
+  CFB_TRY(h->mem_c.reserve((size_t)rows * h->d * 4, &h->epoch));
+  CFB_TRY(h->mem_hat.reserve((size_t)rows * h->d * es, &h->epoch));
+  CFB_TRY(h->slots.reserve((size_t)slot_elems * 4, &h->epoch));
+  CFB_TRY(h->masks.reserve((size_t)mask_bytes, &h->epoch));
+  CFB_TRY(mem_build(mem->cond, mem->n_slots, mem->len, h->w.stream_emb, h->w.pe_mem, h->mem_c.as<float>(), h->d, st));
+  memset(ca, 0, sizeof(*ca));
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    ca->row_base[x] = ml->row_base[x];
+    ca->len[x] = mem->len[x];
+    if (mem->slot[x]) {
+      int* dst = h->slots.as<int>() + ml->slot_off[x];
+      CFB_CUDA(cudaMemcpyAsync(dst, mem->slot[x], (size_t)n_batch * 4, cudaMemcpyDeviceToDevice, st));
+      ca->slot[x] = dst;
+    }
+    if (mem->mask[x]) {
+      uint8_t* dst = h->masks.as<uint8_t>() + ml->mask_off[x];
+      CFB_CUDA(cudaMemcpyAsync(dst, mem->mask[x], (size_t)mem->n_slots[x] * mem->len[x], cudaMemcpyDeviceToDevice, st));
+      ca->mask[x] = dst;
+    }
+  }
+  return CFB_OK;
+}
+
+template <typename T>
+int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, const CrossArgs& ca,
+              float* const att_base[CFB_N_STREAMS], const StepArgs& sa, cudaStream_t st) {
+  const int* step_ptr = h->step.as<int>();
+  CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
+  CFB_TRY(embed<T>(h, h->x.as<float>(), n_clips, n_branch, st));   // torch.cat([latents] * 7), convofusion.py:499
+  CFB_TRY(run_layers<T>(h, n_clips * n_branch, ca, att_base, step_ptr, h->eps.as<float>(), st));
+  return guidance_sched_step(sa, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
+  CFB_CHECK(w && out, "cfb_denoiser_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: convofusion_b200 has no CPU fallback");
+    return CFB_ERR_NO_DEVICE;
+  }
+  CFB_CHECK(w->d_model == 512, "d_model %d unsupported (512)", w->d_model);
+  CFB_CHECK(w->n_tokens > 0 && w->n_tokens <= 16, "n_tokens %d unsupported (<=16)", w->n_tokens);
+  CFB_CHECK(w->latent_dim % 64 == 0 && w->ff_size % 64 == 0, "latent_dim/ff_size must be multiples of 64");
+  CFB_CHECK(w->precision == CFB_F32 || w->precision == CFB_BF16, "bad precision");
+  CFB_CHECK(w->n_layers > 0 && w->layers != nullptr, "no layers");
+  cfb_denoiser* h = new cfb_denoiser();
+  h->w = *w;
+  h->layers.assign(w->layers, w->layers + w->n_layers);
+  h->w.layers = h->layers.data();
+  h->d = w->d_model; h->lat = w->latent_dim; h->ntok = w->n_tokens; h->L = w->n_layers; h->H = w->n_heads;
+  h->ff = w->ff_size; h->prec = w->precision;
+  int rc = init_gemm_tc_kernels();
+  if (rc == CFB_OK) rc = init_attention_kernels();
+  if (rc != CFB_OK) { delete h; return rc; }
+  *out = h;
+  return CFB_OK;
+}
+
+void cfb_denoiser_destroy(cfb_denoiser* h) {
+  if (!h) return;
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
+                       &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
+                       &h->slots, &h->masks};
+  for (DeviceBuf* b : bufs) b->release();
+  delete h;
+}
+
+int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int64_t timestep, const cfb_memory* mem,
+                         float* eps_out, float* const att_out[CFB_N_STREAMS], cfb_stream stream) {
+  CFB_CHECK(h && sample && mem && eps_out && n_batch > 0, "cfb_denoiser_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CFB_TRY(reserve_rows(h, n_batch, n_batch));
+  CFB_TRY(h->tsteps.reserve(4, &h->epoch));
+  const float tf = (float)timestep;
+  CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, &tf, 4, cudaMemcpyHostToDevice, st));
+  CFB_TRY(prep_time(h, 1, st));
+  MemLayout ml; CrossArgs ca;
+  CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    ca.att_batch_stride[x] = (long long)h->L * h->ntok * mem->len[x];
+    ca.att_step_stride[x] = 0;
+  }
+  ca.att_first_batch = 0; ca.step_ptr = nullptr;
+  if (h->prec == CFB_BF16) {
+    CFB_TRY(mem_hat<bf16>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<bf16>(), ml.total_rows, h->d, st));
+    CFB_TRY(embed<bf16>(h, sample, n_batch, 1, st));
+    return run_layers<bf16>(h, n_batch, ca, att_out, nullptr, eps_out, st);
+  }
+  CFB_TRY(mem_hat<float>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<float>(), ml.total_rows, h->d, st));
+  CFB_TRY(embed<float>(h, sample, n_batch, 1, st));
+  return run_layers<float>(h, n_batch, ca, att_out, nullptr, eps_out, st);
+}
+
+int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem, int n_clips, int n_branch,
+               float* latents, const float* step_noise, const float* preseq, int preseq_len, float* record,
+               float* const att_out[CFB_N_STREAMS], int use_graph, cfb_stream stream) {
+  CFB_CHECK(h && sched && mem && latents && n_clips > 0, "cfb_sample: bad argument");
+  CFB_CHECK(n_branch == 6 || n_branch == CFB_N_BRANCH, "cfb_sample: n_branch must be 6 or 7");
+  CFB_CHECK(sched->n_steps > 0 && sched->timesteps && sched->coef, "cfb_sample: empty schedule");
+  CFB_CHECK(sched->kind == CFB_SCHED_DDIM || sched->kind == CFB_SCHED_DDPM, "cfb_sample: unknown scheduler kind");
+  CFB_CHECK(preseq == nullptr || (preseq_len > 0 && preseq_len <= h->ntok), "cfb_sample: bad preseq_len %d", preseq_len);
+  bool want_att = false;
+  if (att_out) for (int x = 0; x < CFB_N_STREAMS; ++x) want_att |= att_out[x] != nullptr;
+  CFB_CHECK(!want_att || n_branch == CFB_N_BRANCH, "cfb_sample: attention maps come from the full-cond branch; use n_branch=7");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = sched->n_steps, n_batch = n_clips * n_branch;
+  const int n_per_clip = h->ntok * h->lat;
+  CFB_TRY(reserve_rows(h, n_batch, n_clips));
+  CFB_TRY(h->tsteps.reserve((size_t)S * 4, &h->epoch));
+  CFB_TRY(h->coef.reserve((size_t)(S + 1) * 8 * 4, &h->epoch));
+  CFB_TRY(h->step.reserve(4, &h->epoch));
+  CFB_TRY(h->x.reserve((size_t)n_clips * n_per_clip * 4, &h->epoch));
+  std::vector<float> tf(S);
+  for (int i = 0; i < S; ++i) tf[i] = (float)sched->timesteps[i];
+  CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, tf.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  CFB_CUDA(cudaMemcpyAsync(h->coef.p, sched->coef, (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st));
+  CFB_CUDA(cudaMemsetAsync(h->coef.as<float>() + (size_t)S * 8, 0, 8 * 4, st));
+  CFB_CUDA(cudaMemsetAsync(h->step.p, 0, 4, st));
+  CFB_CUDA(cudaStreamSynchronize(st));   // tf is a host temporary
+  CFB_TRY(prep_time(h, S, st));
+  MemLayout ml; CrossArgs ca;
+  CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    ca.att_batch_stride[x] = (long long)h->L * h->ntok * mem->len[x];
+    ca.att_step_stride[x] = (long long)n_clips * ca.att_batch_stride[x];
+  }
+  ca.att_first_batch = (n_branch - 1) * n_clips;
+  ca.step_ptr = h->step.as<int>();
+  CFB_CUDA(cudaMemcpyAsync(h->x.p, latents, (size_t)n_clips * n_per_clip * 4, cudaMemcpyDeviceToDevice, st));
+  const int n_inpaint = preseq ? preseq_len * h->lat : 0;
+  if (preseq) {
+    CFB_TRY(h->preseq.reserve((size_t)n_clips * n_inpaint * 4, &h->epoch));
+    CFB_TRY(h->inp_noise.reserve((size_t)n_clips * n_inpaint * 4, &h->epoch));
+    CFB_CUDA(cudaMemcpyAsync(h->preseq.p, preseq, (size_t)n_clips * n_inpaint * 4, cudaMemcpyDeviceToDevice, st));
+    CFB_TRY(inpaint_first(h->x.as<float>(), h->preseq.as<float>(), h->inp_noise.as<float>(), h->coef.as<float>(),
+                          n_clips, n_per_clip, n_inpaint, st));
+  }
+  StepArgs sa{};
+  sa.eps = h->eps.as<float>(); sa.x = h->x.as<float>(); sa.noise = step_noise; sa.coef = h->coef.as<float>();
+  sa.step_ptr = h->step.as<int>(); sa.step_inc = h->step.as<int>(); sa.record = record;
+  sa.preseq = preseq ? h->preseq.as<float>() : nullptr; sa.inp_noise = h->inp_noise.as<float>();
+  sa.n_branch = n_branch; sa.n_clips = n_clips; sa.n_per_clip = n_per_clip; sa.n_inpaint = n_inpaint;
+  sa.n_steps = S; sa.kind = sched->kind; sa.clip_sample = sched->clip_sample; sa.guidance_scale = sched->guidance_scale;
+
+  auto body = [&]() {
+    return h->prec == CFB_BF16 ? step_body<bf16>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, st)
+                               : step_body<float>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, st);
+  };
+
+  if (use_graph) {
+    cfb_denoiser::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.epoch = h->epoch; key.n_clips = n_clips; key.n_branch = n_branch; key.n_steps = S; key.kind = sched->kind;
+    key.clip = sched->clip_sample; key.preseq_len = preseq ? preseq_len : 0; key.scale = sched->guidance_scale;
+    for (int x = 0; x < CFB_N_STREAMS; ++x) {
+      key.n_slots[x] = mem->n_slots[x]; key.len[x] = mem->len[x]; key.has_mask[x] = mem->mask[x] != nullptr;
+      key.att[x] = want_att ? att_out[x] : nullptr;
+    }
+    key.noise = step_noise; key.record = record;
+    if (!h->graph_valid || memcmp(&key, &h->graph_key, sizeof(key)) != 0) {
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+      h->graph_valid = false;
+      cudaGraph_t graph = nullptr;
+      CFB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const unsigned long long launches_before = g_launches;
+      int rc = body();
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      g_launches = launches_before;   // captured, not launched
+      if (rc != CFB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); return CFB_ERR_CUDA; }
+      size_t n_nodes = 0;
+      cudaGraphGetNodes(graph, nullptr, &n_nodes);
+      ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return CFB_ERR_CUDA; }
+      h->graph_key = key; h->graph_valid = true;
+      h->graph_nodes = n_nodes;
+    }
+    for (int i = 0; i < S; ++i) CFB_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    g_launches += (unsigned long long)S * h->graph_nodes;
+  } else {
+    for (int i = 0; i < S; ++i) CFB_TRY(body());
+  }
+  CFB_CUDA(cudaMemcpyAsync(latents, h->x.p, (size_t)n_clips * n_per_clip * 4, cudaMemcpyDeviceToDevice, st));
+  return CFB_OK;
+}
+
+}  // extern "C"

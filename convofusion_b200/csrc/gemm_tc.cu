@@ -1,0 +1,352 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  y[M,N] (+)= act(A[M,K] . W[N,K]^T + bias), bf16 operands,
+// fp32 accumulation in tensor memory.
+//
+// Both operands are K-major (activations row-major [M,K]; nn.Linear weights row-major [N,K]), the
+// canonical "TN" case: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128 x 64 and BN x 64 bf16
+// boxes into a STAGES-deep shared-memory ring; one elected thread issues tcgen05.mma
+// (cta_group::1, kind::f16, M=128, N=BN, K=16) into a 128-lane x BN-column fp32 TMEM accumulator;
+// four epilogue warps read it back with tcgen05.ld.32x32b (one accumulator row per thread) and
+// apply bias / activation / residual-accumulate before storing.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two CTAs fit per SM (<=113 KB smem,
+// BN<=256 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace cfb {
+
+namespace {
+
+constexpr int BM = 128;      // UMMA M (cta_group::1)
+constexpr int BK = 64;       // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
+// [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused when swizzled) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+// | [46,48) version=1 | [61,64) layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, int M, int N,
+                                                           int K, Epilogue ep) {
+  using S = Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + S::BAR_OFF;           // STAGES barriers
+  const uint32_t bar_empty = bar_full + STAGES * 8;      // STAGES barriers
+  const uint32_t bar_acc = bar_empty + STAGES * 8;       // accumulator ready
+  const uint32_t tmem_slot = bar_acc + 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + S::BAR_OFF + (2 * STAGES + 1) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + s * 8, ph ^ 1);
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
+        tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
+        tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (addr >> 4) field
+          umma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(bar_empty + s * 8);  // frees the smem slot once these MMAs retire
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ---- epilogue: thread owns accumulator row (lane quarter q, lane)
+    const int q = warp & 3;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int r = m0 + q * 32 + lane;
+    const bool row_ok = r < M;
+    const float* brow = (ep.bias && row_ok) ? ep.bias + (size_t)(r % ep.bias_period) * N : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int n = n0 + c * 32;
+      if (!row_ok || n >= N) continue;
+      if (brow) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(brow + n + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+      if (ep.act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], ep.act);
+      }
+      for (int rep = 0; rep < ep.replicate; ++rep) {
+        const size_t off = (size_t)rep * ep.rep_stride + (size_t)r * ep.ldo + n;
+        if (ep.out_bf16) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j * 8 + 0], v[j * 8 + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j * 8 + 2], v[j * 8 + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j * 8 + 4], v[j * 8 + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j * 8 + 6], v[j * 8 + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            o[j] = pk;
+          }
+        } else {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            if (ep.accumulate) {
+              const float4 y = o[j];
+              x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+            }
+            o[j] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* p; int rows, cols, ld, box_rows;
+  bool operator==(const MapKey& o) const {
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.p);
+    h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
+    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)k.box_rows;
+    return h;
+  }
+};
+
+// Descriptors are pure functions of (pointer, shape), so they are cached for the process lifetime.
+int get_map(const bf16* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{p, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return CFB_OK; }
+  EncodeTiledFn enc = get_encode();
+  CFB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap tm;
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(p), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%d cols=%d ld=%d box=%d", (int)r, (const void*)p,
+              rows, cols, ld, box_rows);
+    return CFB_ERR_CUDA;
+  }
+  cache.emplace(key, tm);
+  *out = tm;
+  return CFB_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+  using S = Smem<BN, STAGES>;
+  CUtensorMap ta, tb;
+  CFB_TRY(get_map(A, M, K, lda, BM, &ta));
+  CFB_TRY(get_map(W, N, K, ldw, BN, &tb));
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+}  // namespace
+
+int init_gemm_tc_kernels() {
+  static bool done = false;
+  if (done) return CFB_OK;
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  done = true;
+  return CFB_OK;
+}
+
+bool gemm_tc_supported(int M, int N, int K, int lda, int ldw) {
+  return M > 0 && K >= BK && K % BK == 0 && N % 32 == 0 && lda % 8 == 0 && ldw % 8 == 0;
+}
+
+int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep_in,
+            cudaStream_t st) {
+  CFB_CHECK(gemm_tc_supported(M, N, K, lda, ldw), "gemm_tc: unsupported shape %dx%dx%d", M, N, K);
+  CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_tc: operands must be 16-byte aligned");
+  Epilogue ep = ep_in;
+  if (ep.replicate < 1) ep.replicate = 1;
+  if (ep.bias_period < 1) ep.bias_period = 1;
+  CFB_CHECK(!(ep.accumulate && ep.out_bf16), "gemm: accumulate needs float output");
+  CFB_CHECK(ep.ldo % 8 == 0 && ((uintptr_t)ep.out % 16 == 0) && (ep.rep_stride % 8 == 0),
+            "gemm_tc: output must be 16-byte aligned with ldo %% 8 == 0");
+  CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
+  if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, M, N, K, ep, st);
+  if (N % 64 == 0) return launch<64, 4>(A, lda, W, ldw, M, N, K, ep, st);
+  return launch<32, 4>(A, lda, W, ldw, M, N, K, ep, st);
+}
+
+}  // namespace cfb

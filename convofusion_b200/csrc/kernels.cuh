@@ -1,0 +1,63 @@
+// Internal launcher declarations (definitions in rowops.cu / attention.cu / sched.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cfb {
+
+// ---- rowops.cu
+template <typename T>
+int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
+            long long mod_step_stride, T* out, int rows, int d, cudaStream_t st);
+int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_STREAMS], const int len[CFB_N_STREAMS],
+              const float* stream_emb, const float* pe, float* mem_c, int d, cudaStream_t st);
+template <typename T>
+int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st);
+int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st);
+template <typename T> int cast_rows(const float* in, T* out, long long n, cudaStream_t st);
+template <typename T> int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st);
+template <typename T> int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d, cudaStream_t st);
+int mask_frames(float* out, const int* lengths, int n_batch, int L, int d, cudaStream_t st);
+
+// ---- attention.cu
+// Generic MHA core on projected q/k/v (rows sample-major): softmax(q k^T / sqrt(hd) + pad) v.
+template <typename T>
+int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, int n, int Lq, int Lk, int n_heads,
+        int head_dim, const int* kv_len, cudaStream_t st);
+
+// The denoiser's five folded single-head cross-attentions for every (batch entry, stream):
+//   P = softmax(qx[bs, x] . mem_hat[slot]^T + mask),  u[bs, x] = P . mem_hat[slot]
+struct CrossArgs {
+  int row_base[CFB_N_STREAMS];          // first mem_hat row of stream x
+  int len[CFB_N_STREAMS];
+  const int* slot[CFB_N_STREAMS];       // [n_batch] or nullptr (identity)
+  const uint8_t* mask[CFB_N_STREAMS];   // [n_slots, len] or nullptr
+  float* att[CFB_N_STREAMS];            // attention-map output for this layer or nullptr
+  long long att_batch_stride[CFB_N_STREAMS];  // elements between consecutive batch entries
+  int att_first_batch;                  // maps are written for batch entries >= this
+  long long att_step_stride[CFB_N_STREAMS];   // added per *step_ptr (graph replay)
+  const int* step_ptr;
+};
+template <typename T>
+int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,
+                    cudaStream_t st);
+
+// ---- sched.cu
+struct StepArgs {
+  const float* eps;        // [n_branch, B, n]
+  float* x;                // [B, n] latents, updated in place
+  const float* noise;      // [n_steps?, B, n] or nullptr
+  const float* coef;       // device [n_steps, 8]
+  const int* step_ptr;     // device step counter (nullptr = row 0)
+  int* step_inc;           // if set, incremented by one after the update (graph replay)
+  float* record;           // [n_steps, B, n] or nullptr
+  const float* preseq;     // [B, pl*lat] inpainting source or nullptr
+  const float* inp_noise;  // [B, pl*lat]
+  int n_branch, n_clips, n_per_clip, n_inpaint, n_steps, kind, clip_sample;
+  float guidance_scale;
+};
+int guidance_sched_step(const StepArgs& a, cudaStream_t st);
+// Step-0 inpainting incl. the reference's aliasing quirk (unbounded_synthesis.py:66-76).
+int inpaint_first(float* x, const float* preseq, float* inp_noise, const float* coef, int n_clips, int n_per_clip,
+                  int n_inpaint, cudaStream_t st);
+
+}  // namespace cfb

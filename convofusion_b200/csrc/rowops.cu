@@ -1,0 +1,269 @@
+// Row-wise memory-bound kernels: LayerNorm (+ TimeBlock modulation + SiLU) producing the next GEMM's
+// A operand, conditioning-memory construction / per-step normalisation, timestep sinusoid, casts.
+// One warp owns one row of D floats (D = 512 denoiser, 128 VAE): 128-bit loads, statistics by warp
+// shuffle, two-pass variance (mean first, then sum of squared deviations) like ATen's LayerNorm.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cfb {
+
+namespace {
+
+constexpr float LN_EPS = 1e-5f;
+
+template <int D>
+struct RowVec {
+  static constexpr int PER_LANE = D / 32;  // 16 (D=512) or 4 (D=128)
+  static constexpr int NV = PER_LANE / 4;
+  float v[PER_LANE];
+  // lane owns columns {i*128 + lane*4 .. +3} for i in [0, NV): coalesced float4 accesses
+  __device__ __forceinline__ void load(const float* __restrict__ row, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 t = *reinterpret_cast<const float4*>(row + i * 128 + lane * 4);
+      v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ void add(const float* __restrict__ row, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 t = *reinterpret_cast<const float4*>(row + i * 128 + lane * 4);
+      v[i * 4] += t.x; v[i * 4 + 1] += t.y; v[i * 4 + 2] += t.z; v[i * 4 + 3] += t.w;
+    }
+  }
+  __device__ __forceinline__ void normalize() {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) s += v[i];
+    const float mu = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) { v[i] -= mu; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) v[i] *= rstd;
+  }
+  __device__ __forceinline__ void affine(const float* __restrict__ g, const float* __restrict__ b, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 gg = *reinterpret_cast<const float4*>(g + i * 128 + lane * 4);
+      float4 bb = *reinterpret_cast<const float4*>(b + i * 128 + lane * 4);
+      v[i * 4] = v[i * 4] * gg.x + bb.x; v[i * 4 + 1] = v[i * 4 + 1] * gg.y + bb.y;
+      v[i * 4 + 2] = v[i * 4 + 2] * gg.z + bb.z; v[i * 4 + 3] = v[i * 4 + 3] * gg.w + bb.w;
+    }
+  }
+  template <typename T>
+  __device__ __forceinline__ void store(T* __restrict__ row, int lane) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(row + i * 128 + lane * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+      } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[i * 4], v[i * 4 + 1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[i * 4 + 2], v[i * 4 + 3]);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(row + i * 128 + lane * 4) = pk;
+      }
+    }
+  }
+};
+
+// out = LN(x) * g + b  [ * (1 + scale) + shift -> SiLU ]           (cross_attention.py:437-438)
+template <typename T, int D>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                      const float* __restrict__ b, const float* __restrict__ mod,
+                                                      const int* __restrict__ step_ptr, long long mod_step_stride,
+                                                      T* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  RowVec<D> r;
+  r.load(x + (size_t)row * D, lane);
+  r.normalize();
+  r.affine(g, b, lane);
+  if (mod) {
+    const float* m = mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0);
+#pragma unroll
+    for (int i = 0; i < RowVec<D>::NV; ++i) {
+      float4 sc = *reinterpret_cast<const float4*>(m + i * 128 + lane * 4);
+      float4 sh = *reinterpret_cast<const float4*>(m + D + i * 128 + lane * 4);
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.v[i * 4 + j] = act_apply(r.v[i * 4 + j] * (1.0f + scv[j]) + shv[j], CFB_ACT_SILU);
+    }
+  }
+  r.store(out + (size_t)row * D, lane);
+}
+
+// mem_c[row] = cond[row] + stream_emb[x] + pe[pos]          (denoiser.py:332-353, time-independent part)
+struct MemBuildArgs {
+  const float* cond[CFB_N_STREAMS];
+  int row_base[CFB_N_STREAMS + 1];  // first global row of each stream
+  int len[CFB_N_STREAMS];
+};
+template <int D>
+__global__ void __launch_bounds__(256) mem_build_kernel(MemBuildArgs a, const float* __restrict__ stream_emb,
+                                                        const float* __restrict__ pe, float* __restrict__ mem_c) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.row_base[CFB_N_STREAMS]) return;
+  int x = 0;
+#pragma unroll
+  for (int i = 1; i < CFB_N_STREAMS; ++i) x += (row >= a.row_base[i]);
+  const int local = row - a.row_base[x];
+  const int pos = local % a.len[x];
+  RowVec<D> r;
+  r.load(a.cond[x] + (size_t)local * D, lane);
+  r.add(stream_emb + (size_t)x * D, lane);
+  r.add(pe + (size_t)pos * D, lane);
+  r.store(mem_c + (size_t)row * D, lane);
+}
+
+// mem_hat[row] = (mem_c[row] + temb - mean) * rstd : the affine-free LayerNorm every layer's
+// {stream}_norm shares (denoiser.py:255-261 + cross_attention.py:581-585; gamma/beta live in w_qx/w_fu).
+template <typename T, int D>
+__global__ void __launch_bounds__(256) mem_hat_kernel(const float* __restrict__ mem_c, const float* __restrict__ temb,
+                                                      const int* __restrict__ step_ptr, T* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  RowVec<D> r;
+  r.load(mem_c + (size_t)row * D, lane);
+  r.add(temb + (step_ptr ? (size_t)(*step_ptr) * D : 0), lane);
+  r.normalize();
+  r.store(out + (size_t)row * D, lane);
+}
+
+// embeddings.py:245-285 with flip_sin_to_cos=True, freq_shift=0: [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k / half)
+__global__ void time_sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= n * half) return;
+  const int row = i / half, k = i % half;
+  const float exponent = (-9.210340371976184f * (float)k) / (float)half;  // -ln(10000) * k / half, float like torch
+  const float e = t[row] * expf(exponent);
+  out[(size_t)row * dim + k] = cosf(e);
+  out[(size_t)row * dim + half + k] = sinf(e);
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<T>(in[i]);
+}
+
+// out[r, 0:d] = a[r], out[r, d:2d] = b[r]                   (cross_attention.py:114 torch.cat([x, xs.pop()]))
+template <typename T>
+__global__ void concat2_kernel(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ out,
+                               int rows, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * 2 * d) return;
+  const int r = (int)(i / (2 * d)), c = (int)(i % (2 * d));
+  out[i] = from_f32<T>(c < d ? a[(size_t)r * d + c] : b[(size_t)r * d + c - d]);
+}
+
+// rows [B*L, D]: out[b, l] = pe[l] (+ src[b, l])           (vae.py:277,321-322)
+template <typename T>
+__global__ void add_pe_kernel(const float* __restrict__ src, const float* __restrict__ pe, T* __restrict__ out,
+                              int n_batch, int L, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_batch * L * d) return;
+  const int c = (int)(i % d);
+  const int l = (int)((i / d) % L);
+  const float v = pe[(size_t)l * d + c] + (src ? src[i] : 0.f);
+  out[i] = from_f32<T>(v);
+}
+
+// vae.py:362: zero frames at or beyond each clip's length.
+__global__ void mask_frames_kernel(float* __restrict__ out, const int* __restrict__ lengths, int n_batch, int L, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_batch * L * d) return;
+  const int l = (int)((i / d) % L), b = (int)(i / ((long long)d * L));
+  if (l >= lengths[b]) out[i] = 0.f;
+}
+
+}  // namespace
+
+template <typename T>
+int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
+            long long mod_step_stride, T* out, int rows, int d, cudaStream_t st) {
+  if (rows <= 0) return CFB_OK;
+  dim3 grid(ceil_div(rows, 8));
+  if (d == 512) ln_rows_kernel<T, 512><<<grid, 256, 0, st>>>(x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+  else if (d == 128) ln_rows_kernel<T, 128><<<grid, 256, 0, st>>>(x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+  else { set_error("ln_rows: d_model %d unsupported (128 or 512)", d); return CFB_ERR_INVALID; }
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+template int ln_rows<float>(const float*, const float*, const float*, const float*, const int*, long long, float*, int, int, cudaStream_t);
+template int ln_rows<bf16>(const float*, const float*, const float*, const float*, const int*, long long, bf16*, int, int, cudaStream_t);
+
+int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_STREAMS], const int len[CFB_N_STREAMS],
+              const float* stream_emb, const float* pe, float* mem_c, int d, cudaStream_t st) {
+  CFB_CHECK(d == 512, "mem_build: d_model %d unsupported", d);
+  MemBuildArgs a;
+  int base = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    a.cond[x] = cond[x]; a.row_base[x] = base; a.len[x] = len[x] > 0 ? len[x] : 1;
+    base += n_slots[x] * len[x];
+  }
+  a.row_base[CFB_N_STREAMS] = base;
+  if (base == 0) return CFB_OK;
+  mem_build_kernel<512><<<ceil_div(base, 8), 256, 0, st>>>(a, stream_emb, pe, mem_c);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+template <typename T>
+int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st) {
+  CFB_CHECK(d == 512, "mem_hat: d_model %d unsupported", d);
+  if (rows <= 0) return CFB_OK;
+  mem_hat_kernel<T, 512><<<ceil_div(rows, 8), 256, 0, st>>>(mem_c, temb, step_ptr, out, rows);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+template int mem_hat<float>(const float*, const float*, const int*, float*, int, int, cudaStream_t);
+template int mem_hat<bf16>(const float*, const float*, const int*, bf16*, int, int, cudaStream_t);
+
+int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st) {
+  const int total = n * (dim / 2);
+  time_sinusoid_kernel<<<ceil_div(total, 256), 256, 0, st>>>(t, out, n, dim);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+template <typename T>
+int cast_rows(const float* in, T* out, long long n, cudaStream_t st) {
+  if (n <= 0) return CFB_OK;
+  cast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+template int cast_rows<float>(const float*, float*, long long, cudaStream_t);
+template int cast_rows<bf16>(const float*, bf16*, long long, cudaStream_t);
+
+template <typename T>
+int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st) {
+  const long long n = (long long)rows * 2 * d;
+  concat2_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, out, rows, d);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+template int concat2<float>(const float*, const float*, float*, int, int, cudaStream_t);
+template int concat2<bf16>(const float*, const float*, bf16*, int, int, cudaStream_t);
+
+template <typename T>
+int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d, cudaStream_t st) {
+  const long long n = (long long)n_batch * L * d;
+  add_pe_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, pe, out, n_batch, L, d);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+template int add_pe<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
+template int add_pe<bf16>(const float*, const float*, bf16*, int, int, int, cudaStream_t);
+
+int mask_frames(float* out, const int* lengths, int n_batch, int L, int d, cudaStream_t st) {
+  const long long n = (long long)n_batch * L * d;
+  mask_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, lengths, n_batch, L, d);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+}  // namespace cfb

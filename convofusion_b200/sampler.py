@@ -1,0 +1,185 @@
+"""Sampling orchestration: the reference's test_diffusion_forward / _diffusion_reverse /
+diffusion_reverse_forecast / process_samples call chain (convofusion.py:817-1065, 391-549;
+unbounded_synthesis.py:28-187, 244-512) for synthetic, already-featurised inputs, with WEG off.
+
+`ConvoFusionSampler` holds the same sub-module names as the reference LightningModule (`denoiser`, `vae`,
+`text_audio_encoder`, `condition_fuser`), so `load_state_dict(ckpt["state_dict"])` accepts a reference
+checkpoint (its T5 body is stripped on save, base.py:83-104).
+"""
+from __future__ import annotations
+
+import inspect
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .conditioning import (TextAudioController, TextAudioMotionFuser, expand_guidance_batch, guidance_memory,
+                           guidance_slots)
+from .modules import ConvoFusionVae, Denoiser
+from .schedulers import DDIMScheduler, DDPMScheduler
+
+MOTION_FPS = 25.0        # configs/config_cf_beatdnd.yaml:78-87
+WINDOW_FRAMES = 128
+
+
+class Ablation:
+    """Attribute bag standing in for cfg.TRAIN.ABLATION (configs/config_cf_beatdnd.yaml:41-48)."""
+    SKIP_CONNECT = True
+    VAE_TYPE = "convofusion"
+    PE_TYPE = "convofusion"
+    DIFF_PE_TYPE = "convofusion"
+    MLP_DIST = False
+    CAUSAL_ATTN = False
+
+
+def default_denoiser(precision: str = "bf16") -> Denoiser:
+    """configs/modules/denoiser.yaml at config_cf_beatdnd."""
+    return Denoiser(ablation=Ablation(), nfeats=189, condition="text+audio", latent_dim=[1, 128], ff_size=1024,
+                    num_layers=9, num_heads=4, dropout=0.1, normalize_before=True, activation="gelu",
+                    flip_sin_to_cos=True, return_intermediate_dec=False, position_embedding="sine", arch="trans_dec",
+                    freq_shift=0, guidance_scale=7.5, guidance_uncondp=0.1, text_encoded_dim=512,
+                    audio_encoded_dim=512, nclasses=10, precision=precision)
+
+
+def default_vae(precision: str = "bf16") -> ConvoFusionVae:
+    """configs/modules/motion_vae.yaml at config_cf_beatdnd."""
+    return ConvoFusionVae(ablation=Ablation(), nfeats=189, latent_dim=[1, 128], ff_size=1024, num_layers=5, num_heads=2,
+                          dropout=0.1, arch="encoder_decoder", normalize_before=True, activation="gelu",
+                          position_embedding="sine", laplace_kernel_size=5, precision=precision)
+
+
+def default_scheduler(kind: str = "ddim"):
+    """configs/modules/scheduler.yaml params; DDIM is the 50-step override BASELINE.json names."""
+    kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=True)
+    return DDIMScheduler(**kw) if kind == "ddim" else DDPMScheduler(variance_type="fixed_small", **kw)
+
+
+class ConvoFusionSampler(nn.Module):
+    def __init__(self, denoiser: Optional[Denoiser] = None, vae: Optional[ConvoFusionVae] = None, scheduler=None,
+                 noise_scheduler=None, guidance_scale: float = 7.5, num_inference_timesteps: int = 50,
+                 eta: float = 0.0, precision: str = "bf16"):
+        super().__init__()
+        self.denoiser = denoiser if denoiser is not None else default_denoiser(precision)
+        self.vae = vae if vae is not None else default_vae(precision)
+        self.text_audio_encoder = TextAudioController(512)
+        self.condition_fuser = TextAudioMotionFuser(512, self.denoiser.latent_dim)
+        self.scheduler = scheduler if scheduler is not None else default_scheduler("ddim")
+        self.noise_scheduler = noise_scheduler if noise_scheduler is not None else default_scheduler("ddpm")
+        self.guidance_scale = guidance_scale
+        self.num_inference_timesteps = num_inference_timesteps
+        self.eta = eta
+        self.clf_guidance_drops = 6                              # convofusion.py:60
+        self.do_classifier_free_guidance = guidance_scale > 1.0   # convofusion.py:131
+        self.latent_dim = [1, self.denoiser.latent_dim]
+
+    def set_precision(self, precision: str):
+        self.denoiser.set_precision(precision)
+        self.vae.set_precision(precision)
+        return self
+
+    # ------------------------------------------------------------------ conditioning
+    def encode_conditions(self, clip: Dict[str, Tensor], uncond_text: Tensor, uncond_text_attn: Tensor):
+        """convofusion.py:909-973, de-duplicated: (enc 5 x [1+B, M_x, 512], masks)."""
+        return guidance_memory(self.text_audio_encoder, self.condition_fuser, clip, uncond_text, uncond_text_attn)
+
+    # ------------------------------------------------------------------ reverse loops
+    def _diffusion_reverse(self, encoder_hidden_states, lengths=None, cond_masks=dict(), focus_indices=[],
+                           init_latents: Optional[Tensor] = None, step_noise: Optional[Tensor] = None):
+        """The reference's as-written loop (convofusion.py:391-549): one Denoiser.forward on the 7*B batch and one
+        scheduler.step per timestep, attention maps kept per step.  Same arithmetic as `sample()`, ~140 launches and
+        two host syncs per step; kept for drop-in parity with callers that pass a pre-expanded 7*B batch."""
+        if len(focus_indices) > 0:
+            raise NotImplementedError("word-excitation guidance needs autograd through the denoiser (SURVEY 8f rank 2)")
+        dev = encoder_hidden_states[0].device
+        mult = self.clf_guidance_drops + 1
+        bsz = encoder_hidden_states[0].shape[0] // mult
+        latents = init_latents if init_latents is not None else torch.randn(
+            (bsz, 16, self.latent_dim[-1]), device=dev, dtype=torch.float)
+        latents = latents * self.scheduler.init_noise_sigma
+        self.scheduler.set_timesteps(self.num_inference_timesteps)
+        timesteps = self.scheduler.timesteps.to(dev)
+        extra = {}
+        if "eta" in set(inspect.signature(self.scheduler.step).parameters.keys()):
+            extra["eta"] = self.eta
+        attention_matrices = dict()
+        for i, t in enumerate(timesteps):
+            x = torch.cat([latents] * mult)
+            noise_pred, att_mats = self.denoiser(sample=x, timestep=t, encoder_hidden_states=encoder_hidden_states,
+                                                 lengths=None, mem_mask_dict=cond_masks)
+            attention_matrices[t.item()] = [a.chunk(mult)[-1] for a in att_mats]
+            noise_pred = self._combine(noise_pred)
+            if step_noise is not None:
+                extra["variance_noise"] = step_noise[i]
+            latents = self.scheduler.step(noise_pred, t, latents, **extra).prev_sample
+        return latents.permute(1, 0, 2), attention_matrices
+
+    def _combine(self, noise_pred: Tensor) -> Tensor:
+        # convofusion.py:527-541 through the fused kernel with identity scheduler coefficients:
+        # x0 = (0 - (-1)*eps)/1, prev = 1*x0 + 0*eps.
+        import ctypes as C
+        from . import _lib
+        mult = self.clf_guidance_drops + 1
+        eps = noise_pred.detach().to(torch.float32).contiguous()
+        B = eps.shape[0] // mult
+        out = torch.zeros(B, *eps.shape[1:], device=eps.device)
+        coef = torch.tensor([-1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0], device=eps.device)
+        with torch.cuda.device(eps.device):
+            _lib.check(_lib.lib().cfb_guidance_sched_step(eps.data_ptr(), out.data_ptr(), 0, coef.data_ptr(), mult, B,
+                                                          out.numel() // B, _lib.SCHED_DDIM, 0,
+                                                          float(self.guidance_scale), _lib.stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def sample(self, enc: Sequence[Tensor], masks: Dict[str, Optional[Tensor]], n_clips: int,
+               init_latents: Tensor, preseq: Optional[Tensor] = None, step_noise: Optional[Tensor] = None,
+               record: bool = False, return_attention: bool = False, use_graph: bool = True):
+        """Fused path: the whole reverse loop in one C call.  enc/masks are the de-duplicated slots from
+        `encode_conditions`.  Returns (z [16,B,128] like _diffusion_reverse, record, attention)."""
+        n_branch = 7 if return_attention else 6      # the full-cond branch has guidance weight 0 (convofusion.py:539)
+        slots = guidance_slots(n_clips, n_branch, init_latents.device)
+        x = init_latents * self.scheduler.init_noise_sigma
+        lat, rec, att = self.denoiser.sample(self.scheduler, enc, masks, slots, x, self.num_inference_timesteps,
+                                             guidance_scale=self.guidance_scale, eta=self.eta, n_branch=n_branch,
+                                             step_noise=step_noise, preseq=preseq, noise_scheduler=self.noise_scheduler,
+                                             record=record, return_attention=return_attention, use_graph=use_graph)
+        return lat.permute(1, 0, 2), rec, att
+
+    # ------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def decode(self, z: Tensor, lengths: List[int]) -> Tensor:
+        """convofusion.py:1027-1032: z [16,B,128] -> joints [B,T,189]."""
+        ntok, bs, dim = z.shape
+        zz = z.reshape(ntok // 2, 2, bs, dim).permute(1, 2, 0, 3)
+        return self.vae.decode(zz, lengths)
+
+    @torch.no_grad()
+    def generate(self, clip: Dict[str, Tensor], uncond_text: Tensor, uncond_text_attn: Tensor, lengths: List[int],
+                 init_latents: Tensor, **kw):
+        """test_diffusion_forward (convofusion.py:817-1036) for one batch of featurised clips."""
+        enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
+        z, rec, att = self.sample(enc, masks, init_latents.shape[0], init_latents, **kw)
+        return {"m_rst": self.decode(z, lengths), "lat_t": z, "record": rec, "test_attention_maps": att}
+
+    # ------------------------------------------------------------------ unbounded synthesis
+    @torch.no_grad()
+    def synthesize_unbounded(self, windows: Sequence[Dict[str, Tensor]], uncond_text: Tensor, uncond_text_attn: Tensor,
+                             init_noise: Sequence[Tensor], use_graph: bool = True):
+        """process_samples (unbounded_synthesis.py:244-512): serial windows at 50 % overlap; the last 8 latent tokens
+        of window k are inpainted into the first 8 of window k+1 (:442-444, 70-76) and the root x/z of every decoded
+        window is re-anchored on the previous one (:461-465).  `windows[k]` is the featurised conditioning of
+        window k for all B streams; returns the list of per-window joints [B,128,189]."""
+        preseq, prev, outs = None, None, []
+        for k, clip in enumerate(windows):
+            B = clip["mel_lsn"].shape[0]
+            enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
+            z, _, _ = self.sample(enc, masks, B, init_noise[k], preseq=preseq, use_graph=use_graph)
+            preseq = z[z.shape[0] // 2:].permute(1, 0, 2).contiguous()
+            feats = self.decode(z, [WINDOW_FRAMES] * B)
+            if prev is not None:
+                xz = torch.tensor([1.0, 0.0, 1.0], device=feats.device)
+                feats[:, :, :3] = feats[:, :, :3] - feats[:, :1, :3] * xz
+                feats[:, :, :3] = feats[:, :, :3] + prev[:, :1, :3] * xz
+            outs.append(feats)
+            prev = feats[:, WINDOW_FRAMES // 2:, :]
+        return outs

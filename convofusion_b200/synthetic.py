@@ -1,0 +1,67 @@
+"""Seeded synthetic weights and inputs: there is no network for checkpoints or data, so
+tests, goldens and the benchmark all draw from these generators.  Pure torch-CPU RNG -> reproducible on any box
+with the same torch build."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+from torch import nn
+
+
+@torch.no_grad()
+def randomize_(module: nn.Module, seed: int = 1234) -> nn.Module:
+    """Deterministic non-degenerate init: every layer distinct, biases and LayerNorm affine non-trivial (the
+    reference's deepcopy-cloned layers start identical, which would hide layer-indexing bugs)."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in module.named_parameters():
+        leaf = name.split(".")[-1]
+        is_norm = "norm" in name.split(".")[-2] if "." in name else False
+        if p.dim() >= 2 and "embedding" not in name and "emb." not in name and "token" not in name:
+            fan_in = p.shape[-1]
+            v = torch.randn(p.shape, generator=g) / fan_in ** 0.5
+        elif is_norm and leaf == "weight":
+            v = 1.0 + 0.1 * torch.randn(p.shape, generator=g)
+        elif is_norm and leaf == "bias":
+            v = 0.1 * torch.randn(p.shape, generator=g)
+        elif leaf == "bias" or leaf == "in_proj_bias":
+            v = 0.05 * torch.randn(p.shape, generator=g)
+        elif name == "cond_params":
+            v = torch.full(p.shape, 0.2)
+        else:   # embedding tables, global motion tokens
+            v = 0.5 * torch.randn(p.shape, generator=g)
+        p.copy_(v.to(p.dtype))
+    return module
+
+
+def synthetic_clip(n_clips: int, seed: int = 1234, dyadic: bool = False, text_len: int = 32, n_mel_frames: int = 161
+                   ) -> Dict[str, object]:
+    """One batch of featurised clips at BEAT shapes.  Text is the T5 last hidden state."""
+    g = torch.Generator().manual_seed(seed)
+    B, Lt = n_clips, text_len
+    clip = {
+        "mel_lsn": torch.rand(B, n_mel_frames, 80, generator=g) * 80.0 - 80.0,
+        "text_lsn": torch.randn(B, Lt, 768, generator=g),
+        "apb": torch.randint(0, 2, (B, 8), generator=g),
+        "lsn_id": [int(v) for v in torch.randint(1, 36, (B,), generator=g)],
+    }
+    lsn_valid = torch.randint(12, Lt + 1, (B,), generator=g) if B > 1 else torch.tensor([20])
+    clip["text_lsn_attn"] = (torch.arange(Lt)[None, :] < lsn_valid[:, None]).long()
+    uncond_text = torch.randn(Lt, 768, generator=g)
+    uncond_attn = (torch.arange(Lt) < 4).long()
+    if dyadic:   # DnD: the speaker's transcript is real
+        clip["text_spk"] = torch.randn(B, Lt, 768, generator=g)
+        spk_valid = torch.randint(8, Lt + 1, (B,), generator=g)
+        clip["text_spk_attn"] = (torch.arange(Lt)[None, :] < spk_valid[:, None]).long()
+    else:        # monadic BEAT: speaker stream is the unconditional prompt (dataset.py:185-199)
+        clip["text_spk"] = uncond_text.unsqueeze(0).repeat(B, 1, 1)
+        clip["text_spk_attn"] = uncond_attn.unsqueeze(0).repeat(B, 1)
+    return {"clip": clip, "uncond_text": uncond_text, "uncond_text_attn": uncond_attn}
+
+
+def to_device(obj, device):
+    if torch.is_tensor(obj):
+        return obj.to(device)
+    if isinstance(obj, dict):
+        return {k: to_device(v, device) for k, v in obj.items()}
+    return obj

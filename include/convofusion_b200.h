@@ -1,0 +1,211 @@
+/*
+ * convofusion_b200 -- C ABI of the B200-native ConvoFusion sampling hot path.
+ *
+ * The reference (m-hamza-mughal/convofusion) has no FFI: its extension point is the
+ * `target:` string registry (convofusion/config.py:16-31) plus duck-typed calls on the
+ * instantiated Python objects.  This header is therefore the boundary a maintainer
+ * binds with ctypes; every entry point cites the reference
+ * call it replaces.  Plain pointers and sizes only: all pointers are DEVICE pointers
+ * unless a parameter is documented "host".  All functions return 0 on success, a
+ * negative cfb_status otherwise; cfb_last_error() gives the message (thread local).
+ *
+ * Ownership: the caller owns every buffer it passes in (weights must stay alive and
+ * unchanged for the lifetime of the handle that was created from them); handles own
+ * their workspace, TMA descriptors and CUDA graphs.  One handle per (device, stream
+ * of use); handles are not thread-safe.
+ */
+#ifndef CONVOFUSION_B200_H
+#define CONVOFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFB_ABI_VERSION 1
+#define CFB_N_STREAMS 5      /* spkemb, alsn, tlsn, apb, lsnemb: cross_attention.py:579 */
+#define CFB_N_BRANCH 7       /* clf_guidance_drops + 1: convofusion.py:60,399-401 */
+
+typedef enum {
+  CFB_OK = 0,
+  CFB_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  CFB_ERR_CUDA = -2,         /* CUDA runtime or driver error */
+  CFB_ERR_NO_DEVICE = -3,    /* no sm_100 device: there is no CPU fallback */
+  CFB_ERR_INTERNAL = -4
+} cfb_status;
+
+typedef enum { CFB_F32 = 0, CFB_BF16 = 1 } cfb_precision;
+typedef enum { CFB_GEMM_AUTO = 0, CFB_GEMM_SIMT = 1, CFB_GEMM_TCGEN05 = 2 } cfb_gemm_backend;
+typedef enum { CFB_ACT_NONE = 0, CFB_ACT_GELU = 1, CFB_ACT_SILU = 2, CFB_ACT_RELU = 3,
+               CFB_ACT_LEAKY01 = 4 } cfb_act;
+typedef enum { CFB_SCHED_DDIM = 0, CFB_SCHED_DDPM = 1 } cfb_sched_kind;
+
+typedef void* cfb_stream;    /* cudaStream_t */
+
+int cfb_abi_version(void);
+const char* cfb_last_error(void);
+/* Which GEMM engine bf16 contractions use (AUTO = tcgen05 whenever the shape allows). */
+int cfb_set_gemm_backend(int backend);
+/* Kernels launched by this library since process start (bench.py's gpu_launches). */
+unsigned long long cfb_launch_count(void);
+
+/* ------------------------------------------------------------------ denoiser ----- */
+/* Replaces Denoiser.forward (convofusion/models/architectures/denoiser.py:173-386) and the
+ * 9 x TransformerDecoderLayer2Att.forward_pre it drives (operator/cross_attention.py:556-664).
+ * Weights arrive PACKED by the host (convofusion_b200/pack.py): matrices are row-major
+ * [out, in] in the handle's precision (float or bf16); biases / LayerNorm params float.
+ * The five cross-attentions are algebraically folded (DESIGN.md "Folded cross-attention"):
+ *   w_qx  [5*d, d]  = stack_x (W_k,x diag(gamma_x))^T W_q,x / sqrt(d)
+ *   w_fu  [d, 5*d]  = cat_x  F_x O_x W_v,x diag(gamma_x)
+ */
+typedef struct {
+  const float *ln1_g, *ln1_b;                 /* norm1 */
+  const void  *w_in;  const float *b_in;      /* self_attn.in_proj   [3d, d] */
+  const void  *w_so;  const float *b_so;      /* self_attn.out_proj  [d, d]  */
+  const float *tb1_g, *tb1_b;                 /* time_block1.norm */
+  const void  *w_tb1; const float *b_tb1;     /* time_block1.out_layers.2 [d, d] */
+  const float *ln2_g, *ln2_b;                 /* norm2 */
+  const void  *w_qx;  const float *b_qx;      /* folded query/key projection [5d, d] */
+  const void  *w_fu;  const float *b_fu;      /* folded value/out/fuser      [d, 5d] */
+  const float *tb2_g, *tb2_b;
+  const void  *w_tb2; const float *b_tb2;
+  const float *ln3_g, *ln3_b;                 /* norm3 */
+  const void  *w_ff1; const float *b_ff1;     /* linear1 [ff, d] */
+  const void  *w_ff2; const float *b_ff2;     /* linear2 [d, ff] */
+} cfb_denoiser_layer;
+
+typedef struct {
+  int32_t d_model, latent_dim, n_tokens, n_layers, n_heads, ff_size, precision, pe_len;
+  const void  *w_embed;                       /* latent_embd.weight [d, latent] */
+  const float *tok_bias;                      /* [n_tokens, d] = latent_embd.bias + bh_embedding[tok%2] + query_pos.pe[tok/2] */
+  const float *w_t1, *b_t1, *w_t2, *b_t2;     /* time_embedding.linear_{1,2} (always float) */
+  const float *w_tbmod, *b_tbmod;             /* [n_layers*2*2d, d]: time_block{1,2}.emb_layers.1 stacked */
+  const float *stream_emb;                    /* condition_embedding.weight [5, d] */
+  const float *pe_mem;                        /* mem_pos.pe [pe_len, d] */
+  const float *lnf_g, *lnf_b;                 /* decoder.norm */
+  const void  *w_out; const float *b_out;     /* latent_proj [latent, d] */
+  const cfb_denoiser_layer *layers;           /* host array [n_layers] */
+} cfb_denoiser_weights;
+
+/* Conditioning memory of one call.  cond[x]: [n_slots[x], len[x], d] float, batch-first as
+ * returned by TextAudioMotionFuser.forward (condfuser.py:32-51); mask[x]: [n_slots[x], len[x]]
+ * bytes, 1 = ignore (key_padding_mask, cross_attention.py:587-591) or NULL; slot[x]: [n_rows/
+ * n_tokens] int32 mapping each denoiser batch entry to a slot, or NULL for identity. */
+typedef struct {
+  const float   *cond[CFB_N_STREAMS];
+  const uint8_t *mask[CFB_N_STREAMS];
+  const int32_t *slot[CFB_N_STREAMS];
+  int32_t n_slots[CFB_N_STREAMS];
+  int32_t len[CFB_N_STREAMS];
+} cfb_memory;
+
+typedef struct cfb_denoiser cfb_denoiser;
+
+int cfb_denoiser_create(const cfb_denoiser_weights *w, cfb_denoiser **out);
+void cfb_denoiser_destroy(cfb_denoiser *h);
+
+/* One denoiser evaluation: sample [n_batch, n_tokens, latent] float -> eps (same shape).
+ * att_out[x] (or NULL): [n_batch, n_layers, n_tokens, len[x]] float attention weights, the
+ * second return value of Denoiser.forward (cross_attention.py:234). */
+int cfb_denoiser_forward(cfb_denoiser *h, const float *sample, int n_batch, int64_t timestep,
+                         const cfb_memory *mem, float *eps_out, float *const att_out[CFB_N_STREAMS],
+                         cfb_stream stream);
+
+/* ------------------------------------------------------------------ sampling ----- */
+/* Host-side schedule: one row of coefficients per inference step, computed by the host
+ * scheduler mirror exactly like diffusers' float32 table arithmetic:
+ *   coef[i] = { sqrt(1-abar_t), sqrt(abar_t), k0, k1, k2, ia, ib, 0 }
+ *   DDIM: prev = k0*x0 + k1*eps (+ k2*noise if k2 != 0)   DDPM: prev = k0*x0 + k1*x (+ k2*noise)
+ *   x0 = (x - coef0*eps)/coef1, clamped to [-1,1] when clip_sample
+ *   ia, ib: add_noise coefficients of noise_scheduler at t_i (latent inpainting).
+ */
+typedef struct {
+  int32_t kind;              /* cfb_sched_kind */
+  int32_t n_steps;
+  int32_t clip_sample;
+  float   guidance_scale;
+  const int64_t *timesteps;  /* host [n_steps] */
+  const float   *coef;       /* host [n_steps, 8] */
+} cfb_schedule;
+
+/* Replaces Convofusion._diffusion_reverse (modeltype/convofusion.py:391-549) and
+ * diffusion_reverse_forecast (unbounded_synthesis.py:28-187) with WEG off: the whole
+ * n_steps loop (7-branch guidance + scheduler step [+ latent inpainting]) on the device.
+ *   n_clips      B; the denoiser batch is n_branch*B rows of n_tokens, branch-major like
+ *                torch.cat([latents]*7) (convofusion.py:499)
+ *   n_branch     7 = evaluate every branch; 6 = skip the weight-0 full-cond branch
+ *   mem          slot[x] has n_branch*B entries
+ *   latents      in: initial noise * init_noise_sigma [B, n_tokens, latent]; out: final latents
+ *   step_noise   [n_steps, B, n_tokens, latent] or NULL (DDPM / eta>0 noise)
+ *   preseq       [B, preseq_len, latent] or NULL (previous window's latents to inpaint)
+ *   record       [n_steps, B, n_tokens, latent] or NULL: latents after every scheduler step
+ *   att_out[x]   [n_steps, B, n_layers, n_tokens, len[x]] or NULL: maps of the LAST branch
+ *   use_graph    replay one captured CUDA graph per step instead of launching kernels
+ */
+int cfb_sample(cfb_denoiser *h, const cfb_schedule *sched, const cfb_memory *mem, int n_clips,
+               int n_branch, float *latents, const float *step_noise, const float *preseq,
+               int preseq_len, float *record, float *const att_out[CFB_N_STREAMS], int use_graph,
+               cfb_stream stream);
+
+/* Fused 7-way guidance combine + scheduler step (convofusion.py:527-545 + diffusers step()).
+ * eps [n_branch, B, n] ; x [B, n] in/out; coef = one device row of 8 floats as above. */
+int cfb_guidance_sched_step(const float *eps, float *x, const float *noise, const float *coef_dev,
+                            int n_branch, int n_clips, int n_per_clip, int kind, int clip_sample,
+                            float guidance_scale, cfb_stream stream);
+
+/* ------------------------------------------------------------------ VAE decode --- */
+/* Replaces ConvoFusionVae.decode (architectures/vae.py:268-372): SkipTransformerDecoder x2
+ * (cross_attention.py:89-125, 361-382) + final linears + padding mask. */
+typedef struct {
+  const float *ln1_g, *ln1_b; const void *w_in; const float *b_in;   /* self_attn.in_proj [3d,d] */
+  const void  *w_so; const float *b_so;
+  const float *ln2_g, *ln2_b; const void *w_q;  const float *b_q;    /* multihead_attn q rows [d,d] */
+  const void  *w_kv; const float *b_kv;                              /* multihead_attn k,v rows [2d,d] */
+  const void  *w_co; const float *b_co;
+  const float *ln3_g, *ln3_b; const void *w_ff1; const float *b_ff1;
+  const void  *w_ff2; const float *b_ff2;
+} cfb_vae_layer;
+
+typedef struct {
+  const cfb_vae_layer *layers;     /* host [n_layers]: input_blocks.., middle_block, output_blocks.. */
+  const void  *w_skip[4]; const float *b_skip[4];   /* linear_blocks.i [d, 2d], (n_layers-1)/2 used */
+  const float *lnf_g, *lnf_b;      /* decoder.norm */
+  const void  *w_final; const float *b_final; int32_t n_out;   /* {body,hands}_final_layer [n_out, d] */
+} cfb_vae_decoder;
+
+typedef struct {
+  int32_t d_model, n_layers, n_heads, ff_size, precision, pe_len;
+  const float *pe_query, *pe_mem;   /* query_pos_decoder.pe / mem_pos_decoder.pe [pe_len, d] */
+  cfb_vae_decoder part[2];          /* body, hands */
+} cfb_vae_weights;
+
+typedef struct cfb_vae cfb_vae;
+int cfb_vae_create(const cfb_vae_weights *w, cfb_vae **out);
+void cfb_vae_destroy(cfb_vae *h);
+/* z [2, B, n_chunks, d] float; lengths host [B]; out [B, n_frames, n_out_body+n_out_hands]. */
+int cfb_vae_decode(cfb_vae *h, const float *z, int n_clips, int n_chunks, int n_frames,
+                   const int32_t *lengths_host, float *out, cfb_stream stream);
+
+/* ------------------------------------------------------------------ unit ops ----- */
+/* Exposed so tests/ can check each kernel against the oracle through the same ABI.
+ * y[M,N] (+)= act(A[M,K] W[N,K]^T + bias).  a_bf16/out_bf16 pick element types. */
+int cfb_linear(const void *A, int a_bf16, const void *W, const float *bias, void *out, int out_bf16,
+               int M, int N, int K, int act, int a_act, int accumulate, int backend, cfb_stream stream);
+int cfb_layernorm(const float *x, const float *g, const float *b, void *out, int out_bf16,
+                  int rows, int d, cfb_stream stream);
+/* Generic multi-head attention over packed projections (torch.nn.MultiheadAttention core):
+ * q [n*Lq, ldq], k/v [n*Lk, ldk] rows are sample-major; kv_len [n] or NULL. */
+int cfb_mha(const void *q, int ldq, const void *k, const void *v, int ldk, void *out, int ldo,
+            int is_bf16, int n, int Lq, int Lk, int n_heads, int head_dim, const int32_t *kv_len,
+            cfb_stream stream);
+/* Conditioning projections (audioenc.py:29-34; t5.py:48-49,57), float in/out. */
+int cfb_audio_encoder(const float *mel, int rows, const float *w0, const float *b0, const float *w1,
+                      const float *b1, const float *w2, const float *b2, int n_mel, int hidden,
+                      int d_out, float *tmp0, float *tmp1, float *out, cfb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONVOFUSION_B200_H */

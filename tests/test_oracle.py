@@ -1,0 +1,134 @@
+"""Pins the CPU oracle (oracle/convofusion_oracle.py) to outputs of the unmodified reference modules
+(tests/golden/*.pt, produced by tools/make_golden.py inside the build container)."""
+import torch
+
+from convofusion_b200.synthetic import synthetic_clip
+from oracle import convofusion_oracle as O
+from helpers import SCHED_KW, frac_within, golden, max_rel, oracle_batch, oracle_denoise, rel_err, state_dict
+
+TOL = 2e-5   # fp32 restatement vs fp32 reference: reassociation noise only
+
+
+def test_conditioning_matches_reference():
+    g = golden("conditioning.pt")
+    gen = torch.Generator().manual_seed(7)
+    mel = torch.rand(2, 24, 80, generator=gen) * 80 - 80
+    t5 = torch.randn(2, 6, 768, generator=gen)
+    sd = state_dict()
+    assert max_rel(O.audio_encoder(sd, mel), g["audio"]) < TOL
+    assert max_rel(O.text_projection(sd, t5), g["text"]) < TOL
+    apb, _ = O.condition_fuser(sd, torch.tensor([[0, 1, 2, 1]]), [3])
+    _, ids = O.condition_fuser(sd, torch.tensor([[0, 1, 2, 1]]), [3, 35, 0])
+    assert torch.equal(apb, g["fuser_apb"]) and torch.equal(ids, g["fuser_id"])
+
+
+def _denoiser_case(tag, B, dyadic):
+    g = golden(f"denoiser_{tag}.pt")
+    syn = synthetic_clip(B, seed=1234 + B, dyadic=dyadic)
+    enc, masks = oracle_batch(syn)
+    for e, c in zip(enc, g["enc_checksum"]):
+        assert abs(float(e.double().sum()) - c) <= 1e-4 * max(1.0, abs(c))
+    x = torch.randn(B, 16, 128, generator=torch.Generator().manual_seed(99 + B))
+    eps, att = oracle_denoise(torch.cat([x] * 7), g["t"], enc, masks)
+    assert eps.shape == (7 * B, 16, 128)
+    assert max_rel(eps, g["eps"]) < TOL
+    for a, ga in zip(att, g["att_full"]):
+        assert max_rel(a.chunk(7)[-1], ga) < 2e-4   # softmax amplifies fp32 score rounding
+    # the five attention rows are probability distributions with zero weight on padded keys
+    assert torch.allclose(att[2].sum(-1), torch.ones_like(att[2].sum(-1)), atol=1e-5)
+    assert float(att[2][masks["tlsn"][:, None, None, :].expand_as(att[2])].abs().max()) == 0.0
+
+
+def test_denoiser_monadic_matches_reference():
+    _denoiser_case("mono_b1", 1, False)
+
+
+def test_denoiser_dyadic_matches_reference():
+    _denoiser_case("dyad_b2", 2, True)
+
+
+def test_vae_decode_matches_reference_ragged():
+    sd = state_dict()
+    z = torch.randn(2, 3, 8, 128, generator=torch.Generator().manual_seed(5))
+    g = golden("vae_decode.pt")
+    out = O.vae_decode(sd, z, g["lengths"], prefix="vae.")
+    assert out.shape == (3, 128, 189)
+    assert max_rel(out, g["out"]) < TOL
+    assert float(out[1, 100:].abs().max()) == 0.0 and float(out[2, 37:].abs().max()) == 0.0
+    g2 = golden("vae_decode_short.pt")   # max(lengths) < 128 shortens the output (temos_utils.py:15)
+    out2 = O.vae_decode(sd, z[:, :2], g2["lengths"], prefix="vae.")
+    assert out2.shape == (2, 64, 189) and max_rel(out2, g2["out"]) < TOL
+
+
+def test_full_sampling_run_matches_reference_modules():
+    """Config 1 of BASELINE.json (B=1, DDIM-50, CFG 7.5): every per-step latent and the final joints."""
+    syn = synthetic_clip(1, seed=1235, dyadic=False)
+    enc, masks = oracle_batch(syn)
+    init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(100))
+    g = golden("sample_ddim50_clip.pt")
+    sch = O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    rec = []
+    z, att = O.diffusion_reverse(oracle_denoise, sch, enc, masks, init, 50, guidance_scale=7.5, record=rec)
+    rec = torch.stack(rec)
+    # north-star acceptance: >= 90 % of elements within 1e-4 (relative to the tensor's scale) at EVERY step.  Two
+    # fp32 evaluations that differ only by summation order already sit at 1.5e-5 .. 6e-5 L2 (the -36.5 / +7.5
+    # guidance weights amplify eps rounding ~74x), which bounds what any fp32 implementation can promise.
+    assert min(frac_within(rec[i], g["record"][i], 1e-4) for i in range(50)) >= 0.9
+    assert max(rel_err(rec[i], g["record"][i]) for i in range(50)) < 1e-4
+    joints = O.vae_decode(state_dict(), O.latents_to_vae_input(z), [128], prefix="vae.")
+    assert max_rel(joints, g["joints"]) < 1e-3
+    assert max_rel(att[int(sch.timesteps[-1])][2], g["att_last_tlsn"]) < 1e-3
+
+
+def test_guidance_weights_identity():
+    """the combine equals (1-5s) e0 + s (e1+..+e5); the full-cond branch has weight 0."""
+    e = torch.randn(7 * 3, 16, 128, generator=torch.Generator().manual_seed(3))
+    c = O.guidance_combine(e, 7.5)
+    ch = e.chunk(7)
+    closed = (1 - 5 * 7.5) * ch[0] + 7.5 * sum(ch[1:6])
+    assert torch.allclose(c, closed, rtol=1e-4, atol=1e-4)
+    e2 = e.clone()
+    e2[-3:] = 123.0
+    assert torch.equal(O.guidance_combine(e2, 7.5), c)
+
+
+def test_scheduler_tables():
+    d = O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    d.set_timesteps(50)
+    assert d.timesteps.tolist() == list(range(980, -1, -20))
+    m = O.DDIMSchedulerOracle(clip_sample=False, set_alpha_to_one=False, steps_offset=1, **SCHED_KW)
+    m.set_timesteps(50)
+    assert m.timesteps[0] == 981 and m.timesteps[-1] == 1
+    p = O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    p.set_timesteps(1000)
+    assert p.timesteps[0] == 999 and p.timesteps[-1] == 0 and len(p.timesteps) == 1000
+    assert abs(float(p.betas[0]) - 0.00085) < 1e-9 and abs(float(p.betas[-1]) - 0.012) < 1e-8
+    # x_t = add_noise(x0, eps, t); stepping with the true eps must return x0 as pred_original_sample
+    x0 = torch.rand(2, 16, 128) * 1.6 - 0.8
+    eps = torch.randn(2, 16, 128)
+    xt = p.add_noise(x0, eps, torch.tensor([500]))
+    for s in (d, p):
+        s.set_timesteps(50)
+        out = s.step(eps, 500, xt, **({"variance_noise": torch.zeros_like(xt)} if s is p else {}))
+        assert torch.allclose(out.pred_original_sample, x0, atol=2e-5)
+
+
+def test_forecast_aliasing_quirk():
+    """unbounded_synthesis.py:66-76: step 0 inpaints with the fresh noise, later steps with the noised preseq."""
+    calls = []
+
+    def fake_denoise(x, t, enc, masks):
+        calls.append(x[:2].clone())
+        return torch.zeros_like(x), [torch.zeros(x.shape[0], 1, 16, 1)] * 5
+
+    sch = O.DDIMSchedulerOracle(clip_sample=False, **SCHED_KW)
+    nsch = O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    init = torch.randn(2, 16, 128, generator=torch.Generator().manual_seed(1))
+    pre = torch.randn(2, 8, 128, generator=torch.Generator().manual_seed(2))
+    O.diffusion_reverse_forecast(fake_denoise, sch, nsch, None, None, init, 3, pre)
+    sch.set_timesteps(3)
+    t0, t1 = sch.timesteps[0], sch.timesteps[1]
+    first = nsch.add_noise(pre, init[:, :8], t0)
+    assert torch.allclose(calls[0][:, :8], first)
+    assert torch.allclose(calls[1][:, :8], nsch.add_noise(pre, first, t1))
+    assert not torch.allclose(calls[1][:, :8], nsch.add_noise(pre, init[:, :8], t1))
