@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the ConvoFusion sampling hot path (BASELINE.json metric: motion-seconds generated per second).
+
+A "step" is one pass of the hot path over one batch of synthetic clips: conditioning projections (once per clip),
+the DDIM loop (50 denoiser evaluations under 7-branch modality guidance + scheduler), VAE decode to joints.
+One clip = 128 frames @ 25 fps = 5.12 motion-seconds.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N>1: launched under torchrun)
+  python bench.py --impl reference [...]                         the reference algorithm on the host CPU
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MOTION_S_PER_CLIP = 128 / 25.0
+SCHED_KW = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step (BASELINE.json configs[1])")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dyadic", action="store_true", help="configs[2]: DnD-shaped conditioning")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ flops
+def denoiser_flops(n_clips, n_branch, mem_tokens, d=512, ff=1024, L=9, ntok=16, lat=128):
+    """Executed FLOPs of one denoiser evaluation (2*m*n*k over every GEMM + attention contraction) in the folded
+    form this implementation issues, and the as-written reference-equivalent figure."""
+    R = n_clips * n_branch * ntok
+    per_row_layer = 2 * d * (3 * d + d + d + 5 * d + 5 * d + d + 2 * ff)
+    gemm = R * (L * per_row_layer + 2 * lat * d) + n_clips * ntok * 2 * lat * d
+    self_att = n_clips * n_branch * L * 2 * 2 * ntok * ntok * d
+    cross = n_clips * n_branch * L * 2 * 2 * ntok * mem_tokens * d
+    as_written = n_clips * 7 * (L * (212.3e6 + 0.0328e6 * mem_tokens + 1.0486e6 * mem_tokens) + 5.2e6)
+    return {"gemm": gemm, "attention": self_att + cross, "executed": gemm + self_att + cross, "as_written": as_written}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(n_clips, ddim_steps, timed_denoiser_steps, dyadic, threads):
+    """The reference algorithm on host cores: oracle port of Denoiser.forward / guidance / DDIM / VAE decode
+    (oracle/convofusion_oracle.py, pinned to the reference modules by tests/golden).  Times `timed_denoiser_steps`
+    evaluations of the 7*B batch plus one decode and extrapolates the loop linearly to `ddim_steps`."""
+    import torch
+    import convofusion_b200 as cf
+    from convofusion_b200.synthetic import randomize_, synthetic_clip
+    from oracle import convofusion_oracle as O
+    torch.set_num_threads(threads)
+    sd = {k: v for k, v in randomize_(cf.ConvoFusionSampler(precision="fp32"), 1234).state_dict().items()}
+    syn = synthetic_clip(n_clips, seed=1234, dyadic=dyadic)
+    clip = dict(syn["clip"])
+    clip["text_lsn_mask"], clip["text_spk_mask"] = ~clip["text_lsn_attn"].bool(), ~clip["text_spk_attn"].bool()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        enc, masks = O.assemble_guidance_batch(sd, clip, syn["uncond_text"], ~syn["uncond_text_attn"].bool())
+        t_cond = time.perf_counter() - t0
+        sch = O.DDIMSchedulerOracle(**SCHED_KW)
+        sch.set_timesteps(ddim_steps)
+        lat = torch.randn(n_clips, 16, 128, generator=torch.Generator().manual_seed(1))
+        den = lambda x, t: O.denoiser_forward(sd, x, t, enc, masks, prefix="denoiser.")
+        den(torch.cat([lat] * 7), sch.timesteps[0])          # warm-up
+        t0 = time.perf_counter()
+        for t in sch.timesteps[:timed_denoiser_steps]:
+            eps, _ = den(torch.cat([lat] * 7), t)
+            lat = sch.step(O.guidance_combine(eps, 7.5), t, lat, eta=0.0).prev_sample
+        t_step = (time.perf_counter() - t0) / timed_denoiser_steps
+        t0 = time.perf_counter()
+        O.vae_decode(sd, O.latents_to_vae_input(lat.permute(1, 0, 2)), [128] * n_clips, prefix="vae.")
+        t_dec = time.perf_counter() - t0
+    total = t_cond + ddim_steps * t_step + t_dec
+    return {"seconds_per_pass": total, "ms_per_denoiser_step": t_step * 1e3, "decode_ms": t_dec * 1e3,
+            "value": n_clips * MOTION_S_PER_CLIP / total}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_clips, timed = 4, 6
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(n_clips, args.ddim_steps, timed, args.dyadic, cores)
+        if i >= args.warmup:
+            vals.append(r)
+    v = sum(r["value"] for r in vals) / len(vals)
+    ms = sum(r["seconds_per_pass"] for r in vals) / len(vals) * 1e3
+    sample = (f"{n_clips} clips (7x{n_clips} denoiser batch), {timed} of {args.ddim_steps} DDIM steps timed and "
+              f"extrapolated linearly, + conditioning + VAE decode; torch fp32, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "motion_seconds_per_second", "value": v, "unit": "motion-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_clips),
+        "cpu_baseline": {"value": v, "unit": "motion-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "motion-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, batch):
+    return {"workload": ("dyadic DnD-shaped" if args.dyadic else "monadic BEAT-shaped") +
+            f" config_cf_beatdnd random-init, batch {batch} clips/GPU, {args.ddim_steps} DDIM steps, 7-branch guidance 7.5, "
+            "VAE decode to 128x189 joints (BASELINE.json configs[%d])" % (2 if args.dyadic else 1),
+            "clips_per_gpu": batch, "ddim_steps": args.ddim_steps, "guidance_branches_evaluated": 6,
+            "memory_tokens": 234 if args.dyadic else 234,
+            "l2": "no flush: one pass streams 186 MB of bf16 weights 50x plus >150 MB of activations, above the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def gemm_roofline(torch, lib_mod, batch, n_branch, dev, iters=20):
+    """Device time of the dominant kernel (gemm_tc_kernel) over exactly the GEMM shape mix of one denoiser
+    evaluation, CUDA events on the launching stream; weights of all 9 layers rotate so operands exceed L2."""
+    from convofusion_b200 import _lib
+    R, d = batch * n_branch * 16, 512
+    shapes = [(3 * d, d), (d, d), (d, d), (5 * d, d), (d, 5 * d), (d, d), (1024, d), (d, 1024)]
+    Ws = [[torch.randn(n, k, device=dev).bfloat16() for (n, k) in shapes] for _ in range(9)]
+    As = {k: torch.randn(R, k, device=dev).bfloat16() for k in (d, 5 * d, 1024)}
+    outs = {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, d, 5 * d, 1024)}
+    st = torch.cuda.current_stream().cuda_stream
+
+    def one_pass():
+        for layer in Ws:
+            for (n, k), w in zip(shapes, layer):
+                _lib.check(_lib.lib().cfb_linear(As[k].data_ptr(), 1, w.data_ptr(), 0, outs[n].data_ptr(), 1, R, n, k, 0, 0, 0,
+                                                 _lib.GEMM_TCGEN05, st))
+    for _ in range(3):
+        one_pass()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 9 * sum(2.0 * R * n * k for (n, k) in shapes)
+    return flops / (ms * 1e-3) / 1e12, ms, 9 * len(shapes)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import convofusion_b200 as cf
+    from convofusion_b200 import _lib
+    from convofusion_b200.synthetic import randomize_, synthetic_clip
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: convofusion_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n_branch = args.batch, 6
+
+    sampler = randomize_(cf.ConvoFusionSampler(precision=args.precision, num_inference_timesteps=args.ddim_steps), 1234)
+    sampler = sampler.to(dev).eval()
+    syn = synthetic_clip(B, seed=1234 + rank, dyadic=args.dyadic)     # config 5: seeds 1234 + shard id
+    clip, U, Ua = syn["clip"], syn["uncond_text"], syn["uncond_text_attn"]
+    init = torch.randn(B, 16, 128, generator=torch.Generator().manual_seed(77 + rank))
+    host = {k: v.pin_memory() for k, v in clip.items() if torch.is_tensor(v)}
+    host_init = init.pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values()) + host_init.numel() * 4
+    out_host = torch.empty(B, 128, 189).pin_memory()
+    d2h_bytes = out_host.numel() * 4
+    Ud, Uad = U.to(dev), Ua.to(dev)
+    dclip = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in clip.items()}
+    dinit = init.to(dev)
+    lengths = [128] * B
+    gathered = [torch.empty(B, 128, 189, device=dev) for _ in range(world)] if world > 1 else None
+    stream = torch.cuda.Stream(device=dev)
+
+    def pass_device():
+        out = sampler.generate(dclip, Ud, Uad, lengths, dinit, use_graph=not args.no_graph)["m_rst"]
+        if world > 1:
+            dist.all_gather(gathered, out)        # the only collective: output motions at the end
+        return out
+
+    def pass_e2e():
+        c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        c["lsn_id"] = clip["lsn_id"]
+        x = host_init.to(dev, non_blocking=True)
+        out = sampler.generate(c, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
+        if world > 1:
+            dist.all_gather(gathered, out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def timed(fn, warmup, steps, sample_clocks):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            clocks = ClockSampler(local) if sample_clocks else None
+            if clocks:
+                clocks.start()
+            l0 = _lib.lib().cfb_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            launches = _lib.lib().cfb_launch_count() - l0
+            ck = clocks.stop() if clocks else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, ck
+
+    ms_dev, launches, clocks = timed(pass_device, args.warmup, args.steps, True)
+    ms_e2e, _, _ = timed(pass_e2e, 1, args.steps, False)
+
+    # split of one pass: conditioning / loop / decode (device events, rank 0 only, untimed extra pass)
+    parts = {}
+    with torch.cuda.stream(stream):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        enc, masks = sampler.encode_conditions(dclip, Ud, Uad)
+        ev[1].record()
+        z, _, _ = sampler.sample(enc, masks, B, dinit, use_graph=not args.no_graph)
+        ev[2].record()
+        sampler.decode(z, lengths)
+        ev[3].record()
+        torch.cuda.synchronize()
+        parts = {"conditioning_ms": ev[0].elapsed_time(ev[1]), "loop_ms": ev[1].elapsed_time(ev[2]),
+                 "decode_ms": ev[2].elapsed_time(ev[3])}
+        roof = None
+        if rank == 0 and args.precision == "bf16":
+            tf, gemm_ms, n_gemm = gemm_roofline(torch, _lib, B, n_branch, dev)
+            roof = (tf, gemm_ms, n_gemm)
+
+    clips_total = B * world * args.steps
+    value = clips_total * MOTION_S_PER_CLIP / (ms_dev * 1e-3)
+    e2e_value = clips_total * MOTION_S_PER_CLIP / (ms_e2e * 1e-3)
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+        mem_tokens = 234
+        fl = denoiser_flops(B, n_branch, mem_tokens)
+        ms_den = parts["loop_ms"] / args.ddim_steps
+        line = {
+            "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+            "config": workload_config(args, B),
+            "e2e": {"value": e2e_value, "unit": "motion-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "ms_per_denoiser_step": ms_den, "pass_split_ms": parts,
+            "denoiser_step_tflops": {"executed": fl["executed"] / (ms_den * 1e-3) / 1e12,
+                                     "reference_equivalent": fl["as_written"] / (ms_den * 1e-3) / 1e12,
+                                     "executed_gflop_per_step": fl["executed"] / 1e9},
+        }
+        if roof:
+            tf, gemm_ms, n_gemm = roof
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": tf, "peak": peak_tf,
+                                "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                                "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
+                                "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf}
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            r = cpu_reference_run(2, args.ddim_steps, 4, args.dyadic, cores)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 clips (7x2 denoiser batch), 4 of {args.ddim_steps} DDIM steps timed and "
+                                              "extrapolated linearly + conditioning + decode; oracle port, torch fp32",
+                                    "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

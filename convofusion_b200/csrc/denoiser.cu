@@ -59,6 +59,9 @@ struct cfb_denoiser {
   } graph_key;
   bool graph_valid = false;
   size_t graph_nodes = 0;   // kernel nodes in the captured step (for the launch counter)
+  // The legacy default stream cannot be captured: graph mode on it runs on this private stream, fenced by events.
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -240,6 +243,9 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
 void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (!h) return;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
                        &h->slots, &h->masks};
@@ -284,7 +290,19 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   bool want_att = false;
   if (att_out) for (int x = 0; x < CFB_N_STREAMS; ++x) want_att |= att_out[x] != nullptr;
   CFB_CHECK(!want_att || n_branch == CFB_N_BRANCH, "cfb_sample: attention maps come from the full-cond branch; use n_branch=7");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user_st = (cudaStream_t)stream;
+  cudaStream_t st = user_st;
+  const bool fenced = use_graph && (user_st == nullptr || user_st == cudaStreamLegacy || user_st == cudaStreamPerThread);
+  if (fenced) {
+    if (!h->own_stream) {
+      CFB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+      CFB_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+      CFB_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    st = h->own_stream;
+    CFB_CUDA(cudaEventRecord(h->ev_in, user_st));
+    CFB_CUDA(cudaStreamWaitEvent(st, h->ev_in, 0));
+  }
   const int S = sched->n_steps, n_batch = n_clips * n_branch;
   const int n_per_clip = h->ntok * h->lat;
   CFB_TRY(reserve_rows(h, n_batch, n_clips));
@@ -364,6 +382,10 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
     for (int i = 0; i < S; ++i) CFB_TRY(body());
   }
   CFB_CUDA(cudaMemcpyAsync(latents, h->x.p, (size_t)n_clips * n_per_clip * 4, cudaMemcpyDeviceToDevice, st));
+  if (fenced) {
+    CFB_CUDA(cudaEventRecord(h->ev_out, st));
+    CFB_CUDA(cudaStreamWaitEvent(user_st, h->ev_out, 0));
+  }
   return CFB_OK;
 }
 

@@ -1,0 +1,179 @@
+"""CPU-side checks of the host logic: weight folding, scheduler mirrors, guidance slot tables, the C ABI's
+symbol table, and the fail-loudly contract when no GPU is present.  No kernel runs here."""
+import ctypes
+import math
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import convofusion_b200 as cf
+from convofusion_b200 import _lib
+from convofusion_b200.conditioning import BRANCH_STREAM, expand_guidance_batch, guidance_slots
+from convofusion_b200.pack import STREAMS, fold_cross_attention
+from oracle import convofusion_oracle as O
+from helpers import SCHED_KW, rel_err, state_dict
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_folded_cross_attention_is_exact_algebra():
+    """pack.fold_cross_attention vs the as-written five MultiheadAttentions + att_fuser (cross_attention.py:578-652),
+    evaluated in float64 so only algebra (not rounding) is compared."""
+    sd = {k: v.double() for k, v in state_dict().items() if k.startswith("denoiser.decoder.layers.3.")}
+    lp, d = "denoiser.decoder.layers.3.", 512
+    g = torch.Generator().manual_seed(0)
+    B, lens = 3, (5, 9, 7, 8, 1)
+    t2 = torch.randn(16, B, d, generator=g, dtype=torch.float64)            # norm2(tgt)
+    mems = [torch.randn(L, B, d, generator=g, dtype=torch.float64) * 2 + 0.3 for L in lens]
+    masks = {"tlsn": torch.tensor([[0, 0, 0, 1, 1, 1, 1]] * B).bool(), "spkemb": torch.tensor([[0, 0, 1, 1, 1]] * B).bool()}
+    outs = []
+    for name, mem in zip(STREAMS, mems):
+        m = O._ln(sd, lp + f"{name}_norm.", mem)
+        o, _ = O._mha_sd(sd, lp + f"multihead_attn_{name}.", t2, m, m, 1, masks.get(name))
+        outs.append(o)
+    want = O._lin(sd, lp + "att_fuser.", torch.cat(outs, -1))
+    w_qx, b_qx, w_fu, b_fu = fold_cross_attention(sd, lp, d)
+    qx = F.linear(t2, w_qx, b_qx)                                           # [16,B,5d]
+    us = []
+    for x, (name, mem) in enumerate(zip(STREAMS, mems)):
+        mu = mem.mean(-1, keepdim=True)
+        xhat = (mem - mu) / torch.sqrt(((mem - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
+        s = torch.einsum("qbd,kbd->bqk", qx[..., x * d:(x + 1) * d], xhat)
+        if masks.get(name) is not None:
+            s = s.masked_fill(masks[name][:, None, :], float("-inf"))
+        us.append(torch.einsum("bqk,kbd->qbd", torch.softmax(s, -1), xhat))
+    got = F.linear(torch.cat(us, -1), w_fu, b_fu)
+    assert rel_err(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["ddim", "ddim_mld", "ddim_eta", "ddpm"])
+def test_scheduler_mirror_matches_oracle(kind):
+    """step_table() rows fed through the kernel's formula reproduce the oracle scheduler's step() exactly."""
+    if kind == "ddpm":
+        mine, ora = cf.DDPMScheduler(clip_sample=True, **SCHED_KW), O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    elif kind == "ddim_mld":
+        kw = dict(clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+        mine, ora = cf.DDIMScheduler(**kw, **SCHED_KW), O.DDIMSchedulerOracle(**kw, **SCHED_KW)
+    else:
+        mine, ora = cf.DDIMScheduler(clip_sample=True, **SCHED_KW), O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    eta = 0.7 if kind == "ddim_eta" else 0.0
+    n = 20
+    tab = mine.step_table(n, eta=eta)
+    ora.set_timesteps(n)
+    assert tab["timesteps"].tolist() == ora.timesteps.tolist()
+    assert tab["needs_noise"] == (kind in ("ddpm", "ddim_eta"))
+    g = torch.Generator().manual_seed(4)
+    x, eps, z = (torch.randn(2, 16, 128, generator=g) for _ in range(3))
+    for i, t in enumerate(tab["timesteps"]):
+        c = [torch.tensor(v) for v in tab["coef"][i]]
+        x0 = (x - c[0] * eps) / c[1]
+        if tab["clip_sample"]:
+            x0 = x0.clamp(-1, 1)
+        prev = c[2] * x0 + c[3] * (eps if kind != "ddpm" else x)
+        if float(c[4]) != 0.0:
+            prev = prev + c[4] * z
+        kw = {"variance_noise": z} if kind in ("ddpm", "ddim_eta") else {}
+        if kind.startswith("ddim"):
+            kw["eta"] = eta
+        want = ora.step(eps, int(t), x, **kw).prev_sample
+        assert torch.equal(prev, want), (kind, i)
+        a = ora.alphas_cumprod[int(t)]
+        assert tab["coef"][i, 5] == np.float32(a ** 0.5) and tab["coef"][i, 6] == np.float32((1 - a) ** 0.5)
+
+
+def test_scheduler_public_surface():
+    import inspect
+    d, p = cf.DDIMScheduler(**SCHED_KW), cf.DDPMScheduler(**SCHED_KW)
+    assert "eta" in inspect.signature(d.step).parameters          # convofusion.py:427-429 detects DDIM this way
+    assert "eta" not in inspect.signature(p.step).parameters
+    for s in (d, p):
+        assert s.init_noise_sigma == 1.0 and s.config.num_train_timesteps == 1000 and s.betas.shape == (1000,)
+        s.set_timesteps(50)
+        assert len(s.timesteps) == 50 and s.timesteps.dtype == torch.int64
+    x0, n = torch.randn(2, 8, 128), torch.randn(2, 8, 128)
+    assert torch.equal(p.add_noise(x0, n, torch.tensor(400)), O.DDPMSchedulerOracle(**SCHED_KW).add_noise(x0, n, 400))
+    with pytest.raises(NotImplementedError):
+        cf.DDIMScheduler(prediction_type="sample", **SCHED_KW)
+    with pytest.raises(ValueError):
+        d.set_timesteps(2000)
+
+
+def test_guidance_slots_reproduce_the_seven_branch_batch():
+    B = 3
+    slots = guidance_slots(B, 7, "cpu")
+    for x in range(5):
+        s = slots[x].view(7, B)
+        for g in range(7):
+            cond = g == 6 or BRANCH_STREAM.get(g) == x
+            assert s[g].tolist() == ([1, 2, 3] if cond else [0, 0, 0])
+    assert all(len(s) == 6 * B for s in guidance_slots(B, 6, "cpu"))
+    # gathering slots == torch.cat([...]*7) ordering of convofusion.py:911-929
+    enc = [torch.arange(4.0).view(4, 1, 1).expand(4, 2, 3).contiguous() + 10 * x for x in range(5)]
+    masks = {"tlsn": torch.tensor([[1, 1], [0, 1], [0, 0], [1, 0]]).bool(), "spkemb": None, "alsn": None}
+    enc7, masks7 = expand_guidance_batch(enc, masks, B)
+    u, c = torch.zeros(B), torch.arange(1.0, B + 1)
+    want_tlsn = torch.cat([u, c, u, u, u, u, c]) + 20       # text_lsn list at :911
+    want_alsn = torch.cat([u, u, c, u, u, u, c]) + 10       # melspec_lsn cat at :916
+    want_spk = torch.cat([u, u, u, c, u, u, c])             # text_spk at :918
+    want_apb = torch.cat([u, u, u, u, c, u, c]) + 30        # active_passive_bit at :921-927
+    want_id = torch.cat([u, u, u, u, u, c, c]) + 40         # lsn_id at :929
+    for got, want in zip(enc7, (want_spk, want_alsn, want_tlsn, want_apb, want_id)):
+        assert got[:, 0, 0].tolist() == want.tolist()
+    assert masks7["tlsn"].shape == (7 * B, 2) and masks7["tlsn"][B].tolist() == [False, True]
+    assert masks7["alsn"] is None
+
+
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / "include" / "convofusion_b200.h").read_text()
+    declared = set(re.findall(r"\b(cfb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cfb_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert ctypes.sizeof(_lib.DenoiserLayer) == 26 * 8
+    assert ctypes.sizeof(_lib.DenoiserWeights) == 8 * 4 + 15 * 8
+    assert ctypes.sizeof(_lib.Memory) == 15 * 8 + 10 * 4
+    assert ctypes.sizeof(_lib.Schedule) == 16 + 16
+    assert ctypes.sizeof(_lib.VaeLayer) == 20 * 8
+    assert ctypes.sizeof(_lib.VaeDecoder) == 8 + 32 + 32 + 32 + 8
+    assert ctypes.sizeof(_lib.VaeWeights) == 24 + 16 + 2 * ctypes.sizeof(_lib.VaeDecoder)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks behaviour on a box without a GPU")
+def test_no_cpu_fallback():
+    den = cf.default_denoiser("fp32")
+    with pytest.raises(_lib.CfbError):
+        den(torch.zeros(7, 16, 128), torch.tensor(10), [torch.zeros(7, 4, 512)] * 5, None, {})
+    with pytest.raises(_lib.CfbError):
+        cf.default_vae("fp32").decode(torch.zeros(2, 1, 8, 128), [128])
+    sch = cf.DDIMScheduler(**SCHED_KW)
+    sch.set_timesteps(50)
+    with pytest.raises(_lib.CfbError):
+        sch.step(torch.zeros(1, 16, 128), 0, torch.zeros(1, 16, 128))
+    w, h = _lib.DenoiserWeights(), ctypes.c_void_p()
+    assert _lib.lib().cfb_denoiser_create(ctypes.byref(w), ctypes.byref(h)) == -3      # CFB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in _lib.lib().cfb_last_error()
+
+
+def test_state_dict_layout_is_the_reference_layout():
+    """Spot-check the key convention of SURVEY 8b (full strict-load against the reference modules is done by
+    tools/make_golden.py, which needs /root/reference)."""
+    keys = set(state_dict())
+    for k in ("denoiser.cond_params", "denoiser.query_pos.pe", "denoiser.decoder.layers.8.multihead_attn_lsnemb.in_proj_weight",
+              "denoiser.decoder.layers.0.time_block2.emb_layers.1.bias", "denoiser.decoder.layers.4.time_block1.out_layers.2.weight",
+              "denoiser.decoder.layers.2.apb_norm.weight", "denoiser.decoder.norm.bias", "vae.body_decoder.linear_blocks.1.weight",
+              "vae.hands_encoder.input_blocks.0.self_attn.out_proj.bias", "vae.body_global_motion_token",
+              "vae.mem_pos_decoder.pe", "text_audio_encoder.text_encoder.projection.1.weight",
+              "text_audio_encoder.audio_encoder.main.3.bias", "text_audio_encoder.audio_time_proj.weight",
+              "condition_fuser.lsn_id_emb.weight", "condition_fuser.latent_proj.2.bias"):
+        assert k in keys, k
+    assert state_dict()["text_audio_encoder.audio_time_proj.weight"].shape == (512, 161)
+    assert sum(v.numel() for k, v in state_dict().items() if k.startswith("denoiser.") and not k.endswith(".pe")) == 92923013
