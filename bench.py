@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--dyadic", action="store_true", help="configs[2]: DnD-shaped conditioning")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the GEMM micro-measurement (profiling runs)")
     return ap.parse_args()
 
 
@@ -61,10 +62,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -72,10 +73,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
@@ -285,7 +286,7 @@ def run_ours(args):
         parts = {"conditioning_ms": ev[0].elapsed_time(ev[1]), "loop_ms": ev[1].elapsed_time(ev[2]),
                  "decode_ms": ev[2].elapsed_time(ev[3])}
         roof = None
-        if rank == 0 and args.precision == "bf16":
+        if rank == 0 and args.precision == "bf16" and not args.no_roofline:
             tf, gemm_ms, n_gemm = gemm_roofline(torch, _lib, B, n_branch, dev)
             roof = (tf, gemm_ms, n_gemm)
 

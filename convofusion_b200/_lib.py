@@ -32,7 +32,8 @@ class DenoiserWeights(C.Structure):
                                           "precision", "pe_len")] +
                 [(n, C.c_void_p) for n in ("w_embed", "tok_bias", "w_t1", "b_t1", "w_t2", "b_t2", "w_tbmod",
                                            "b_tbmod", "stream_emb", "pe_mem", "lnf_g", "lnf_b", "w_out", "b_out")] +
-                [("layers", C.POINTER(DenoiserLayer))])
+                [("w_zx", C.c_void_p * N_STREAMS), ("a_zx", C.c_void_p * N_STREAMS), ("w_yx", C.c_void_p * N_STREAMS),
+                 ("layers", C.POINTER(DenoiserLayer))])
 
 
 class Memory(C.Structure):

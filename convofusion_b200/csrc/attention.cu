@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
   float* Ss = Qs + CROSS_MAXQ * CROSS_D;   // [16][Mp]
   const int Mp = (M + 3) & ~3;
   const int slot = a.slot[x] ? a.slot[x][bs] : bs;
+  if (a.skip_slot0 && slot == 0) return;   // block-uniform: covered by the shared-slot GEMM path
   const T* mem = mem_hat + ((size_t)a.row_base[x] + (size_t)slot * M) * CROSS_D;
   const uint8_t* msk = a.mask[x] ? a.mask[x] + (size_t)slot * M : nullptr;
 
@@ -116,9 +117,13 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
   }
   __syncthreads();
   // ---- scores: each warp walks keys j = warp, warp+8, ...; lanes split the 512 columns.
+  float kv_next[16];
+  if (warp < M) load_row16<T>(mem + (size_t)warp * CROSS_D, lane, kv_next);
   for (int j = warp; j < M; j += 8) {
     float kv[16];
-    load_row16<T>(mem + (size_t)j * CROSS_D, lane, kv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) kv[i] = kv_next[i];
+    if (j + 8 < M) load_row16<T>(mem + (size_t)(j + 8) * CROSS_D, lane, kv_next);   // next key row in flight
     const bool masked = msk && msk[j];
     for (int qi = 0; qi < n_tokens; ++qi) {
       float s = 0.f;
@@ -164,20 +169,31 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
   float acc[CROSS_MAXQ][2];
 #pragma unroll
   for (int qi = 0; qi < CROSS_MAXQ; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
-  for (int j = 0; j < M; ++j) {
-    float v0, v1;
-    if constexpr (sizeof(T) == 4) {
-      const float2 t = *reinterpret_cast<const float2*>(mem + (size_t)j * CROSS_D + c);
-      v0 = t.x; v1 = t.y;
-    } else {
-      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(mem + (size_t)j * CROSS_D + c);
-      v0 = __low2float(t); v1 = __high2float(t);
+  // 8 key rows are fetched before any is consumed: the loop is bound by L2 latency, not by its 32 FMAs per key
+  constexpr int PF = 8;
+  for (int j0 = 0; j0 < M; j0 += PF) {
+    float v0[PF], v1[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int j = min(j0 + u, M - 1);
+      if constexpr (sizeof(T) == 4) {
+        const float2 t = *reinterpret_cast<const float2*>(mem + (size_t)j * CROSS_D + c);
+        v0[u] = t.x; v1[u] = t.y;
+      } else {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(mem + (size_t)j * CROSS_D + c);
+        v0[u] = __low2float(t); v1[u] = __high2float(t);
+      }
     }
 #pragma unroll
-    for (int qi = 0; qi < CROSS_MAXQ; ++qi) {
-      const float p = Ss[qi * Mp + j];   // rows >= n_tokens are never stored below
-      acc[qi][0] = fmaf(p, v0, acc[qi][0]);
-      acc[qi][1] = fmaf(p, v1, acc[qi][1]);
+    for (int u = 0; u < PF; ++u) {
+      if (j0 + u >= M) break;
+      const int j = j0 + u;
+#pragma unroll
+      for (int qi = 0; qi < CROSS_MAXQ; ++qi) {
+        const float p = Ss[qi * Mp + j];   // rows >= n_tokens are never stored below
+        acc[qi][0] = fmaf(p, v0[u], acc[qi][0]);
+        acc[qi][1] = fmaf(p, v1[u], acc[qi][1]);
+      }
     }
   }
   for (int qi = 0; qi < n_tokens; ++qi) {
@@ -192,6 +208,197 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
 
 constexpr int ATT_MAX_SMEM = 160 * 1024;
 
+// Denoiser self-attention (cross_attention.py:570): 16 tokens, head_dim 128.  One warp owns one
+// (sample, head); lane = (query i, parity p).  q/k/v of the head are staged as float in shared memory
+// with a 132-float row pitch so every 128-bit access below is conflict-free per quarter-warp: lane
+// (i,p) scores keys j = 2*jj+p (adjacent rows -> banks +4) and accumulates output chunks 2*c+p.
+constexpr int SA_L = 16, SA_HD = 128, SA_PITCH = 132;
+
+template <typename T>
+__global__ void __launch_bounds__(128) self_attn16_kernel(const T* __restrict__ qkv, int ld, int E,
+                                                          T* __restrict__ out, int ldo, int n_heads) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y * 4 + warp;
+  if (h >= n_heads) return;
+  const int b = blockIdx.x;
+  float* Q = sm + warp * 3 * SA_L * SA_PITCH;
+  float* K = Q + SA_L * SA_PITCH;
+  float* V = K + SA_L * SA_PITCH;
+  for (int r = 0; r < 3 * SA_L; ++r) {           // 48 rows of 128 elements, 4 per lane: coalesced
+    const int which = r / SA_L, row = r % SA_L;
+    const T* src = qkv + (size_t)(b * SA_L + row) * ld + which * E + h * SA_HD + lane * 4;
+    float4 v;
+    if constexpr (sizeof(T) == 4) {
+      v = *reinterpret_cast<const float4*>(src);
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(src);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+      v = make_float4(__low2float(a), __high2float(a), __low2float(c), __high2float(c));
+    }
+    if (which == 0) {                            // torch scales q by sqrt(1/head_dim) before q k^T
+      const float s = sqrtf(1.0f / (float)SA_HD);
+      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    }
+    *reinterpret_cast<float4*>(Q + which * SA_L * SA_PITCH + row * SA_PITCH + lane * 4) = v;
+  }
+  __syncwarp();
+  const int i = lane >> 1, p = lane & 1;
+  float s[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) s[jj] = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < SA_HD; d += 4) {
+    const float4 qv = *reinterpret_cast<const float4*>(Q + i * SA_PITCH + d);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const float4 kv = *reinterpret_cast<const float4*>(K + (2 * jj + p) * SA_PITCH + d);
+      s[jj] = fmaf(qv.x, kv.x, s[jj]); s[jj] = fmaf(qv.y, kv.y, s[jj]);
+      s[jj] = fmaf(qv.z, kv.z, s[jj]); s[jj] = fmaf(qv.w, kv.w, s[jj]);
+    }
+  }
+  float mx = s[0];
+#pragma unroll
+  for (int jj = 1; jj < 8; ++jj) mx = fmaxf(mx, s[jj]);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  float sum = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) { s[jj] = expf(s[jj] - mx); sum += s[jj]; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  const float inv = 1.0f / sum;
+  float4 acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float mine = s[jj] * inv;
+    const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const float p_even = p ? other : mine;     // key 2*jj
+    const float p_odd = p ? mine : other;      // key 2*jj + 1
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 v0 = *reinterpret_cast<const float4*>(V + (2 * jj) * SA_PITCH + (2 * c + p) * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(V + (2 * jj + 1) * SA_PITCH + (2 * c + p) * 4);
+      acc[c].x = fmaf(p_even, v0.x, acc[c].x); acc[c].y = fmaf(p_even, v0.y, acc[c].y);
+      acc[c].z = fmaf(p_even, v0.z, acc[c].z); acc[c].w = fmaf(p_even, v0.w, acc[c].w);
+      acc[c].x = fmaf(p_odd, v1.x, acc[c].x); acc[c].y = fmaf(p_odd, v1.y, acc[c].y);
+      acc[c].z = fmaf(p_odd, v1.z, acc[c].z); acc[c].w = fmaf(p_odd, v1.w, acc[c].w);
+    }
+  }
+  T* orow = out + (size_t)(b * SA_L + i) * ldo + h * SA_HD;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    T* o = orow + (2 * c + p) * 4;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(o) = acc[c];
+    } else {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(acc[c].x, acc[c].y);
+      const __nv_bfloat162 d2 = __floats2bfloat162_rn(acc[c].z, acc[c].w);
+      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&d2);
+      *reinterpret_cast<uint2*>(o) = pk;
+    }
+  }
+}
+
+constexpr int SA_SMEM = 4 * 3 * SA_L * SA_PITCH * (int)sizeof(float);   // 101,376 B per 4-warp block
+
+// One warp per query row; see SharedAttnArgs.
+__global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+                                                             SharedAttnArgs a, int rows, int n_tokens) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int bs = r / n_tokens;
+#pragma unroll
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    bf16* prow = P + (size_t)r * a.ld_p + a.p_off[x];
+    const int M = a.len[x], kp = a.kp[x];
+    if (a.slot[x][bs] != 0) {
+      for (int j = lane; j < kp; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    const float* srow = S + (size_t)r * a.ld_s + a.s_off[x];
+    const uint8_t* msk = a.mask[x];
+    float mx = -INFINITY;
+    for (int j = lane; j < M; j += 32) {
+      const float s = (msk && msk[j]) ? -INFINITY : srow[j];
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < M; j += 32) {
+      const float s = (msk && msk[j]) ? -INFINITY : srow[j];
+      sum += expf(s - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < kp; j += 32) {
+      float p = 0.f;
+      if (j < M) {
+        const float s = (msk && msk[j]) ? -INFINITY : srow[j];
+        p = expf(s - mx) * inv;
+      }
+      prow[j] = __float2bfloat16_rn(p);
+    }
+  }
+}
+
+// z0[l][s_off[x] + j] = a_{x,l} . xhat_{x,slot 0, j}: the key-dependent bias of the shared-slot scores.
+struct Z0Args {
+  const float* a_zx[CFB_N_STREAMS];   // [L, 512]
+  int row_base[CFB_N_STREAMS], len[CFB_N_STREAMS], s_off[CFB_N_STREAMS];
+  int tok_base[CFB_N_STREAMS + 1];    // prefix sum of len
+};
+__global__ void __launch_bounds__(256) z0_kernel(const bf16* __restrict__ mem_hat, float* __restrict__ z0, Z0Args a,
+                                                 int n_layers, int n_tot) {
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= a.tok_base[CFB_N_STREAMS]) return;
+  int x = 0;
+#pragma unroll
+  for (int i = 1; i < CFB_N_STREAMS; ++i) x += (t >= a.tok_base[i]);
+  const int j = t - a.tok_base[x];
+  float kv[16];
+  load_row16<bf16>(mem_hat + ((size_t)a.row_base[x] + j) * CROSS_D, lane, kv);
+  for (int l = 0; l < n_layers; ++l) {
+    const float* av = a.a_zx[x] + (size_t)l * CROSS_D;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = *reinterpret_cast<const float4*>(av + i * 128 + lane * 4);
+      s = fmaf(q.x, kv[i * 4], s); s = fmaf(q.y, kv[i * 4 + 1], s);
+      s = fmaf(q.z, kv[i * 4 + 2], s); s = fmaf(q.w, kv[i * 4 + 3], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) z0[(size_t)l * n_tot + a.s_off[x] + j] = s;
+  }
+}
+
+}  // namespace
+
+int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
+                    const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
+                    int n_layers, int n_tot, cudaStream_t st) {
+  Z0Args a;
+  int tok = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    a.a_zx[x] = a_zx[x]; a.row_base[x] = row_base[x]; a.len[x] = len[x]; a.s_off[x] = s_off[x];
+    a.tok_base[x] = tok; tok += len[x];
+  }
+  a.tok_base[CFB_N_STREAMS] = tok;
+  z0_kernel<<<ceil_div(tok, 8), 256, 0, st>>>(mem_hat, z0, a, n_layers, n_tot);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
+  const int rows = n_batch * n_tokens;
+  if (rows <= 0) return CFB_OK;
+  softmax_shared_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, P, a, rows, n_tokens);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+namespace {
 }  // namespace
 
 // Opt in to large dynamic shared memory once, outside any stream capture.
@@ -202,6 +409,8 @@ int init_attention_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   done = true;
   return CFB_OK;
 }
@@ -211,6 +420,14 @@ int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, i
         int head_dim, const int* kv_len, cudaStream_t st) {
   if (n <= 0) return CFB_OK;
   CFB_CHECK(Lq > 0 && Lk > 0 && head_dim > 0 && n_heads > 0, "mha: bad shape");
+  // packed self-attention of the denoiser: q, k, v are column blocks of one [rows, 3E] matrix
+  if (Lq == SA_L && Lk == SA_L && head_dim == SA_HD && kv_len == nullptr && ldq == ldk &&
+      k == q + n_heads * head_dim && v == q + 2 * n_heads * head_dim && ldq % 4 == 0 && ldo % 4 == 0) {
+    dim3 grid(n, ceil_div(n_heads, 4));
+    self_attn16_kernel<T><<<grid, 128, SA_SMEM, st>>>(q, ldq, n_heads * head_dim, out, ldo, n_heads);
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  }
   const size_t smem = ((size_t)Lk * (head_dim + 1) + (size_t)Lk * head_dim + 4 * head_dim + 4 * Lk) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "mha: Lk=%d head_dim=%d needs %zu B of shared memory", Lk, head_dim, smem);
   const int q_per_block = Lq >= 64 ? 32 : Lq;

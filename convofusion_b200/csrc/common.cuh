@@ -96,8 +96,17 @@ struct Epilogue {
 int gemm_simt(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw, int M, int N, int K,
               int a_act, const Epilogue& ep, cudaStream_t st);
 bool gemm_tc_supported(int M, int N, int K, int lda, int ldw);
+// w_rows (0 = N): number of valid rows of W; rows in [w_rows, N) read as zeros (TMA out-of-bounds fill).
 int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,
-            cudaStream_t st);
+            cudaStream_t st, int w_rows = 0);
+// Grouped tcgen05 GEMM: group z computes rows [row_start, row_start+rows) of A_z . W_z^T (+bias_z) into out_z;
+// A_z / out_z are base pointers indexed by ABSOLUTE row; N, K, lda, ldw, ep flags are shared.
+constexpr int TC_MAX_GROUPS = 10;
+struct TcGroup {
+  const bf16* A; const bf16* W; const float* bias; void* out; int row_start; int rows;
+};
+int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
+                    const Epilogue& ep, cudaStream_t st);
 extern int g_gemm_backend;
 
 // y = act(A W^T + b) dispatch: bf16 operands use tcgen05 when allowed, everything else SIMT.

@@ -49,13 +49,14 @@ struct cfb_denoiser {
   int d, lat, ntok, L, H, ff, prec;
   unsigned epoch = 0;
   DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
-      preseq, slots, masks;
+      preseq, slots, masks, uc, sS, sP, zall, z0all, ytall;
   // cached CUDA graph of one sampling step
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey {
     unsigned epoch; int n_clips, n_branch, n_steps, kind, clip, preseq_len; float scale;
     int n_slots[CFB_N_STREAMS], len[CFB_N_STREAMS]; bool has_mask[CFB_N_STREAMS];
     const void *noise, *record, *att[CFB_N_STREAMS];
+    int plan[2 + 3 * TC_MAX_GROUPS];
   } graph_key;
   bool graph_valid = false;
   size_t graph_nodes = 0;   // kernel nodes in the captured step (for the launch counter)
@@ -73,6 +74,22 @@ struct MemLayout {
   int mask_off[CFB_N_STREAMS];   // byte offsets into h->masks
 };
 
+// Shared-slot plan (bf16 only).  When slot tables are given, slot 0 of every stream is the memory that most of the
+// guidance batch attends to (the unconditional constant).  For those (row, stream) pairs the algebra is pushed onto
+// the memory side once per step:
+//   Z_{x,l} = xhat_0x A_{x,l}        (keys in query space)        -> scores  S = norm2(tgt) . [Z_0;..;Z_4]^T + z0
+//   Y_{x,l} = xhat_0x G_{x,l}^T      (values in residual space)   -> update  h += softmax(S) . [Y_0;..;Y_4]
+// so the 512->2560 query projection and the 2560->512 fuser shrink to two GEMMs with N = 320 and K = 448.
+// Pairs on any other slot (one stream per single-modality branch) run in `groups`: contiguous row blocks with
+// their own stream weights (grouped tcgen05 GEMMs) around the per-pair attention kernel.
+struct SharedPlan {
+  bool on = false;
+  int s_off[CFB_N_STREAMS], p_off[CFB_N_STREAMS], kp[CFB_N_STREAMS];
+  int n_tot = 0, k_tot = 0;
+  int n_groups = 0;
+  int g_stream[TC_MAX_GROUPS], g_row_start[TC_MAX_GROUPS], g_rows[TC_MAX_GROUPS];
+};
+
 template <typename T>
 int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaStream_t st) {
   // denoiser.py:183-187,316-326: latent_embd + body/hand embedding + SineBH positional encoding
@@ -84,9 +101,26 @@ int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaSt
   return gemm(h->xin.p, sizeof(T) == 2, h->lat, h->w.w_embed, sizeof(T) == 2, h->lat, rows, h->d, h->lat, 0, ep, st);
 }
 
+// Per-step memory-side precompute of the shared-slot plan: Z (keys), z0 (key bias) and Y^T (values) for all layers.
+int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml, const int len[CFB_N_STREAMS],
+                      cudaStream_t st) {
+  const int d = h->d, Ld = h->L * h->d;
+  const bf16* mh = h->mem_hat.as<bf16>();
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    const bf16* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
+    const int rows_avail = ml.total_rows - ml.row_base[x];
+    Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = 1; ez.out = h->zall.as<bf16>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
+    CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
+    Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = 1; ey.out = h->ytall.as<bf16>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
+    const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
+    CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+  }
+  return shared_key_bias(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
+}
+
 template <typename T>
 int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
-               float* eps_out, cudaStream_t st) {
+               float* eps_out, cudaStream_t st, const SharedPlan* sp = nullptr) {
   const int R = n_batch * h->ntok, d = h->d;
   const int tb = sizeof(T) == 2;
   float* hres = h->h.as<float>();
@@ -117,11 +151,49 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     CFB_TRY(lin_res(a, d, w.w_tb1, w.b_tb1));
     // five cross-attentions + att_fuser (:578-652), folded
     CFB_TRY(ln_rows<T>(hres, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
-    CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
     for (int x = 0; x < CFB_N_STREAMS; ++x)
       ca.att[x] = att_base && att_base[x] ? att_base[x] + (size_t)l * h->ntok * ca.len[x] : nullptr;
-    CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), qx, ca, n_batch, h->ntok, d, st));
-    CFB_TRY(lin_res(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu));
+    bool shared_done = false;
+    if constexpr (sizeof(T) == 2) {
+      if (sp && sp->on) {
+        const int Ld = h->L * d;
+        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h
+        Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = h->sS.p;
+        es.ldo = sp->n_tot; es.replicate = 1;
+        CFB_TRY(gemm_tc(a, d, h->zall.as<bf16>() + (size_t)l * d, Ld, R, sp->n_tot, d, es, st));
+        SharedAttnArgs sa{};
+        for (int x = 0; x < CFB_N_STREAMS; ++x) {
+          sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
+          sa.slot[x] = ca.slot[x]; sa.mask[x] = ca.mask[x];
+        }
+        sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot;
+        CFB_TRY(softmax_shared(h->sS.as<float>(), h->sP.as<bf16>(), sa, n_batch, h->ntok, st));
+        Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
+        CFB_TRY(gemm_tc(h->sP.as<bf16>(), sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d,
+                        sp->k_tot, ey, st));
+        if (sp->n_groups > 0) {   // conditional pairs: own-stream projection, per-pair attention, own-stream fuser block
+          TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
+          bf16* uc = h->uc.as<bf16>();
+          for (int z = 0; z < sp->n_groups; ++z) {
+            const int x = sp->g_stream[z];
+            gq[z] = TcGroup{a, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx + x * d, sp->g_row_start[z], sp->g_rows[z]};
+            gg[z] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, hres, sp->g_row_start[z], sp->g_rows[z]};
+          }
+          Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+          CFB_TRY(gemm_tc_grouped(gq, sp->n_groups, R, d, d, d, d, eq, st));
+          ca.skip_slot0 = 1;
+          CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, st));
+          Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+          CFB_TRY(gemm_tc_grouped(gg, sp->n_groups, R, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
+        }
+        shared_done = true;
+      }
+    }
+    if (!shared_done) {
+      CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
+      CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), qx, ca, n_batch, h->ntok, d, st));
+      CFB_TRY(lin_res(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu));
+    }
     // time_block2 (:655)
     CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
     CFB_TRY(lin_res(a, d, w.w_tb2, w.b_tb2));
@@ -203,12 +275,60 @@ int prep_memory(cfb_denoiser* h, const cfb_memory* mem, int n_batch, MemLayout* 
 
 template <typename T>
 int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, const CrossArgs& ca,
-              float* const att_base[CFB_N_STREAMS], const StepArgs& sa, cudaStream_t st) {
+              float* const att_base[CFB_N_STREAMS], const StepArgs& sa, const SharedPlan& sp, cudaStream_t st) {
   const int* step_ptr = h->step.as<int>();
   CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
+  if (sp.on) CFB_TRY(shared_precompute(h, sp, ml, ca.len, st));
   CFB_TRY(embed<T>(h, h->x.as<float>(), n_clips, n_branch, st));   // torch.cat([latents] * 7), convofusion.py:499
-  CFB_TRY(run_layers<T>(h, n_clips * n_branch, ca, att_base, step_ptr, h->eps.as<float>(), st));
+  CFB_TRY(run_layers<T>(h, n_clips * n_branch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp));
   return guidance_sched_step(sa, st);
+}
+
+// Decide whether the shared-slot plan applies and derive the conditional row groups from the slot tables.
+int make_shared_plan(cfb_denoiser* h, const cfb_memory* mem, int n_batch, SharedPlan* sp, cudaStream_t st) {
+  sp->on = false;
+  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT) return CFB_OK;
+  for (int x = 0; x < CFB_N_STREAMS; ++x)
+    if (mem->slot[x] == nullptr) return CFB_OK;
+  std::vector<int> hs((size_t)n_batch);
+  int ng = 0, s_off = 0, p_off = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    CFB_CUDA(cudaMemcpyAsync(hs.data(), mem->slot[x], (size_t)n_batch * 4, cudaMemcpyDeviceToHost, st));
+    CFB_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < n_batch;) {
+      CFB_CHECK(hs[b] >= 0 && hs[b] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, hs[b]);
+      if (hs[b] == 0) { ++b; continue; }
+      int e = b;
+      while (e < n_batch && hs[e] != 0) {
+        CFB_CHECK(hs[e] >= 0 && hs[e] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, hs[e]);
+        ++e;
+      }
+      if (ng == TC_MAX_GROUPS) return CFB_OK;   // too fragmented: keep the general path
+      sp->g_stream[ng] = x; sp->g_row_start[ng] = b * h->ntok; sp->g_rows[ng] = (e - b) * h->ntok;
+      ++ng;
+      b = e;
+    }
+    sp->s_off[x] = s_off; s_off += (mem->len[x] + 31) & ~31;
+    sp->kp[x] = (mem->len[x] + 63) & ~63;
+    sp->p_off[x] = p_off; p_off += sp->kp[x];
+  }
+  sp->n_tot = s_off; sp->k_tot = p_off; sp->n_groups = ng;
+  const size_t R = (size_t)n_batch * h->ntok, Ld = (size_t)h->L * h->d;
+  const unsigned before = h->epoch;
+  CFB_TRY(h->uc.reserve(R * CFB_N_STREAMS * h->d * 2, &h->epoch));
+  CFB_TRY(h->sS.reserve(R * sp->n_tot * 4, &h->epoch));
+  CFB_TRY(h->sP.reserve(R * sp->k_tot * 2, &h->epoch));
+  CFB_TRY(h->zall.reserve((size_t)sp->n_tot * Ld * 2, &h->epoch));
+  CFB_TRY(h->z0all.reserve((size_t)h->L * sp->n_tot * 4, &h->epoch));
+  CFB_TRY(h->ytall.reserve(Ld * sp->k_tot * 2, &h->epoch));
+  if (h->epoch != before) {   // fresh allocations: padding rows/columns must hold finite values
+    CFB_CUDA(cudaMemsetAsync(h->zall.p, 0, h->zall.cap, st));
+    CFB_CUDA(cudaMemsetAsync(h->z0all.p, 0, h->z0all.cap, st));
+    CFB_CUDA(cudaMemsetAsync(h->ytall.p, 0, h->ytall.cap, st));
+    CFB_CUDA(cudaMemsetAsync(h->uc.p, 0, h->uc.cap, st));
+  }
+  sp->on = true;
+  return CFB_OK;
 }
 
 }  // namespace
@@ -248,7 +368,7 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall};
   for (DeviceBuf* b : bufs) b->release();
   delete h;
 }
@@ -320,6 +440,8 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_TRY(prep_time(h, S, st));
   MemLayout ml; CrossArgs ca;
   CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
+  SharedPlan sp;
+  CFB_TRY(make_shared_plan(h, mem, n_batch, &sp, st));
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     ca.att_batch_stride[x] = (long long)h->L * h->ntok * mem->len[x];
     ca.att_step_stride[x] = (long long)n_clips * ca.att_batch_stride[x];
@@ -343,8 +465,8 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   sa.n_steps = S; sa.kind = sched->kind; sa.clip_sample = sched->clip_sample; sa.guidance_scale = sched->guidance_scale;
 
   auto body = [&]() {
-    return h->prec == CFB_BF16 ? step_body<bf16>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, st)
-                               : step_body<float>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, st);
+    return h->prec == CFB_BF16 ? step_body<bf16>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, sp, st)
+                               : step_body<float>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, sp, st);
   };
 
   if (use_graph) {
@@ -357,6 +479,10 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
+    key.plan[0] = sp.on; key.plan[1] = sp.on ? sp.n_groups : 0;
+    for (int z = 0; sp.on && z < sp.n_groups; ++z) {
+      key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
+    }
     if (!h->graph_valid || memcmp(&key, &h->graph_key, sizeof(key)) != 0) {
       if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
       h->graph_valid = false;

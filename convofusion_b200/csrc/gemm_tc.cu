@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
+#include <cstring>
 
 namespace cfb {
 
@@ -116,11 +117,14 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
+// One 128 x BN output tile: rows [m0, min(m0+128, m_end)), columns [n0, n0+BN).
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, int M, int N,
-                                                           int K, Epilogue ep) {
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const int m0,
+                                          const int M /* first row NOT to store */, const int n0, const int N,
+                                          const int K, const Epilogue& ep) {
   using S = Smem<BN, STAGES>;
+  const CUtensorMap& tmA = *tmA_p;
+  const CUtensorMap& tmB = *tmB_p;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = base + S::BAR_OFF;           // STAGES barriers
@@ -131,7 +135,6 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + S::BAR_OFF + (2 * STAGES + 1) * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -244,6 +247,37 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
   }
 }
 
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, int M, int N,
+                                                           int K, Epilogue ep) {
+  gemm_tile<BN, STAGES>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+}
+
+// Grouped launch: blockIdx.z picks a group = (A map, B map, row block, bias, output).  All groups share N, K and
+// the epilogue flags.  Used for the conditional rows of the guidance batch, where every branch owns one
+// contiguous row block and its own stream's weights.
+struct GroupedArgs {
+  CUtensorMap tmA[TC_MAX_GROUPS];
+  CUtensorMap tmB[TC_MAX_GROUPS];
+  int row_start[TC_MAX_GROUPS];
+  int rows[TC_MAX_GROUPS];
+  const float* bias[TC_MAX_GROUPS];
+  void* out[TC_MAX_GROUPS];
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_grouped_kernel(const __grid_constant__ GroupedArgs g, int N, int K,
+                                                                   Epilogue ep) {
+  const int z = blockIdx.z;
+  const int m0 = g.row_start[z] + blockIdx.y * BM;
+  const int m_end = g.row_start[z] + g.rows[z];
+  if (m0 >= m_end) return;   // uniform for the whole CTA, before any barrier / TMEM allocation
+  ep.bias = g.bias[z];
+  ep.out = g.out[z];
+  gemm_tile<BN, STAGES>(&g.tmA[z], &g.tmB[z], m0, m_end, blockIdx.x * BN, N, K, ep);
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -306,13 +340,35 @@ int get_map(const bf16* p, int rows, int cols, int ld, int box_rows, CUtensorMap
 }
 
 template <int BN, int STAGES>
-int launch(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep,
+           cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   CUtensorMap ta, tb;
   CFB_TRY(get_map(A, M, K, lda, BM, &ta));
-  CFB_TRY(get_map(W, N, K, ldw, BN, &tb));
+  CFB_TRY(get_map(W, w_rows, K, ldw, BN, &tb));   // rows past w_rows read as zeros (TMA out-of-bounds fill)
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
   gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+template <int BN, int STAGES>
+int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
+                   const Epilogue& ep, cudaStream_t st) {
+  using S = Smem<BN, STAGES>;
+  GroupedArgs g;
+  memset(&g, 0, sizeof(g));
+  int max_rows = 0;
+  for (int z = 0; z < n_groups; ++z) {
+    CFB_TRY(get_map(groups[z].A, a_rows_total, K, lda, BM, &g.tmA[z]));
+    CFB_TRY(get_map(groups[z].W, N, K, ldw, BN, &g.tmB[z]));
+    g.row_start[z] = groups[z].row_start; g.rows[z] = groups[z].rows;
+    g.bias[z] = groups[z].bias; g.out[z] = groups[z].out;
+    if (groups[z].rows > max_rows) max_rows = groups[z].rows;
+  }
+  if (max_rows <= 0) return CFB_OK;
+  dim3 grid(ceil_div(N, BN), ceil_div(max_rows, BM), n_groups);
+  gemm_tc_grouped_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(g, N, K, ep);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -325,6 +381,7 @@ int init_gemm_tc_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   done = true;
   return CFB_OK;
 }
@@ -333,20 +390,38 @@ bool gemm_tc_supported(int M, int N, int K, int lda, int ldw) {
   return M > 0 && K >= BK && K % BK == 0 && N % 32 == 0 && lda % 8 == 0 && ldw % 8 == 0;
 }
 
-int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep_in,
-            cudaStream_t st) {
-  CFB_CHECK(gemm_tc_supported(M, N, K, lda, ldw), "gemm_tc: unsupported shape %dx%dx%d", M, N, K);
-  CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_tc: operands must be 16-byte aligned");
-  Epilogue ep = ep_in;
+static int check_epilogue(Epilogue& ep) {
   if (ep.replicate < 1) ep.replicate = 1;
   if (ep.bias_period < 1) ep.bias_period = 1;
   CFB_CHECK(!(ep.accumulate && ep.out_bf16), "gemm: accumulate needs float output");
-  CFB_CHECK(ep.ldo % 8 == 0 && ((uintptr_t)ep.out % 16 == 0) && (ep.rep_stride % 8 == 0),
-            "gemm_tc: output must be 16-byte aligned with ldo %% 8 == 0");
+  CFB_CHECK(ep.ldo % 8 == 0 && (ep.rep_stride % 8 == 0), "gemm_tc: ldo %% 8 must be 0");
+  return CFB_OK;
+}
+
+int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep_in,
+            cudaStream_t st, int w_rows) {
+  CFB_CHECK(gemm_tc_supported(M, N, K, lda, ldw), "gemm_tc: unsupported shape %dx%dx%d", M, N, K);
+  CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_tc: operands must be 16-byte aligned");
+  Epilogue ep = ep_in;
+  CFB_TRY(check_epilogue(ep));
+  CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
-  if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, M, N, K, ep, st);
-  if (N % 64 == 0) return launch<64, 4>(A, lda, W, ldw, M, N, K, ep, st);
-  return launch<32, 4>(A, lda, W, ldw, M, N, K, ep, st);
+  if (w_rows <= 0 || w_rows > N) w_rows = N;
+  if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  if (N % 64 == 0) return launch<64, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  return launch<32, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+}
+
+int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
+                    const Epilogue& ep_in, cudaStream_t st) {
+  CFB_CHECK(n_groups > 0 && n_groups <= TC_MAX_GROUPS, "gemm_tc_grouped: %d groups (max %d)", n_groups, TC_MAX_GROUPS);
+  CFB_CHECK(N % 128 == 0 && K % BK == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_tc_grouped: unsupported shape N=%d K=%d", N, K);
+  Epilogue ep = ep_in;
+  CFB_TRY(check_epilogue(ep));
+  for (int z = 0; z < n_groups; ++z)
+    CFB_CHECK(((uintptr_t)groups[z].A % 16 == 0) && ((uintptr_t)groups[z].W % 16 == 0) && ((uintptr_t)groups[z].out % 16 == 0) &&
+              ((uintptr_t)groups[z].bias % 16 == 0), "gemm_tc_grouped: group %d operands must be 16-byte aligned", z);
+  return launch_grouped<128, 3>(groups, n_groups, a_rows_total, lda, ldw, N, K, ep, st);
 }
 
 }  // namespace cfb

@@ -36,7 +36,21 @@ struct CrossArgs {
   int att_first_batch;                  // maps are written for batch entries >= this
   long long att_step_stride[CFB_N_STREAMS];   // added per *step_ptr (graph replay)
   const int* step_ptr;
+  int skip_slot0;                       // 1: (batch entry, stream) pairs on slot 0 are handled by the shared path
 };
+// Shared-slot path: scores of every row against slot 0 of every stream come from ONE GEMM (S, fp32, stream x
+// at columns s_off[x] .. +len[x]); this turns them into bf16 probabilities P (stream x at p_off[x] .. +kp[x],
+// zero padded), writing zeros where the pair is conditional (slot != 0) and handled by cross_attention().
+struct SharedAttnArgs {
+  int len[CFB_N_STREAMS], s_off[CFB_N_STREAMS], p_off[CFB_N_STREAMS], kp[CFB_N_STREAMS];
+  const int* slot[CFB_N_STREAMS];       // [n_batch]
+  const uint8_t* mask[CFB_N_STREAMS];   // key padding mask of slot 0 or nullptr
+  int ld_s, ld_p;
+};
+int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st);
+int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
+                    const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
+                    int n_layers, int n_tot, cudaStream_t st);
 template <typename T>
 int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,
                     cudaStream_t st);

@@ -70,6 +70,7 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
     ff = sd[p + "decoder.layers.0.linear1.weight"].shape[0]
     layers = (_lib.DenoiserLayer * n_layers)()
     tbw, tbb = [], []
+    zx, az, yx = [[] for _ in STREAMS], [[] for _ in STREAMS], [[] for _ in STREAMS]
     for l in range(n_layers):
         lp = f"{p}decoder.layers.{l}."
         L = layers[l]
@@ -82,6 +83,10 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
         L.ln2_g, L.ln2_b = pk.vec(sd[lp + "norm2.weight"]), pk.vec(sd[lp + "norm2.bias"])
         w_qx, b_qx, w_fu, b_fu = fold_cross_attention(sd, lp, d)
         L.w_qx, L.b_qx, L.w_fu, L.b_fu = pk.mat(w_qx), pk.vec(b_qx), pk.mat(w_fu), pk.vec(b_fu)
+        for x in range(len(STREAMS)):
+            zx[x].append(w_qx[x * d:(x + 1) * d].T)          # A_x^T: memory row -> key in query space
+            az[x].append(b_qx[x * d:(x + 1) * d][None, :])
+            yx[x].append(w_fu[:, x * d:(x + 1) * d])         # G_x: memory row -> its residual contribution
         L.tb2_g, L.tb2_b = pk.vec(sd[lp + "time_block2.norm.weight"]), pk.vec(sd[lp + "time_block2.norm.bias"])
         L.w_tb2 = pk.mat(sd[lp + "time_block2.out_layers.2.weight"])
         L.b_tb2 = pk.vec(sd[lp + "time_block2.out_layers.2.bias"])
@@ -107,6 +112,8 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
     w.stream_emb, w.pe_mem = pk.vec(sd[p + "condition_embedding.weight"]), pk.vec(pe_m)
     w.lnf_g, w.lnf_b = pk.vec(sd[p + "decoder.norm.weight"]), pk.vec(sd[p + "decoder.norm.bias"])
     w.w_out, w.b_out = pk.mat(sd[p + "latent_proj.weight"]), pk.vec(sd[p + "latent_proj.bias"])
+    for x in range(len(STREAMS)):
+        w.w_zx[x], w.a_zx[x], w.w_yx[x] = pk.mat(torch.cat(zx[x], 0)), pk.vec(torch.cat(az[x], 0)), pk.mat(torch.cat(yx[x], 0))
     w.layers = C.cast(layers, C.POINTER(_lib.DenoiserLayer))
     return {"struct": w, "layers": layers, "keep": pk.keep}
 

@@ -86,6 +86,12 @@ typedef struct {
   const float *pe_mem;                        /* mem_pos.pe [pe_len, d] */
   const float *lnf_g, *lnf_b;                 /* decoder.norm */
   const void  *w_out; const float *b_out;     /* latent_proj [latent, d] */
+  /* Shared-memory fast path (slot 0 of a stream attended by many batch entries, DESIGN.md "Shared slot"):
+   * per stream x, stacked over layers l:  w_zx[x] [L*d, d] rows l*d.. = A_{x,l}^T  (A = w_qx block x),
+   * a_zx[x] [L, d] = a_{x,l} (b_qx block x),  w_yx[x] [L*d, d] rows l*d.. = G_{x,l} (w_fu column block x). */
+  const void  *w_zx[CFB_N_STREAMS];
+  const float *a_zx[CFB_N_STREAMS];
+  const void  *w_yx[CFB_N_STREAMS];
   const cfb_denoiser_layer *layers;           /* host array [n_layers] */
 } cfb_denoiser_weights;
 

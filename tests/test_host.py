@@ -139,7 +139,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.DenoiserLayer) == 26 * 8
-    assert ctypes.sizeof(_lib.DenoiserWeights) == 8 * 4 + 15 * 8
+    assert ctypes.sizeof(_lib.DenoiserWeights) == 8 * 4 + 30 * 8
     assert ctypes.sizeof(_lib.Memory) == 15 * 8 + 10 * 4
     assert ctypes.sizeof(_lib.Schedule) == 16 + 16
     assert ctypes.sizeof(_lib.VaeLayer) == 20 * 8
