@@ -94,29 +94,47 @@ __device__ __forceinline__ void load_row16(const T* __restrict__ row, int lane, 
   }
 }
 
-// grid (n_batch, n_streams); 256 threads.  qx/u rows are [n_batch * 16, 5 * 512].
+// grid (n_batch, n_streams, 16 / QPB); 256 threads.  qx/u rows are [n_batch * 16, 5 * 512].
+// A block owns QPB = 4 of the 16 queries of one (batch entry, stream) pair: the pair's work is CUDA-core fp32 math
+// (about 5 MFLOP for the 161 audio keys) and splitting it four ways is what keeps all SMs busy when only one
+// branch of the guidance batch is conditional on a stream.
+// Shared memory: Qs [QPB][512] float queries, St [M][QPB] float scores/probabilities (key-major).
+constexpr int QPB = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, const T* __restrict__ mem_hat,
                                                     T* __restrict__ u, CrossArgs a, int n_tokens) {
   extern __shared__ float sm[];
-  const int bs = blockIdx.x, x = blockIdx.y;
+  const int bs = blockIdx.x, x = blockIdx.y, q0 = blockIdx.z * QPB;
   const int M = a.len[x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = CFB_N_STREAMS * CROSS_D;
-  float* Qs = sm;                          // [16][512]
-  float* Ss = Qs + CROSS_MAXQ * CROSS_D;   // [16][Mp]
-  const int Mp = (M + 3) & ~3;
+  float* Qs = sm;                   // [QPB][512]
+  float* St = Qs + QPB * CROSS_D;   // [M][QPB]
   const int slot = a.slot[x] ? a.slot[x][bs] : bs;
   if (a.skip_slot0 && slot == 0) return;   // block-uniform: covered by the shared-slot GEMM path
   const T* mem = mem_hat + ((size_t)a.row_base[x] + (size_t)slot * M) * CROSS_D;
   const uint8_t* msk = a.mask[x] ? a.mask[x] + (size_t)slot * M : nullptr;
 
-  for (int i = threadIdx.x; i < n_tokens * CROSS_D; i += blockDim.x) {
-    const int qi = i / CROSS_D, c = i % CROSS_D;
-    Qs[i] = to_f32<T>(qx[(size_t)(bs * n_tokens + qi) * ld + x * CROSS_D + c]);
+  for (int i = threadIdx.x * 4; i < QPB * CROSS_D; i += blockDim.x * 4) {   // stage the queries (zero past n_tokens)
+    const int qi = q0 + i / CROSS_D, c = i % CROSS_D;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qi < n_tokens) {
+      const T* src = qx + (size_t)(bs * n_tokens + qi) * ld + x * CROSS_D + c;
+      if constexpr (sizeof(T) == 4) {
+        v = *reinterpret_cast<const float4*>(src);
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(src);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      }
+    }
+    *reinterpret_cast<float4*>(Qs + i) = v;
   }
   __syncthreads();
-  // ---- scores: each warp walks keys j = warp, warp+8, ...; lanes split the 512 columns.
+  // ---- scores: warp w walks keys w, w+8, ...; lanes split the 512 columns; the QPB partial sums are independent
+  // chains, reduced across lanes by a transpose-reduce.
   float kv_next[16];
   if (warp < M) load_row16<T>(mem + (size_t)warp * CROSS_D, lane, kv_next);
   for (int j = warp; j < M; j += 8) {
@@ -124,30 +142,48 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
 #pragma unroll
     for (int i = 0; i < 16; ++i) kv[i] = kv_next[i];
     if (j + 8 < M) load_row16<T>(mem + (size_t)(j + 8) * CROSS_D, lane, kv_next);   // next key row in flight
-    const bool masked = msk && msk[j];
-    for (int qi = 0; qi < n_tokens; ++qi) {
-      float s = 0.f;
+    float s[QPB];
+#pragma unroll
+    for (int qi = 0; qi < QPB; ++qi) {
+      float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 qv = *reinterpret_cast<const float4*>(Qs + qi * CROSS_D + i * 128 + lane * 4);
-        s = fmaf(qv.x, kv[i * 4], s); s = fmaf(qv.y, kv[i * 4 + 1], s);
-        s = fmaf(qv.z, kv[i * 4 + 2], s); s = fmaf(qv.w, kv[i * 4 + 3], s);
+        acc = fmaf(qv.x, kv[i * 4], acc); acc = fmaf(qv.y, kv[i * 4 + 1], acc);
+        acc = fmaf(qv.z, kv[i * 4 + 2], acc); acc = fmaf(qv.w, kv[i * 4 + 3], acc);
       }
-      s = warp_sum(s);
-      if (lane == 0) Ss[qi * Mp + j] = masked ? -INFINITY : s;
+      s[qi] = acc;
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {     // lanes with bit 4 set keep queries 2,3
+      const bool up = lane & 16;
+      const float give = up ? s[i] : s[i + 2];
+      const float got = __shfl_xor_sync(0xffffffffu, give, 16);
+      s[i] = (up ? s[i + 2] : s[i]) + got;
+    }
+    {                                 // lanes with bit 3 set keep the odd query of their pair
+      const bool up = lane & 8;
+      const float give = up ? s[0] : s[1];
+      const float got = __shfl_xor_sync(0xffffffffu, give, 8);
+      s[0] = (up ? s[1] : s[0]) + got;
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 4);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    const int qsel = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+    if ((lane & 7) == 0) St[j * QPB + qsel] = (msk && msk[j]) ? -INFINITY : s[0];
   }
   __syncthreads();
-  // ---- softmax per query row (warp w: rows w, w+8)
-  for (int qi = warp; qi < n_tokens; qi += 8) {
-    float* srow = Ss + qi * Mp;
+  // ---- softmax per query (warps 0..QPB-1)
+  if (warp < QPB && q0 + warp < n_tokens) {
+    const int ql = warp, qi = q0 + warp;
     float mx = -INFINITY;
-    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, srow[j]);
+    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, St[j * QPB + ql]);
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < M; j += 32) {
-      const float e = expf(srow[j] - mx);
-      srow[j] = e;
+      const float e = expf(St[j * QPB + ql] - mx);
+      St[j * QPB + ql] = e;
       sum += e;
     }
     sum = warp_sum(sum);
@@ -158,50 +194,52 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
       arow = a.att[x] + step_off + (long long)(bs - a.att_first_batch) * a.att_batch_stride[x] + (long long)qi * M;
     }
     for (int j = lane; j < M; j += 32) {
-      const float p = srow[j] * inv;
-      srow[j] = p;
+      const float p = St[j * QPB + ql] * inv;
+      St[j * QPB + ql] = p;
       if (arow) arow[j] = p;
     }
   }
   __syncthreads();
-  // ---- u = P . mem_hat: thread owns columns {2t, 2t+1}
+  // ---- u = P . mem_hat: thread owns columns {2t, 2t+1}; 8 key rows are fetched before any is consumed
   const int c = threadIdx.x * 2;
-  float acc[CROSS_MAXQ][2];
+  float acc[QPB][2];
 #pragma unroll
-  for (int qi = 0; qi < CROSS_MAXQ; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
-  // 8 key rows are fetched before any is consumed: the loop is bound by L2 latency, not by its 32 FMAs per key
+  for (int qi = 0; qi < QPB; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
   constexpr int PF = 8;
   for (int j0 = 0; j0 < M; j0 += PF) {
     float v0[PF], v1[PF];
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int j = min(j0 + u, M - 1);
+    for (int k = 0; k < PF; ++k) {
+      const int j = min(j0 + k, M - 1);
       if constexpr (sizeof(T) == 4) {
         const float2 t = *reinterpret_cast<const float2*>(mem + (size_t)j * CROSS_D + c);
-        v0[u] = t.x; v1[u] = t.y;
+        v0[k] = t.x; v1[k] = t.y;
       } else {
         const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(mem + (size_t)j * CROSS_D + c);
-        v0[u] = __low2float(t); v1[u] = __high2float(t);
+        v0[k] = __low2float(t); v1[k] = __high2float(t);
       }
     }
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      if (j0 + u >= M) break;
-      const int j = j0 + u;
-#pragma unroll
-      for (int qi = 0; qi < CROSS_MAXQ; ++qi) {
-        const float p = Ss[qi * Mp + j];   // rows >= n_tokens are never stored below
-        acc[qi][0] = fmaf(p, v0[u], acc[qi][0]);
-        acc[qi][1] = fmaf(p, v1[u], acc[qi][1]);
+    for (int k = 0; k < PF; ++k) {
+      const int j = j0 + k;
+      if (j < M) {
+        const float4 p = *reinterpret_cast<const float4*>(St + j * QPB);   // warp-wide broadcast of the 4 probabilities
+        acc[0][0] = fmaf(p.x, v0[k], acc[0][0]); acc[0][1] = fmaf(p.x, v1[k], acc[0][1]);
+        acc[1][0] = fmaf(p.y, v0[k], acc[1][0]); acc[1][1] = fmaf(p.y, v1[k], acc[1][1]);
+        acc[2][0] = fmaf(p.z, v0[k], acc[2][0]); acc[2][1] = fmaf(p.z, v1[k], acc[2][1]);
+        acc[3][0] = fmaf(p.w, v0[k], acc[3][0]); acc[3][1] = fmaf(p.w, v1[k], acc[3][1]);
       }
     }
   }
-  for (int qi = 0; qi < n_tokens; ++qi) {
+#pragma unroll   // fully unrolled so acc[][] stays in registers
+  for (int ql = 0; ql < QPB; ++ql) {
+    const int qi = q0 + ql;
+    if (qi >= n_tokens) break;
     T* o = u + (size_t)(bs * n_tokens + qi) * ld + x * CROSS_D + c;
     if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float2*>(o) = make_float2(acc[qi][0], acc[qi][1]);
+      *reinterpret_cast<float2*>(o) = make_float2(acc[ql][0], acc[ql][1]);
     } else {
-      *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[qi][0], acc[qi][1]);
+      *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(acc[ql][0], acc[ql][1]);
     }
   }
 }
@@ -449,9 +487,9 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
     CFB_CHECK(a.len[x] > 0, "cross_attention: stream %d has no memory tokens", x);
     if (a.len[x] > maxM) maxM = a.len[x];
   }
-  const size_t smem = ((size_t)CROSS_MAXQ * CROSS_D + (size_t)CROSS_MAXQ * ((maxM + 3) & ~3)) * sizeof(float);
+  const size_t smem = ((size_t)QPB * CROSS_D + (size_t)QPB * maxM) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "cross_attention: %d memory tokens exceed the shared-memory budget", maxM);
-  dim3 grid(n_batch, CFB_N_STREAMS);
+  dim3 grid(n_batch, CFB_N_STREAMS, ceil_div(n_tokens, QPB));
   cross_kernel<T><<<grid, 256, smem, st>>>(qx, mem_hat, u, a, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;

@@ -88,6 +88,9 @@ struct SharedPlan {
   int n_tot = 0, k_tot = 0;
   int n_groups = 0;
   int g_stream[TC_MAX_GROUPS], g_row_start[TC_MAX_GROUPS], g_rows[TC_MAX_GROUPS];
+  // Groups whose row blocks overlap (the full-cond branch carries all five streams) accumulate into the same rows
+  // of h, so they are issued in separate rounds: within a round all row blocks are disjoint.
+  int g_round[TC_MAX_GROUPS], n_rounds = 0;
 };
 
 template <typename T>
@@ -184,7 +187,13 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           ca.skip_slot0 = 1;
           CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, st));
           Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
-          CFB_TRY(gemm_tc_grouped(gg, sp->n_groups, R, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
+          for (int r = 0; r < sp->n_rounds; ++r) {
+            TcGroup round[TC_MAX_GROUPS];
+            int n = 0;
+            for (int z = 0; z < sp->n_groups; ++z)
+              if (sp->g_round[z] == r) round[n++] = gg[z];
+            CFB_TRY(gemm_tc_grouped(round, n, R, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
+          }
         }
         shared_done = true;
       }
@@ -313,6 +322,19 @@ int make_shared_plan(cfb_denoiser* h, const cfb_memory* mem, int n_batch, Shared
     sp->p_off[x] = p_off; p_off += sp->kp[x];
   }
   sp->n_tot = s_off; sp->k_tot = p_off; sp->n_groups = ng;
+  sp->n_rounds = 0;
+  for (int z = 0; z < ng; ++z) {   // greedy interval colouring
+    bool used[TC_MAX_GROUPS] = {};
+    for (int y = 0; y < z; ++y) {
+      const bool overlap = sp->g_row_start[y] < sp->g_row_start[z] + sp->g_rows[z] &&
+                           sp->g_row_start[z] < sp->g_row_start[y] + sp->g_rows[y];
+      if (overlap) used[sp->g_round[y]] = true;
+    }
+    int r = 0;
+    while (used[r]) ++r;
+    sp->g_round[z] = r;
+    if (r + 1 > sp->n_rounds) sp->n_rounds = r + 1;
+  }
   const size_t R = (size_t)n_batch * h->ntok, Ld = (size_t)h->L * h->d;
   const unsigned before = h->epoch;
   CFB_TRY(h->uc.reserve(R * CFB_N_STREAMS * h->d * 2, &h->epoch));

@@ -185,55 +185,91 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
       umma_commit(bar_acc);
     }
   } else {
-    // ---- epilogue: thread owns accumulator row (lane quarter q, lane)
+    // ---- epilogue.  tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
+    // (a warp would touch 32 different cache lines per instruction).  The pipeline stages are idle once bar_acc has
+    // fired, so each warp transposes its 32 x BN slab through that shared memory and then walks its rows with the
+    // lanes spread across the columns: every global access of the bias / residual / output is row-contiguous.
     const int q = warp & 3;
+    constexpr int PITCH = BN + 4;              // floats; +4 keeps the 128-bit transposed stores conflict-free
+    constexpr int CPL = BN / 32;               // columns per lane: 4 (BN=128), 2, 1
+    static_assert(4 * 32 * PITCH * 4 <= STAGES * S::STAGE_BYTES, "epilogue staging does not fit in the pipeline smem");
+    float* stg = reinterpret_cast<float*>(gen_base) + q * 32 * PITCH;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    const int r = m0 + q * 32 + lane;
-    const bool row_ok = r < M;
-    const float* brow = (ep.bias && row_ok) ? ep.bias + (size_t)(r % ep.bias_period) * N : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int n = n0 + c * 32;
-      if (!row_ok || n >= N) continue;
-      if (brow) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(brow + n + j);
-          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-        }
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * PITCH + c * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    const int n = n0 + lane * CPL;
+    const int r0 = m0 + q * 32;
+    float bias_v[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) bias_v[i] = (ep.bias && ep.bias_period == 1) ? ep.bias[n + i] : 0.f;
+    const bool out_f32 = !ep.out_bf16;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = r0 + rr;
+      if (r >= M) break;
+      float v[CPL];
+      if constexpr (CPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(stg + rr * PITCH + lane * 4);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else if constexpr (CPL == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(stg + rr * PITCH + lane * 2);
+        v[0] = t.x; v[1] = t.y;
+      } else {
+        v[0] = stg[rr * PITCH + lane];
+      }
+      if (ep.bias && ep.bias_period != 1) {
+        const float* brow = ep.bias + (size_t)(r % ep.bias_period) * N + n;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] += brow[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) v[i] += bias_v[i];
       }
       if (ep.act) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], ep.act);
+        for (int i = 0; i < CPL; ++i) v[i] = act_apply(v[i], ep.act);
       }
       for (int rep = 0; rep < ep.replicate; ++rep) {
         const size_t off = (size_t)rep * ep.rep_stride + (size_t)r * ep.ldo + n;
-        if (ep.out_bf16) {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + off);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j * 8 + 0], v[j * 8 + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j * 8 + 2], v[j * 8 + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j * 8 + 4], v[j * 8 + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j * 8 + 6], v[j * 8 + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            o[j] = pk;
-          }
-        } else {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        if (out_f32) {
+          float* o = reinterpret_cast<float*>(ep.out) + off;
+          if constexpr (CPL == 4) {
+            float4 x = make_float4(v[0], v[1], v[2], v[3]);
             if (ep.accumulate) {
-              const float4 y = o[j];
+              const float4 y = *reinterpret_cast<const float4*>(o);
               x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
             }
-            o[j] = x;
+            *reinterpret_cast<float4*>(o) = x;
+          } else if constexpr (CPL == 2) {
+            float2 x = make_float2(v[0], v[1]);
+            if (ep.accumulate) {
+              const float2 y = *reinterpret_cast<const float2*>(o);
+              x.x += y.x; x.y += y.y;
+            }
+            *reinterpret_cast<float2*>(o) = x;
+          } else {
+            *o = ep.accumulate ? (*o + v[0]) : v[0];
+          }
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
+          if constexpr (CPL == 4) {
+            const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
+            const __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+            *reinterpret_cast<uint2*>(o) = pk;
+          } else if constexpr (CPL == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v[0], v[1]);
+          } else {
+            *o = __float2bfloat16_rn(v[0]);
           }
         }
       }
