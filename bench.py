@@ -161,26 +161,42 @@ def gemm_roofline(torch, lib_mod, batch, n_branch, dev, iters=20):
     evaluation, CUDA events on the launching stream; weights of all 9 layers rotate so operands exceed L2."""
     from convofusion_b200 import _lib
     R, d = batch * n_branch * 16, 512
-    shapes = [(3 * d, d), (d, d), (d, d), (5 * d, d), (d, 5 * d), (d, d), (1024, d), (d, 1024)]
+    # (N, K, epilogue) of the eight full-batch GEMMs of one layer in the shared-slot plan: in_proj, self out_proj,
+    # time_block1, shared scores, shared values, time_block2, linear1 (GELU), linear2.  "res" = fp32 residual update.
+    spec = [(3 * d, d, "bf16"), (d, d, "res"), (d, d, "res"), (320, d, "f32"), (d, 448, "res"), (d, d, "res"),
+            (1024, d, "gelu"), (d, 1024, "res")]
+    shapes = [(n, k) for n, k, _ in spec]
     Ws = [[torch.randn(n, k, device=dev).bfloat16() for (n, k) in shapes] for _ in range(9)]
-    As = {k: torch.randn(R, k, device=dev).bfloat16() for k in (d, 5 * d, 1024)}
-    outs = {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, d, 5 * d, 1024)}
-    st = torch.cuda.current_stream().cuda_stream
+    As = {k: torch.randn(R, k, device=dev).bfloat16() for k in (d, 448, 1024)}
+    outs = {"bf16": {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, 1024)},
+            "f32": {n: torch.zeros(R, n, device=dev) for n in (d, 320)}}
+    side = torch.cuda.Stream(device=dev)
+    st = side.cuda_stream
 
     def one_pass():
         for layer in Ws:
-            for (n, k), w in zip(shapes, layer):
-                _lib.check(_lib.lib().cfb_linear(As[k].data_ptr(), 1, w.data_ptr(), 0, outs[n].data_ptr(), 1, R, n, k, 0, 0, 0,
-                                                 _lib.GEMM_TCGEN05, st))
-    for _ in range(3):
-        one_pass()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        one_pass()
-    e1.record()
-    torch.cuda.synchronize()
+            for (n, k, kind), w in zip(spec, layer):
+                obf = kind in ("bf16", "gelu")
+                out = outs["bf16" if obf else "f32"][n]
+                _lib.check(_lib.lib().cfb_linear(As[k].data_ptr(), 1, w.data_ptr(), 0, out.data_ptr(), int(obf), R, n, k,
+                                                 1 if kind == "gelu" else 0, 0, int(kind == "res"), _lib.GEMM_TCGEN05, st))
+    # An eager launch through ctypes costs ~12 us of host time, more than most of these kernels run, so the pass is
+    # captured into a CUDA graph and replayed: the events below bracket device time only.
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            one_pass()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            one_pass()
+        graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flops = 9 * sum(2.0 * R * n * k for (n, k) in shapes)
     return flops / (ms * 1e-3) / 1e12, ms, 9 * len(shapes)

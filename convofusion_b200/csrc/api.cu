@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 
 int init_gemm_tc_kernels();
 int init_attention_kernels();
+int tc_trace_read(unsigned long long out[16]);
 
 static int ensure_device() {
   int ndev = 0;
@@ -32,6 +33,9 @@ static int ensure_device() {
 using namespace cfb;
 
 extern "C" {
+
+// Debug only (not part of include/convofusion_b200.h): phase timestamps of the last traced tcgen05 GEMM CTA.
+int cfb_debug_tc_trace(unsigned long long* out16) { return cfb::tc_trace_read(out16); }
 
 int cfb_abi_version(void) { return CFB_ABI_VERSION; }
 const char* cfb_last_error(void) { return g_err; }

@@ -244,6 +244,168 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core version of the per-pair attention (bf16): one block per (batch entry, stream), 8 warps.
+//   scores  S[16, M] = Q[16,512] . xhat^T : mma.sync.m16n8k16, A from shared memory (ldmatrix), B fragments
+//           straight from the row-major key rows in global memory (a key row IS a column-major B column);
+//           warp w owns key tiles w, w+8, ...
+//   softmax in fp32 in shared memory -> P (bf16, zero padded to a multiple of 16 keys)
+//   values  U[16,512] = P[16,M] . xhat[M,512] : key tiles of 16 rows are staged with cp.async (double buffered)
+//           and read with ldmatrix.trans; warp w owns output columns [64w, 64w+64).
+// 16-query tiles are exactly one MMA row block, so nothing is wasted on padding.
+constexpr int XP = CROSS_D + 8;   // bf16 row pitch in shared memory: rows shift by 16 B -> conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t r[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__ qx, const bf16* __restrict__ mem_hat,
+                                                        bf16* __restrict__ u, CrossArgs a, int n_tokens, int Sp, int Pp) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int bs = blockIdx.x, x = blockIdx.y;
+  const int M = a.len[x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ld = CFB_N_STREAMS * CROSS_D;
+  const int slot = a.slot[x] ? a.slot[x][bs] : bs;
+  if (a.skip_slot0 && slot == 0) return;   // block-uniform
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);            // [16][XP]
+  bf16* Xs = Qs + 16 * XP;                              // [2][16][XP]
+  float* Ss = reinterpret_cast<float*>(Xs + 2 * 16 * XP);   // [16][Sp]
+  bf16* Ps = reinterpret_cast<bf16*>(Ss + 16 * Sp);     // [16][Pp]
+  const bf16* mem = mem_hat + ((size_t)a.row_base[x] + (size_t)slot * M) * CROSS_D;
+  const uint8_t* msk = a.mask[x] ? a.mask[x] + (size_t)slot * M : nullptr;
+  const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(Qs);
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(Xs);
+  const uint32_t ps_addr = (uint32_t)__cvta_generic_to_shared(Ps);
+
+  // stage Q (zero rows past n_tokens): 16 rows x 64 chunks of 16 B
+  for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+    const int r = i >> 6, ch = i & 63;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < n_tokens) v = *reinterpret_cast<const uint4*>(qx + (size_t)(bs * n_tokens + r) * ld + x * CROSS_D + ch * 8);
+    *reinterpret_cast<uint4*>(Qs + r * XP + ch * 8) = v;
+  }
+  // first value tile in flight while the scores are computed
+  const int nkt = (M + 15) >> 4;
+  auto stage_tile = [&](int kt, int buf) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int r = i >> 6, ch = i & 63;
+      const int j = min(kt * 16 + r, M - 1);
+      cp_async16(xs_addr + (uint32_t)(((buf * 16 + r) * XP + ch * 8) * 2), mem + (size_t)j * CROSS_D + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_tile(0, 0);
+  __syncthreads();
+
+  // ---- scores
+  const int nnt = (M + 7) >> 3;
+  for (int nt = warp; nt < nnt; nt += 8) {
+    const int key0 = nt * 8;
+    const bf16* kp = mem + (size_t)min(key0 + g, M - 1) * CROSS_D + 2 * t;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int kc = 0; kc < 4; ++kc) {            // 4 chunks of 8 k-steps: 16 B-fragment loads in flight per chunk
+      uint32_t b[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        b[2 * i] = *reinterpret_cast<const uint32_t*>(kp + (kc * 8 + i) * 16);
+        b[2 * i + 1] = *reinterpret_cast<const uint32_t*>(kp + (kc * 8 + i) * 16 + 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t af[4];
+        ldsm_x4(af, qs_addr + (uint32_t)(((lane & 15) * XP + (kc * 8 + i) * 16 + (lane >> 4) * 8) * 2));
+        mma_bf16_16816(c, af, b[2 * i], b[2 * i + 1]);
+      }
+    }
+    const int j0 = key0 + 2 * t, j1 = j0 + 1;
+    const bool m0 = j0 >= M || (msk && msk[j0]), m1 = j1 >= M || (msk && msk[min(j1, M - 1)]);
+    Ss[g * Sp + j0] = m0 ? -INFINITY : c[0];
+    Ss[g * Sp + j1] = m1 ? -INFINITY : c[1];
+    Ss[(g + 8) * Sp + j0] = m0 ? -INFINITY : c[2];
+    Ss[(g + 8) * Sp + j1] = m1 ? -INFINITY : c[3];
+  }
+  __syncthreads();
+  // ---- softmax: warp w handles query rows w and w + 8; P is written as bf16, zero beyond M
+  for (int qi = warp; qi < 16; qi += 8) {
+    float* srow = Ss + qi * Sp;
+    bf16* prow = Ps + qi * Pp;
+    if (qi >= n_tokens) {
+      for (int j = lane; j < nkt * 16; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, srow[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < M; j += 32) {
+      const float e = expf(srow[j] - mx);
+      srow[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float* arow = nullptr;
+    if (a.att[x] && bs >= a.att_first_batch) {
+      const long long step_off = a.step_ptr ? (long long)(*a.step_ptr) * a.att_step_stride[x] : 0;
+      arow = a.att[x] + step_off + (long long)(bs - a.att_first_batch) * a.att_batch_stride[x] + (long long)qi * M;
+    }
+    for (int j = lane; j < nkt * 16; j += 32) {
+      float p = 0.f;
+      if (j < M) {
+        p = srow[j] * inv;
+        if (arow) arow[j] = p;
+      }
+      prow[j] = __float2bfloat16_rn(p);
+    }
+  }
+  // ---- values
+  float acc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                         // tile kt landed for everyone; tile kt-1's buffer is free; P is visible
+    if (kt + 1 < nkt) stage_tile(kt + 1, buf ^ 1);
+    uint32_t af[4];
+    ldsm_x4(af, ps_addr + (uint32_t)(((lane & 15) * Pp + kt * 16 + (lane >> 4) * 8) * 2));
+    const int brow = (lane & 7) + ((lane >> 3) & 1) * 8;       // key row inside the tile
+    const int bcol = warp * 64 + (lane >> 4) * 8;              // first of the two 8-column blocks of this x4
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      uint32_t bf[4];
+      ldsm_x4_trans(bf, xs_addr + (uint32_t)(((buf * 16 + brow) * XP + bcol + nn * 16) * 2));
+      mma_bf16_16816(acc[2 * nn], af, bf[0], bf[1]);
+      mma_bf16_16816(acc[2 * nn + 1], af, bf[2], bf[3]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int col = x * CROSS_D + warp * 64 + n * 8 + 2 * t;
+    if (g < n_tokens)
+      *reinterpret_cast<__nv_bfloat162*>(u + (size_t)(bs * n_tokens + g) * ld + col) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
+    if (g + 8 < n_tokens)
+      *reinterpret_cast<__nv_bfloat162*>(u + (size_t)(bs * n_tokens + g + 8) * ld + col) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+  }
+}
+
 constexpr int ATT_MAX_SMEM = 160 * 1024;
 
 // Denoiser self-attention (cross_attention.py:570): 16 tokens, head_dim 128.  One warp owns one
@@ -447,6 +609,7 @@ int init_attention_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   done = true;
@@ -486,6 +649,17 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     CFB_CHECK(a.len[x] > 0, "cross_attention: stream %d has no memory tokens", x);
     if (a.len[x] > maxM) maxM = a.len[x];
+  }
+  if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernel (in-place u == qx is fine: Q is staged before u is written)
+    const int Sp = ((maxM + 7) & ~7) + 8, Pp = ((maxM + 15) & ~15) + 8;
+    const size_t smem_mma = (size_t)3 * 16 * XP * 2 + (size_t)16 * Sp * 4 + (size_t)16 * Pp * 2;
+    // CFB_GEMM_SIMT selects the CUDA-core engines everywhere (tests cross-check the two implementations)
+    if (smem_mma <= (size_t)ATT_MAX_SMEM && g_gemm_backend != CFB_GEMM_SIMT) {
+      dim3 grid(n_batch, CFB_N_STREAMS);
+      cross_mma_kernel<<<grid, 256, smem_mma, st>>>(qx, mem_hat, u, a, n_tokens, Sp, Pp);
+      CFB_LAUNCH_CHECK();
+      return CFB_OK;
+    }
   }
   const size_t smem = ((size_t)QPB * CROSS_D + (size_t)QPB * maxM) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "cross_attention: %d memory tokens exceed the shared-memory budget", maxM);

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <cstring>
+#include <cstdlib>
 
 namespace cfb {
 
@@ -55,6 +56,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// Multicast variants: the data (and the complete_tx on the barrier at the same offset) land in every CTA of `mask`.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -108,6 +122,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#ifndef CFB_TC_TRACE
+#define CFB_TC_TRACE 0
+#endif
+// Debug timeline of CTA (0,0,0): globaltimer ns at the phase boundaries (build with -DCFB_TC_TRACE=1).
+__device__ unsigned long long g_tc_trace[16];
+__device__ __forceinline__ void trace(int slot) {
+  if constexpr (CFB_TC_TRACE != 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      g_tc_trace[slot] = t;
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -118,11 +147,30 @@ struct Smem {
 };
 
 // One 128 x BN output tile: rows [m0, min(m0+128, m_end)), columns [n0, n0+BN).
-template <int BN, int STAGES>
+//
+// Cluster multicast (CN x CM CTAs = CN consecutive n-tiles x CM consecutive m-tiles).  With 128x128 tiles a CTA pulls
+// 32 KB from L2 per 64-deep K block for 1 M MACs (32 MAC/B), and the L2->SM path, not the tensor pipe, bounds the
+// kernel.  The CN CTAs of a cluster row need the SAME A tile and the CM CTAs of a cluster column the SAME B tile, so
+// each CTA loads only a 1/CN slice of A and a 1/CM slice of B and TMA-multicasts it into every sharer's shared
+// memory (same offset, each sharer's own `full` barrier).  A stage may be overwritten only when every CTA that
+// receives data from this producer has consumed it, so consumers release a stage with a multicast tcgen05.commit to
+// the `empty` barrier of all CN + CM - 1 CTAs that feed them.
+template <int BN, int STAGES, int CN = 1, int CM = 1>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const int m0,
                                           const int M /* first row NOT to store */, const int n0, const int N,
                                           const int K, const Epilogue& ep) {
   using S = Smem<BN, STAGES>;
+  constexpr int CL = CN * CM;
+  uint32_t crank = 0;
+  if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint32_t rn = crank % CN, rm = crank / CN;
+  // CTAs sharing my A tile (same rm) and my B tile (same rn); their union feeds / is fed by me
+  uint32_t mask_a = 0, mask_b = 0;
+#pragma unroll
+  for (int i = 0; i < CN; ++i) mask_a |= 1u << (rm * CN + i);
+#pragma unroll
+  for (int j = 0; j < CM; ++j) mask_b |= 1u << (rn + j * CN);
+  const uint16_t mask_u = (uint16_t)(mask_a | mask_b);
   const CUtensorMap& tmA = *tmA_p;
   const CUtensorMap& tmB = *tmB_p;
   extern __shared__ uint8_t smem_raw[];
@@ -136,34 +184,50 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = K / BK;
+  if (threadIdx.x == 0) trace(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
-      mbar_init(bar_empty + s * 8, 1);
+      mbar_init(bar_empty + s * 8, CN + CM - 1);   // one release per CTA that consumes data I produce
     }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) {   // barriers of every CTA must be initialised before a peer multicasts into them
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  if (threadIdx.x == 0) trace(1);
 
   if (warp == 0) {
     if (lane == 0) {
+      constexpr int A_SLICE = BM / CN, B_SLICE = BN / CM;   // rows this CTA loads for its sharers
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + s * 8, ph ^ 1);
         const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
         mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
-        tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
-        tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
+        if constexpr (CN > 1)
+          tma_load_2d_mc(sa + rn * (A_SLICE * BK * 2), &tmA, kb * BK, m0 + (int)rn * A_SLICE, bar_full + s * 8, (uint16_t)mask_a);
+        else
+          tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
+        if constexpr (CM > 1)
+          tma_load_2d_mc(sb + rm * (B_SLICE * BK * 2), &tmB, kb * BK, n0 + (int)rm * B_SLICE, bar_full + s * 8, (uint16_t)mask_b);
+        else
+          tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
+        if (kb == 0) trace(2);
       }
+      trace(3);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -173,6 +237,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_full + s * 8, ph);
         tc_fence_after();
+        if (kb == 0) trace(4);
         const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
         const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
@@ -180,9 +245,12 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
           // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (addr >> 4) field
           umma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
-        umma_commit(bar_empty + s * 8);  // frees the smem slot once these MMAs retire
+        // frees the smem slot once these MMAs retire -- in my own CTA and in every CTA that feeds me
+        if constexpr (CL > 1) umma_commit_mc(bar_empty + s * 8, mask_u);
+        else umma_commit(bar_empty + s * 8);
       }
       umma_commit(bar_acc);
+      trace(5);
     }
   } else {
     // ---- epilogue.  tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
@@ -196,6 +264,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     float* stg = reinterpret_cast<float*>(gen_base) + q * 32 * PITCH;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) trace(6);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -205,89 +274,131 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         *reinterpret_cast<float4*>(stg + lane * PITCH + c * 32 + j * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
     __syncwarp();
+    if (warp == 2 && lane == 0) trace(7);
     const int n = n0 + lane * CPL;
     const int r0 = m0 + q * 32;
     float bias_v[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) bias_v[i] = (ep.bias && ep.bias_period == 1) ? ep.bias[n + i] : 0.f;
     const bool out_f32 = !ep.out_bf16;
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = r0 + rr;
-      if (r >= M) break;
-      float v[CPL];
-      if constexpr (CPL == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(stg + rr * PITCH + lane * 4);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else if constexpr (CPL == 2) {
-        const float2 t = *reinterpret_cast<const float2*>(stg + rr * PITCH + lane * 2);
-        v[0] = t.x; v[1] = t.y;
-      } else {
-        v[0] = stg[rr * PITCH + lane];
+    // Rows are processed RB at a time in three separate phases -- gather (shared-memory slab, residual, periodic
+    // bias), compute, scatter -- so the RB global loads of a batch are all in flight together.  Interleaving load and
+    // store per row serialises on the store->load ordering the compiler must assume (12 us instead of 1 us per tile).
+    constexpr int RB = 8;
+    const bool do_acc = out_f32 && ep.accumulate;
+    const bool row_bias = ep.bias && ep.bias_period != 1;
+#pragma unroll 1
+    for (int rb = 0; rb < 32; rb += RB) {
+      float v[RB][CPL], res[RB][CPL];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int rr = rb + i;
+        if constexpr (CPL == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(stg + rr * PITCH + lane * 4);
+          v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+        } else if constexpr (CPL == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(stg + rr * PITCH + lane * 2);
+          v[i][0] = t.x; v[i][1] = t.y;
+        } else {
+          v[i][0] = stg[rr * PITCH + lane];
+        }
       }
-      if (ep.bias && ep.bias_period != 1) {
-        const float* brow = ep.bias + (size_t)(r % ep.bias_period) * N + n;
+      if (do_acc) {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] += brow[i];
+        for (int i = 0; i < RB; ++i) {
+          const int r = r0 + rb + i;
+          if (r < M) {
+            const float* o = reinterpret_cast<const float*>(ep.out) + (size_t)r * ep.ldo + n;
+            if constexpr (CPL == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(o);
+              res[i][0] = t.x; res[i][1] = t.y; res[i][2] = t.z; res[i][3] = t.w;
+            } else if constexpr (CPL == 2) {
+              const float2 t = *reinterpret_cast<const float2*>(o);
+              res[i][0] = t.x; res[i][1] = t.y;
+            } else {
+              res[i][0] = *o;
+            }
+          }
+        }
+      }
+      if (row_bias) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = r0 + rb + i;
+          if (r < M) {
+            const float* brow = ep.bias + (size_t)(r % ep.bias_period) * N + n;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) v[i][c] += brow[c];
+          }
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] += bias_v[i];
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) v[i][c] += bias_v[c];
       }
       if (ep.act) {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] = act_apply(v[i], ep.act);
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) v[i][c] = act_apply(v[i][c], ep.act);
+      }
+      if (do_acc) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) v[i][c] += res[i][c];
       }
       for (int rep = 0; rep < ep.replicate; ++rep) {
-        const size_t off = (size_t)rep * ep.rep_stride + (size_t)r * ep.ldo + n;
-        if (out_f32) {
-          float* o = reinterpret_cast<float*>(ep.out) + off;
-          if constexpr (CPL == 4) {
-            float4 x = make_float4(v[0], v[1], v[2], v[3]);
-            if (ep.accumulate) {
-              const float4 y = *reinterpret_cast<const float4*>(o);
-              x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-            }
-            *reinterpret_cast<float4*>(o) = x;
-          } else if constexpr (CPL == 2) {
-            float2 x = make_float2(v[0], v[1]);
-            if (ep.accumulate) {
-              const float2 y = *reinterpret_cast<const float2*>(o);
-              x.x += y.x; x.y += y.y;
-            }
-            *reinterpret_cast<float2*>(o) = x;
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = r0 + rb + i;
+          if (r >= M) continue;
+          const size_t off = (size_t)rep * ep.rep_stride + (size_t)r * ep.ldo + n;
+          if (out_f32) {
+            float* o = reinterpret_cast<float*>(ep.out) + off;
+            if constexpr (CPL == 4) *reinterpret_cast<float4*>(o) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+            else if constexpr (CPL == 2) *reinterpret_cast<float2*>(o) = make_float2(v[i][0], v[i][1]);
+            else *o = v[i][0];
           } else {
-            *o = ep.accumulate ? (*o + v[0]) : v[0];
-          }
-        } else {
-          bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
-          if constexpr (CPL == 4) {
-            const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
-            const __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
-            *reinterpret_cast<uint2*>(o) = pk;
-          } else if constexpr (CPL == 2) {
-            *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v[0], v[1]);
-          } else {
-            *o = __float2bfloat16_rn(v[0]);
+            bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
+            if constexpr (CPL == 4) {
+              const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i][0], v[i][1]);
+              const __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i][2], v[i][3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+              *reinterpret_cast<uint2*>(o) = pk;
+            } else if constexpr (CPL == 2) {
+              *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v[i][0], v[i][1]);
+            } else {
+              *o = __float2bfloat16_rn(v[i][0]);
+            }
           }
         }
       }
     }
   }
+  if (warp == 2 && lane == 0) trace(8);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) {   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) trace(9);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, BN);
+    if (lane == 0) trace(10);
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, int CN, int CM>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, int M, int N,
                                                            int K, Epilogue ep) {
-  gemm_tile<BN, STAGES>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, CN, CM>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 // Grouped launch: blockIdx.z picks a group = (A map, B map, row block, bias, output).  All groups share N, K and
@@ -303,7 +414,7 @@ struct GroupedArgs {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_grouped_kernel(const __grid_constant__ GroupedArgs g, int N, int K,
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_kernel(const __grid_constant__ GroupedArgs g, int N, int K,
                                                                    Epilogue ep) {
   const int z = blockIdx.z;
   const int m0 = g.row_start[z] + blockIdx.y * BM;
@@ -375,15 +486,25 @@ int get_map(const bf16* p, int rows, int cols, int ld, int box_rows, CUtensorMap
   return CFB_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CN, int CM>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep,
            cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   CUtensorMap ta, tb;
-  CFB_TRY(get_map(A, M, K, lda, BM, &ta));
-  CFB_TRY(get_map(W, w_rows, K, ldw, BN, &tb));   // rows past w_rows read as zeros (TMA out-of-bounds fill)
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+  CFB_TRY(get_map(A, M, K, lda, BM / CN, &ta));          // each CTA loads (and multicasts) a 1/CN slice of the A tile
+  CFB_TRY(get_map(W, w_rows, K, ldw, BN / CM, &tb));     // rows past w_rows read as zeros (TMA out-of-bounds fill)
+  dim3 grid(ceil_div(N, BN), ceil_div(ceil_div(M, BM), CM) * CM);   // whole clusters; surplus m-tiles store nothing
+  if constexpr (CN * CM == 1) {
+    gemm_tc_kernel<BN, STAGES, 1, 1><<<grid, NTHREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CN; attr[0].val.clusterDim.y = CM; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CN, CM>, ta, tb, M, N, K, ep));
+  }
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -411,12 +532,24 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
 
 }  // namespace
 
+int g_tc_cluster = 11;   // 10*CN_max + CM_max; 11 = no clusters
+
+int tc_trace_read(unsigned long long out[16]) {
+  CFB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 16));
+  return CFB_OK;
+}
+
 int init_gemm_tc_kernels() {
   static bool done = false;
   if (done) return CFB_OK;
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  if (const char* e = getenv("CFB_TC_CLUSTER")) g_tc_cluster = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   done = true;
   return CFB_OK;
@@ -443,9 +576,21 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
   if (w_rows <= 0 || w_rows > N) w_rows = N;
-  if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-  if (N % 64 == 0) return launch<64, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-  return launch<32, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  if (N % 128 == 0) {
+    // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.
+    // Multicast pays when several tiles share an operand; a single m-tile (tiny M) gains nothing from CM.
+    const int n_tiles = N / 128, m_tiles = ceil_div(M, BM);
+    const int cn_max = g_tc_cluster / 10, cm_max = g_tc_cluster % 10;
+    const int cn = (cn_max >= 4 && n_tiles % 4 == 0) ? 4 : ((cn_max >= 2 && n_tiles % 2 == 0) ? 2 : 1);
+    const int cm = (cm_max >= 2 && m_tiles >= 2 && w_rows == N) ? 2 : 1;
+    if (cn == 4 && cm == 2) return launch<128, 3, 4, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+    if (cn == 2 && cm == 2) return launch<128, 3, 2, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+    if (cn == 4) return launch<128, 3, 4, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+    if (cn == 2) return launch<128, 3, 2, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+    return launch<128, 3, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  }
+  if (N % 64 == 0) return launch<64, 4, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  return launch<32, 4, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
 }
 
 int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,

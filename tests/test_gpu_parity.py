@@ -77,6 +77,34 @@ def test_denoiser_forward_bf16_tolerance():
     assert err < BF16_TOL["eps_l2"]
 
 
+def test_bf16_forward_tensor_core_engines_vs_cuda_core_engines():
+    """Same bf16 operands through (a) tcgen05 GEMMs + mma.sync attention and (b) the CUDA-core GEMM + attention
+    kernels: one evaluation with ragged masks, attention maps included; only summation order / intermediate
+    rounding may differ."""
+    s = gpu_sampler("bf16")
+    syn = synthetic_clip(3, seed=78, dyadic=True)
+    enc, masks = gpu_batch(s, syn)
+    enc7, masks7 = expand_guidance_batch(enc, masks, 3)
+    x = torch.randn(21, 16, 128, generator=torch.Generator().manual_seed(6)).to(DEV)
+    eps_tc, att_tc = s.denoiser(x, torch.tensor(500), enc7, None, masks7)
+    _lib.check(_lib.lib().cfb_set_gemm_backend(_lib.GEMM_SIMT))
+    try:
+        eps_cc, att_cc = s.denoiser(x, torch.tensor(500), enc7, None, masks7)
+    finally:
+        _lib.check(_lib.lib().cfb_set_gemm_backend(_lib.GEMM_AUTO))
+    o_enc, o_masks = oracle_batch(syn)
+    want, watt = oracle_denoise(x.cpu(), 500, o_enc, o_masks)
+    e_tc, e_cc = rel_err(eps_tc.cpu(), want), rel_err(eps_cc.cpu(), want)
+    print(f"bf16 eps L2 vs oracle: tensor-core {e_tc:.2e}, cuda-core {e_cc:.2e}; tc-vs-cc {rel_err(eps_tc, eps_cc):.2e}")
+    assert e_tc < BF16_TOL["eps_l2"] and e_cc < BF16_TOL["eps_l2"] and e_tc < 2 * e_cc + 1e-3
+    for i in range(5):
+        # bf16 scores (|s| up to ~10, 0.4 % operand rounding) move individual probabilities by up to ~15 % in deep layers
+        assert max_rel(att_tc[i].cpu(), watt[i]) < 0.3, i
+        assert max_rel(att_tc[i].cpu(), att_cc[i].cpu()) < 0.3, i
+        assert float(att_tc[i].sum(-1).sub(1).abs().max()) < 1e-4
+    assert float(att_tc[2][masks7["tlsn"][:, None, None, :].expand_as(att_tc[2])].abs().max()) == 0.0
+
+
 def test_ragged_and_edge_inputs():
     """Ragged text lengths per clip, a clip whose listener text has one valid token, B not a tile multiple."""
     s = gpu_sampler("fp32")
