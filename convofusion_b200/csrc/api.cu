@@ -1,11 +1,13 @@
 // Library-level C ABI: error reporting, switches, and the unit-op entry points the tests use.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace cfb {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
+int g_use_pdl = getenv("CFB_PDL") ? atoi(getenv("CFB_PDL")) : 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(128) mha_kernel(const T* __restrict__ q, int l
                                                   const T* __restrict__ v, int ldk, T* __restrict__ out, int ldo,
                                                   int Lq, int Lk, int hd, const int* __restrict__ kv_len,
                                                   int q_per_block) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int b = blockIdx.x, h = blockIdx.y, q0 = blockIdx.z * q_per_block;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,6 +105,7 @@ constexpr int QPB = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, const T* __restrict__ mem_hat,
                                                     T* __restrict__ u, CrossArgs a, int n_tokens) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int bs = blockIdx.x, x = blockIdx.y, q0 = blockIdx.z * QPB;
   const int M = a.len[x];
@@ -275,6 +277,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__ qx, const bf16* __restrict__ mem_hat,
                                                         bf16* __restrict__ u, CrossArgs a, int n_tokens, int Sp, int Pp) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int bs = blockIdx.x, x = blockIdx.y;
   const int M = a.len[x];
@@ -417,6 +420,7 @@ constexpr int SA_L = 16, SA_HD = 128, SA_PITCH = 132;
 template <typename T>
 __global__ void __launch_bounds__(128) self_attn16_kernel(const T* __restrict__ qkv, int ld, int E,
                                                           T* __restrict__ out, int ldo, int n_heads) {
+  pdl_sync();
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y * 4 + warp;
@@ -506,6 +510,7 @@ constexpr int SA_SMEM = 4 * 3 * SA_L * SA_PITCH * (int)sizeof(float);   // 101,3
 // One warp per query row; see SharedAttnArgs.
 __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __restrict__ S, bf16* __restrict__ P,
                                                              SharedAttnArgs a, int rows, int n_tokens) {
+  pdl_sync();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
   const int bs = r / n_tokens;
@@ -551,6 +556,7 @@ struct Z0Args {
 };
 __global__ void __launch_bounds__(256) z0_kernel(const bf16* __restrict__ mem_hat, float* __restrict__ z0, Z0Args a,
                                                  int n_layers, int n_tot) {
+  pdl_sync();
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (t >= a.tok_base[CFB_N_STREAMS]) return;
   int x = 0;
@@ -585,7 +591,7 @@ int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_
     a.tok_base[x] = tok; tok += len[x];
   }
   a.tok_base[CFB_N_STREAMS] = tok;
-  z0_kernel<<<ceil_div(tok, 8), 256, 0, st>>>(mem_hat, z0, a, n_layers, n_tot);
+  launch_k(z0_kernel, ceil_div(tok, 8), 256, 0, st, mem_hat, z0, a, n_layers, n_tot);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -593,7 +599,7 @@ int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_
 int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
   const int rows = n_batch * n_tokens;
   if (rows <= 0) return CFB_OK;
-  softmax_shared_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(S, P, a, rows, n_tokens);
+  launch_k(softmax_shared_kernel, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -625,7 +631,7 @@ int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, i
   if (Lq == SA_L && Lk == SA_L && head_dim == SA_HD && kv_len == nullptr && ldq == ldk &&
       k == q + n_heads * head_dim && v == q + 2 * n_heads * head_dim && ldq % 4 == 0 && ldo % 4 == 0) {
     dim3 grid(n, ceil_div(n_heads, 4));
-    self_attn16_kernel<T><<<grid, 128, SA_SMEM, st>>>(q, ldq, n_heads * head_dim, out, ldo, n_heads);
+    launch_k(self_attn16_kernel<T>, grid, 128, SA_SMEM, st, q, ldq, n_heads * head_dim, out, ldo, n_heads);
     CFB_LAUNCH_CHECK();
     return CFB_OK;
   }
@@ -633,7 +639,7 @@ int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, i
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "mha: Lk=%d head_dim=%d needs %zu B of shared memory", Lk, head_dim, smem);
   const int q_per_block = Lq >= 64 ? 32 : Lq;
   dim3 grid(n, n_heads, ceil_div(Lq, q_per_block));
-  mha_kernel<T><<<grid, 128, smem, st>>>(q, ldq, k, v, ldk, out, ldo, Lq, Lk, head_dim, kv_len, q_per_block);
+  launch_k(mha_kernel<T>, grid, 128, smem, st, q, ldq, k, v, ldk, out, ldo, Lq, Lk, head_dim, kv_len, q_per_block);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -656,7 +662,7 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
     // CFB_GEMM_SIMT selects the CUDA-core engines everywhere (tests cross-check the two implementations)
     if (smem_mma <= (size_t)ATT_MAX_SMEM && g_gemm_backend != CFB_GEMM_SIMT) {
       dim3 grid(n_batch, CFB_N_STREAMS);
-      cross_mma_kernel<<<grid, 256, smem_mma, st>>>(qx, mem_hat, u, a, n_tokens, Sp, Pp);
+      launch_k(cross_mma_kernel, grid, 256, smem_mma, st, qx, mem_hat, u, a, n_tokens, Sp, Pp);
       CFB_LAUNCH_CHECK();
       return CFB_OK;
     }
@@ -664,7 +670,7 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
   const size_t smem = ((size_t)QPB * CROSS_D + (size_t)QPB * maxM) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "cross_attention: %d memory tokens exceed the shared-memory budget", maxM);
   dim3 grid(n_batch, CFB_N_STREAMS, ceil_div(n_tokens, QPB));
-  cross_kernel<T><<<grid, 256, smem, st>>>(qx, mem_hat, u, a, n_tokens);
+  launch_k(cross_kernel<T>, grid, 256, smem, st, qx, mem_hat, u, a, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }

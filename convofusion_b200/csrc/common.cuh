@@ -51,6 +51,28 @@ extern unsigned long long g_launches;
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch.  Every kernel of this library starts with pdl_sync() (tcgen05 GEMM: after its
+// shared-memory/TMEM prologue): `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as all of this
+// kernel's CTAs have started, `wait` blocks until the PREVIOUS kernel has completed and its writes are visible.
+// With ~190 kernels of 3-10 us per sampling step this hides launch latency and prologues behind predecessors' tails.
+extern int g_use_pdl;
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }

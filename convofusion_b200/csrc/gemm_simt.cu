@@ -40,6 +40,7 @@ template <typename TA, typename TW>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A, int lda,
                                                         const TW* __restrict__ W, int ldw, int M, int N,
                                                         int K, int a_act, bool vec_a, bool vec_w, Epilogue ep) {
+  pdl_sync();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Ws[BK][BN + PAD];
   const int t = threadIdx.x;
@@ -108,13 +109,13 @@ int gemm_simt(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int
   const bool vec_a = ((uintptr_t)A % (4 * ea) == 0) && (lda % 4 == 0);
   const bool vec_w = ((uintptr_t)W % (4 * ew) == 0) && (ldw % 4 == 0);
   if (a_bf16 && w_bf16)
-    gemm_simt_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
+    launch_k(gemm_simt_kernel<bf16, bf16>, grid, 256, 0, st, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
   else if (!a_bf16 && !w_bf16)
-    gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
+    launch_k(gemm_simt_kernel<float, float>, grid, 256, 0, st, (const float*)A, lda, (const float*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
   else if (a_bf16 && !w_bf16)
-    gemm_simt_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)A, lda, (const float*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
+    launch_k(gemm_simt_kernel<bf16, float>, grid, 256, 0, st, (const bf16*)A, lda, (const float*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
   else
-    gemm_simt_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)A, lda, (const bf16*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
+    launch_k(gemm_simt_kernel<float, bf16>, grid, 256, 0, st, (const float*)A, lda, (const bf16*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }

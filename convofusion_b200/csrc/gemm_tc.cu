@@ -206,6 +206,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
   }
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  pdl_sync();   // everything above touched only shared/tensor memory; operands of the previous kernel are read below
   if (threadIdx.x == 0) trace(1);
 
   if (warp == 0) {
@@ -495,7 +496,7 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, in
   CFB_TRY(get_map(W, w_rows, K, ldw, BN / CM, &tb));     // rows past w_rows read as zeros (TMA out-of-bounds fill)
   dim3 grid(ceil_div(N, BN), ceil_div(ceil_div(M, BM), CM) * CM);   // whole clusters; surplus m-tiles store nothing
   if constexpr (CN * CM == 1) {
-    gemm_tc_kernel<BN, STAGES, 1, 1><<<grid, NTHREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+    launch_k(gemm_tc_kernel<BN, STAGES, 1, 1>, grid, NTHREADS, S::TOTAL, st, ta, tb, M, N, K, ep);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
@@ -525,7 +526,7 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
   }
   if (max_rows <= 0) return CFB_OK;
   dim3 grid(ceil_div(N, BN), ceil_div(max_rows, BM), n_groups);
-  gemm_tc_grouped_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(g, N, K, ep);
+  launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }

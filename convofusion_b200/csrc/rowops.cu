@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
                                                       const float* __restrict__ b, const float* __restrict__ mod,
                                                       const int* __restrict__ step_ptr, long long mod_step_stride,
                                                       T* __restrict__ out, int rows) {
+  pdl_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   RowVec<D> r;
@@ -103,6 +104,7 @@ struct MemBuildArgs {
 template <int D>
 __global__ void __launch_bounds__(256) mem_build_kernel(MemBuildArgs a, const float* __restrict__ stream_emb,
                                                         const float* __restrict__ pe, float* __restrict__ mem_c) {
+  pdl_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= a.row_base[CFB_N_STREAMS]) return;
   int x = 0;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) mem_build_kernel(MemBuildArgs a, const fl
 template <typename T, int D>
 __global__ void __launch_bounds__(256) mem_hat_kernel(const float* __restrict__ mem_c, const float* __restrict__ temb,
                                                       const int* __restrict__ step_ptr, T* __restrict__ out, int rows) {
+  pdl_sync();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   RowVec<D> r;
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256) mem_hat_kernel(const float* __restrict__ 
 
 // embeddings.py:245-285 with flip_sin_to_cos=True, freq_shift=0: [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k / half)
 __global__ void time_sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= n * half) return;
@@ -145,6 +149,7 @@ __global__ void time_sinusoid_kernel(const float* __restrict__ t, float* __restr
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = from_f32<T>(in[i]);
 }
@@ -153,6 +158,7 @@ __global__ void cast_kernel(const float* __restrict__ in, T* __restrict__ out, l
 template <typename T>
 __global__ void concat2_kernel(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ out,
                                int rows, int d) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * 2 * d) return;
   const int r = (int)(i / (2 * d)), c = (int)(i % (2 * d));
@@ -163,6 +169,7 @@ __global__ void concat2_kernel(const float* __restrict__ a, const float* __restr
 template <typename T>
 __global__ void add_pe_kernel(const float* __restrict__ src, const float* __restrict__ pe, T* __restrict__ out,
                               int n_batch, int L, int d) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_batch * L * d) return;
   const int c = (int)(i % d);
@@ -173,6 +180,7 @@ __global__ void add_pe_kernel(const float* __restrict__ src, const float* __rest
 
 // vae.py:362: zero frames at or beyond each clip's length.
 __global__ void mask_frames_kernel(float* __restrict__ out, const int* __restrict__ lengths, int n_batch, int L, int d) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_batch * L * d) return;
   const int l = (int)((i / d) % L), b = (int)(i / ((long long)d * L));
@@ -186,8 +194,8 @@ int ln_rows(const float* x, const float* g, const float* b, const float* mod, co
             long long mod_step_stride, T* out, int rows, int d, cudaStream_t st) {
   if (rows <= 0) return CFB_OK;
   dim3 grid(ceil_div(rows, 8));
-  if (d == 512) ln_rows_kernel<T, 512><<<grid, 256, 0, st>>>(x, g, b, mod, step_ptr, mod_step_stride, out, rows);
-  else if (d == 128) ln_rows_kernel<T, 128><<<grid, 256, 0, st>>>(x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+  if (d == 512) launch_k(ln_rows_kernel<T, 512>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+  else if (d == 128) launch_k(ln_rows_kernel<T, 128>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
   else { set_error("ln_rows: d_model %d unsupported (128 or 512)", d); return CFB_ERR_INVALID; }
   CFB_LAUNCH_CHECK();
   return CFB_OK;
@@ -206,7 +214,7 @@ int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_ST
   }
   a.row_base[CFB_N_STREAMS] = base;
   if (base == 0) return CFB_OK;
-  mem_build_kernel<512><<<ceil_div(base, 8), 256, 0, st>>>(a, stream_emb, pe, mem_c);
+  launch_k(mem_build_kernel<512>, ceil_div(base, 8), 256, 0, st, a, stream_emb, pe, mem_c);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -215,7 +223,7 @@ template <typename T>
 int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st) {
   CFB_CHECK(d == 512, "mem_hat: d_model %d unsupported", d);
   if (rows <= 0) return CFB_OK;
-  mem_hat_kernel<T, 512><<<ceil_div(rows, 8), 256, 0, st>>>(mem_c, temb, step_ptr, out, rows);
+  launch_k(mem_hat_kernel<T, 512>, ceil_div(rows, 8), 256, 0, st, mem_c, temb, step_ptr, out, rows);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -224,7 +232,7 @@ template int mem_hat<bf16>(const float*, const float*, const int*, bf16*, int, i
 
 int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st) {
   const int total = n * (dim / 2);
-  time_sinusoid_kernel<<<ceil_div(total, 256), 256, 0, st>>>(t, out, n, dim);
+  launch_k(time_sinusoid_kernel, ceil_div(total, 256), 256, 0, st, t, out, n, dim);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -232,7 +240,7 @@ int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st) {
 template <typename T>
 int cast_rows(const float* in, T* out, long long n, cudaStream_t st) {
   if (n <= 0) return CFB_OK;
-  cast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  launch_k(cast_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, st, in, out, n);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -242,7 +250,7 @@ template int cast_rows<bf16>(const float*, bf16*, long long, cudaStream_t);
 template <typename T>
 int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st) {
   const long long n = (long long)rows * 2 * d;
-  concat2_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, out, rows, d);
+  launch_k(concat2_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, st, a, b, out, rows, d);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -252,7 +260,7 @@ template int concat2<bf16>(const float*, const float*, bf16*, int, int, cudaStre
 template <typename T>
 int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d, cudaStream_t st) {
   const long long n = (long long)n_batch * L * d;
-  add_pe_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, pe, out, n_batch, L, d);
+  launch_k(add_pe_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, st, src, pe, out, n_batch, L, d);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -261,7 +269,7 @@ template int add_pe<bf16>(const float*, const float*, bf16*, int, int, int, cuda
 
 int mask_frames(float* out, const int* lengths, int n_batch, int L, int d, cudaStream_t st) {
   const long long n = (long long)n_batch * L * d;
-  mask_frames_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, lengths, n_batch, L, d);
+  launch_k(mask_frames_kernel, (unsigned)((n + 255) / 256), 256, 0, st, out, lengths, n_batch, L, d);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }

@@ -12,6 +12,7 @@ namespace cfb {
 namespace {
 
 __global__ void __launch_bounds__(256) guidance_sched_kernel(StepArgs a) {
+  pdl_sync();
   const int total = a.n_clips * a.n_per_clip;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) guidance_sched_kernel(StepArgs a) {
 
 __global__ void inpaint_first_kernel(float* x, const float* preseq, float* inp_noise, const float* coef, int n_clips,
                                      int n_per_clip, int n_inpaint) {
+  pdl_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_clips * n_inpaint) return;
   const int b = j / n_inpaint, within = j % n_inpaint;
@@ -59,7 +61,8 @@ __global__ void inpaint_first_kernel(float* x, const float* preseq, float* inp_n
   inp_noise[j] = v;
 }
 
-__global__ void step_inc_kernel(int* p) { *p += 1; }
+__global__ void step_inc_kernel(int* p) {
+  pdl_sync(); *p += 1; }
 
 }  // namespace
 
@@ -67,10 +70,10 @@ int guidance_sched_step(const StepArgs& a, cudaStream_t st) {
   const int total = a.n_clips * a.n_per_clip;
   if (total <= 0) return CFB_OK;
   CFB_CHECK(a.n_branch == 1 || a.n_branch == 6 || a.n_branch == CFB_N_BRANCH, "guidance: n_branch must be 1, 6 or 7");
-  guidance_sched_kernel<<<ceil_div(total, 256), 256, 0, st>>>(a);
+  launch_k(guidance_sched_kernel, ceil_div(total, 256), 256, 0, st, a);
   CFB_LAUNCH_CHECK();
   if (a.step_inc) {
-    step_inc_kernel<<<1, 1, 0, st>>>(a.step_inc);
+    launch_k(step_inc_kernel, 1, 1, 0, st, a.step_inc);
     CFB_LAUNCH_CHECK();
   }
   return CFB_OK;
@@ -80,7 +83,7 @@ int inpaint_first(float* x, const float* preseq, float* inp_noise, const float* 
                   int n_inpaint, cudaStream_t st) {
   const int total = n_clips * n_inpaint;
   if (total <= 0) return CFB_OK;
-  inpaint_first_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, preseq, inp_noise, coef, n_clips, n_per_clip, n_inpaint);
+  launch_k(inpaint_first_kernel, ceil_div(total, 256), 256, 0, st, x, preseq, inp_noise, coef, n_clips, n_per_clip, n_inpaint);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
