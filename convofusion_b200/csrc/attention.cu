@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
                                                     T* __restrict__ u, CrossArgs a, int n_tokens) {
   pdl_sync();
   extern __shared__ float sm[];
-  const int bs = blockIdx.x, x = blockIdx.y, q0 = blockIdx.z * QPB;
+  const int bs = blockIdx.x + a.bs_offset, x = blockIdx.y, q0 = blockIdx.z * QPB;
   const int M = a.len[x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = CFB_N_STREAMS * CROSS_D;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
                                                         bf16* __restrict__ u, CrossArgs a, int n_tokens, int Sp, int Pp) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t smraw[];
-  const int bs = blockIdx.x, x = blockIdx.y;
+  const int bs = blockIdx.x + a.bs_offset, x = blockIdx.y;
   const int M = a.len[x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __rest
   pdl_sync();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
-  const int bs = r / n_tokens;
+  const int bs = r / n_tokens + a.bs_offset;
 #pragma unroll
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     bf16* prow = P + (size_t)r * a.ld_p + a.p_off[x];

@@ -112,6 +112,15 @@ struct Epilogue {
   int ldo;
   int replicate;       // write `replicate` copies, copy c at out + c * rep_stride elements
   long long rep_stride;
+  // Fused LayerNorm of the UPDATED rows (tcgen05 path, float out with ldo == N == 512): the CTA that finishes a
+  // 128-row block last (per-block counter) normalises those rows of `out` and writes the next GEMM's bf16 operand:
+  // ln_out = LN(out) * ln_g + ln_b, optionally followed by TimeBlock modulation * (1 + scale) + shift and SiLU.
+  bf16* ln_out;              // nullptr = no fused LayerNorm
+  const float* ln_g; const float* ln_b;
+  const float* ln_mod;       // [scale(512) | shift(512)] or nullptr
+  const int* ln_step;        // device step counter selecting the modulation row, or nullptr
+  long long ln_mod_stride;
+  int* ln_counters;          // one int per 128-row block, zero before the launch; reset by the kernel
 };
 
 // GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace cfb {
 
@@ -49,7 +50,7 @@ struct cfb_denoiser {
   int d, lat, ntok, L, H, ff, prec;
   unsigned epoch = 0;
   DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
-      preseq, slots, masks, uc, sS, sP, zall, z0all, ytall;
+      preseq, slots, masks, uc, sS, sP, zall, z0all, ytall, lncnt;
   // cached CUDA graph of one sampling step
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey {
@@ -63,6 +64,11 @@ struct cfb_denoiser {
   // The legacy default stream cannot be captured: graph mode on it runs on this private stream, fenced by events.
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // Concurrent chains of the sampling step (independent groups of batch entries on forked streams)
+  static constexpr int MAX_CHAINS = 8;
+  cudaStream_t chain_st[MAX_CHAINS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
+  int n_chains = 1;
 };
 
 namespace {
@@ -121,16 +127,24 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
   return shared_key_bias(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
 }
 
+// Runs the 9 layers + final projection for the batch entries [b0, b0 + n_batch) (a "chain").  Rows of different batch
+// entries never interact, so disjoint chains may run concurrently on different streams; they share only read-only
+// data (weights, mem_hat, zall / ytall / z0all).  n_batch_total = entries of the whole call (tensor-map extents).
 template <typename T>
 int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
-               float* eps_out, cudaStream_t st, const SharedPlan* sp = nullptr) {
-  const int R = n_batch * h->ntok, d = h->d;
+               float* eps_out_all, cudaStream_t st, const SharedPlan* sp = nullptr, int b0 = 0, int n_batch_total = 0) {
+  if (n_batch_total <= 0) n_batch_total = n_batch;
+  const int R = n_batch * h->ntok, d = h->d, row0 = b0 * h->ntok, R_total = n_batch_total * h->ntok;
   const int tb = sizeof(T) == 2;
-  float* hres = h->h.as<float>();
-  T* a = h->a.as<T>();
-  T* qkv = h->qkv.as<T>();
-  T* qx = h->qx.as<T>();
-  T* f = h->f.as<T>();
+  float* hres = h->h.as<float>() + (size_t)row0 * d;
+  T* a_abs = h->a.as<T>();
+  T* qx_abs = h->qx.as<T>();
+  T* a = a_abs + (size_t)row0 * d;
+  T* qkv = h->qkv.as<T>() + (size_t)row0 * 3 * d;
+  T* qx = qx_abs + (size_t)row0 * CFB_N_STREAMS * d;
+  T* f = h->f.as<T>() + (size_t)row0 * h->ff;
+  float* eps_out = eps_out_all + (size_t)row0 * h->lat;
+  ca.bs_offset = b0;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
@@ -140,28 +154,76 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
   };
+  // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  On the
+  // tcgen05 path the LayerNorm runs inside the GEMM (last-arriving CTA of each 128-row block); otherwise it is a
+  // separate row kernel.  `a` may be the GEMM's own A operand: a block is normalised only after all its tiles are done.
+  // measured slower than the separate row kernel (one SM normalising 128 rows is bound by its own L2 port): opt-in
+  static const bool want_fuse = getenv("CFB_FUSE_LN") && atoi(getenv("CFB_FUSE_LN")) != 0;
+  const bool fuse_ln = want_fuse && tb && g_gemm_backend != CFB_GEMM_SIMT && row0 % 128 == 0;
+  auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
+                        const float* mod) {
+    Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
+    const bool fuse = fuse_ln && gemm_tc_supported(R, d, K, K, K);
+    if (fuse) {
+      ep.ln_out = reinterpret_cast<bf16*>(a); ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_mod = mod; ep.ln_step = mod ? step_ptr : nullptr;
+      ep.ln_mod_stride = mod_stride; ep.ln_counters = h->lncnt.as<int>() + row0 / 128;
+    }
+    CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
+    if (!fuse) CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
+    return (int)CFB_OK;
+  };
+  CFB_TRY(ln_rows<T>(hres, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr, nullptr, 0, a, R, d, st));
   for (int l = 0; l < h->L; ++l) {
     const cfb_denoiser_layer& w = h->layers[l];
     const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
     const float* mod2 = mod1 + 2 * d;
-    // self-attention block (cross_attention.py:568-572)
-    CFB_TRY(ln_rows<T>(hres, w.ln1_g, w.ln1_b, nullptr, nullptr, 0, a, R, d, st));
+    // self-attention block (cross_attention.py:568-572); a = norm1(h) on entry
     CFB_TRY(lin_T(a, d, w.w_in, w.b_in, qkv, 3 * d, 0));
     CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
-    CFB_TRY(lin_res(a, d, w.w_so, w.b_so));
-    // time_block1 (:575)
-    CFB_TRY(ln_rows<T>(hres, w.tb1_g, w.tb1_b, mod1, step_ptr, mod_stride, a, R, d, st));
-    CFB_TRY(lin_res(a, d, w.w_tb1, w.b_tb1));
-    // five cross-attentions + att_fuser (:578-652), folded
-    CFB_TRY(ln_rows<T>(hres, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1));          // + time_block1 prologue (:575)
+    CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr));     // + norm2 (:578)
+    // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
     for (int x = 0; x < CFB_N_STREAMS; ++x)
       ca.att[x] = att_base && att_base[x] ? att_base[x] + (size_t)l * h->ntok * ca.len[x] : nullptr;
     bool shared_done = false;
     if constexpr (sizeof(T) == 2) {
       if (sp && sp->on) {
         const int Ld = h->L * d;
-        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h
-        Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = h->sS.p;
+        if (sp->n_groups > 0) {   // conditional pairs: own-stream projection, per-pair attention, own-stream fuser block
+          // groups carry ABSOLUTE rows and base pointers; a chain takes the part of each group inside its row range
+          TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
+          int ground[TC_MAX_GROUPS], ng = 0;
+          bf16* uc = h->uc.as<bf16>();
+          float* h_abs = h->h.as<float>();
+          for (int z = 0; z < sp->n_groups; ++z) {
+            const int lo = sp->g_row_start[z] > row0 ? sp->g_row_start[z] : row0;
+            const int hi_g = sp->g_row_start[z] + sp->g_rows[z], hi = hi_g < row0 + R ? hi_g : row0 + R;
+            if (hi <= lo) continue;
+            const int x = sp->g_stream[z];
+            gq[ng] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx_abs + x * d, lo, hi - lo};
+            gg[ng] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, h_abs, lo, hi - lo};
+            ground[ng++] = sp->g_round[z];
+          }
+          if (ng > 0) {
+            Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+            CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, st));
+            ca.skip_slot0 = 1;
+            CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, st));
+            Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+            for (int r = 0; r < sp->n_rounds; ++r) {
+              TcGroup round[TC_MAX_GROUPS];
+              int n = 0;
+              for (int z = 0; z < ng; ++z)
+                if (ground[z] == r) round[n++] = gg[z];
+              if (n > 0) CFB_TRY(gemm_tc_grouped(round, n, R_total, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
+            }
+          }
+        }
+        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h;
+        // issued last so that time_block2's LayerNorm can ride on the values GEMM
+        float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
+        bf16* sP = h->sP.as<bf16>() + (size_t)row0 * sp->k_tot;
+        Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
         es.ldo = sp->n_tot; es.replicate = 1;
         CFB_TRY(gemm_tc(a, d, h->zall.as<bf16>() + (size_t)l * d, Ld, R, sp->n_tot, d, es, st));
         SharedAttnArgs sa{};
@@ -169,50 +231,31 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
           sa.slot[x] = ca.slot[x]; sa.mask[x] = ca.mask[x];
         }
-        sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot;
-        CFB_TRY(softmax_shared(h->sS.as<float>(), h->sP.as<bf16>(), sa, n_batch, h->ntok, st));
+        sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
+        CFB_TRY(softmax_shared(sS, sP, sa, n_batch, h->ntok, st));
         Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-        CFB_TRY(gemm_tc(h->sP.as<bf16>(), sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d,
-                        sp->k_tot, ey, st));
-        if (sp->n_groups > 0) {   // conditional pairs: own-stream projection, per-pair attention, own-stream fuser block
-          TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
-          bf16* uc = h->uc.as<bf16>();
-          for (int z = 0; z < sp->n_groups; ++z) {
-            const int x = sp->g_stream[z];
-            gq[z] = TcGroup{a, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx + x * d, sp->g_row_start[z], sp->g_rows[z]};
-            gg[z] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, hres, sp->g_row_start[z], sp->g_rows[z]};
-          }
-          Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
-          CFB_TRY(gemm_tc_grouped(gq, sp->n_groups, R, d, d, d, d, eq, st));
-          ca.skip_slot0 = 1;
-          CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, st));
-          Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
-          for (int r = 0; r < sp->n_rounds; ++r) {
-            TcGroup round[TC_MAX_GROUPS];
-            int n = 0;
-            for (int z = 0; z < sp->n_groups; ++z)
-              if (sp->g_round[z] == r) round[n++] = gg[z];
-            CFB_TRY(gemm_tc_grouped(round, n, R, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
-          }
+        if (fuse_ln) {
+          ey.ln_out = reinterpret_cast<bf16*>(a); ey.ln_g = w.tb2_g; ey.ln_b = w.tb2_b; ey.ln_mod = mod2; ey.ln_step = step_ptr;
+          ey.ln_mod_stride = mod_stride; ey.ln_counters = h->lncnt.as<int>() + row0 / 128;
         }
+        CFB_TRY(gemm_tc(sP, sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d, sp->k_tot, ey, st));
+        if (!fuse_ln) CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
         shared_done = true;
       }
     }
     if (!shared_done) {
       CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
-      CFB_TRY(cross_attention<T>(qx, h->mem_hat.as<T>(), qx, ca, n_batch, h->ntok, d, st));
-      CFB_TRY(lin_res(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu));
+      CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
+      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2));   // + time_block2 prologue (:655)
     }
-    // time_block2 (:655)
-    CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
-    CFB_TRY(lin_res(a, d, w.w_tb2, w.b_tb2));
-    // feed-forward (:659-661)
-    CFB_TRY(ln_rows<T>(hres, w.ln3_g, w.ln3_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr));      // + norm3 (:659)
+    // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
     CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU));
-    CFB_TRY(lin_res(f, h->ff, w.w_ff2, w.b_ff2));
+    const bool last = l + 1 == h->L;
+    CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
+                       last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr));
   }
-  // decoder.norm + latent_proj (cross_attention.py:238-239, denoiser.py:382)
-  CFB_TRY(ln_rows<T>(hres, h->w.lnf_g, h->w.lnf_b, nullptr, nullptr, 0, a, R, d, st));
+  // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
   return gemm(a, tb, d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
 }
@@ -243,6 +286,10 @@ int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
   CFB_TRY(h->xin.reserve((size_t)n_in * h->ntok * h->lat * es, &h->epoch));
   CFB_TRY(h->eps.reserve(R * h->lat * 4, &h->epoch));
+  if (h->lncnt.cap < (R / 128 + 2) * 4) {   // fused-LayerNorm block counters: zero once, the kernels re-arm them
+    CFB_TRY(h->lncnt.reserve((R / 128 + 2) * 4, &h->epoch));
+    CFB_CUDA(cudaMemset(h->lncnt.p, 0, h->lncnt.cap));
+  }
   return CFB_OK;
 }
 
@@ -289,7 +336,27 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
   CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
   if (sp.on) CFB_TRY(shared_precompute(h, sp, ml, ca.len, st));
   CFB_TRY(embed<T>(h, h->x.as<float>(), n_clips, n_branch, st));   // torch.cat([latents] * 7), convofusion.py:499
-  CFB_TRY(run_layers<T>(h, n_clips * n_branch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp));
+  // The step is a chain of ~190 short kernels, bound by launch / prologue / epilogue latency rather than by
+  // throughput.  Batch entries are independent through the whole denoiser, so they are cut into n_chains groups
+  // (multiples of 8 entries = one 128-row tile) that run the layer stack concurrently on forked streams.
+  const int n_batch = n_clips * n_branch;
+  const int per = ((n_batch + h->n_chains - 1) / h->n_chains + 7) & ~7;
+  const int nc = (n_batch + per - 1) / per;
+  if (nc <= 1) {
+    CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp));
+  } else {
+    CFB_CUDA(cudaEventRecord(h->ev_fork, st));
+    for (int c = 0; c < nc; ++c) {
+      const int b0 = c * per, nb = (b0 + per <= n_batch ? per : n_batch - b0);
+      cudaStream_t cs = c == 0 ? st : h->chain_st[c];
+      if (c > 0) CFB_CUDA(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch));
+      if (c > 0) {
+        CFB_CUDA(cudaEventRecord(h->ev_join[c], cs));
+        CFB_CUDA(cudaStreamWaitEvent(st, h->ev_join[c], 0));
+      }
+    }
+  }
   return guidance_sched_step(sa, st);
 }
 
@@ -388,9 +455,14 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int c = 0; c < cfb_denoiser::MAX_CHAINS; ++c) {
+    if (h->chain_st[c]) cudaStreamDestroy(h->chain_st[c]);
+    if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+  }
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->lncnt};
   for (DeviceBuf* b : bufs) b->release();
   delete h;
 }
@@ -464,6 +536,18 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
   SharedPlan sp;
   CFB_TRY(make_shared_plan(h, mem, n_batch, &sp, st));
+  {
+    const char* e = getenv("CFB_CHAINS");
+    int want = e ? atoi(e) : 6;
+    if (want < 1) want = 1;
+    if (want > cfb_denoiser::MAX_CHAINS) want = cfb_denoiser::MAX_CHAINS;
+    h->n_chains = want;
+    if (!h->ev_fork) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int c = 1; c < want; ++c) {
+      if (!h->chain_st[c]) CFB_CUDA(cudaStreamCreateWithFlags(&h->chain_st[c], cudaStreamNonBlocking));
+      if (!h->ev_join[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+    }
+  }
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     ca.att_batch_stride[x] = (long long)h->L * h->ntok * mem->len[x];
     ca.att_step_stride[x] = (long long)n_clips * ca.att_batch_stride[x];
@@ -501,7 +585,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains; key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

@@ -378,6 +378,80 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         }
       }
     }
+    // ---- fused LayerNorm of this 128-row block by the CTA that completes it (see Epilogue::ln_out)
+    if (ep.ln_out != nullptr) {
+      __shared__ int s_last;
+      __threadfence();                                            // my residual stores before my counter increment
+      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
+      if (warp == 2 && lane == 0) {
+        const int done = atomicAdd(ep.ln_counters + blockIdx.y, 1);
+        s_last = (done == (int)gridDim.x - 1);
+        if (s_last) ep.ln_counters[blockIdx.y] = 0;               // every n-tile of this block has arrived: re-arm
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();                                          // order the counter observation before the reads
+        const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
+        constexpr int LD = 512, NR = 4;                           // rows in flight per warp
+        float gam[16], bet[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_g + i * 128 + lane * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(ep.ln_b + i * 128 + lane * 4);
+          gam[4 * i] = g4.x; gam[4 * i + 1] = g4.y; gam[4 * i + 2] = g4.z; gam[4 * i + 3] = g4.w;
+          bet[4 * i] = b4.x; bet[4 * i + 1] = b4.y; bet[4 * i + 2] = b4.z; bet[4 * i + 3] = b4.w;
+        }
+        const float* hbase = reinterpret_cast<const float*>(ep.out);
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += NR) {
+          float x[NR][16];
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            const int r = min(m0 + q * 32 + rb + j, M - 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(hbase + (size_t)r * LD + i * 128 + lane * 4));
+              x[j][4 * i] = t.x; x[j][4 * i + 1] = t.y; x[j][4 * i + 2] = t.z; x[j][4 * i + 3] = t.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            const int r = m0 + q * 32 + rb + j;
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum += x[j][i];
+            const float mu = warp_sum(sum) * (1.0f / LD);
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { x[j][i] -= mu; sq += x[j][i] * x[j][i]; }
+            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / LD) + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[j][i] = x[j][i] * rstd * gam[i] + bet[i];
+            if (mod) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 sc = *reinterpret_cast<const float4*>(mod + i * 128 + lane * 4);
+                const float4 sh = *reinterpret_cast<const float4*>(mod + LD + i * 128 + lane * 4);
+                x[j][4 * i] = act_apply(x[j][4 * i] * (1.0f + sc.x) + sh.x, CFB_ACT_SILU);
+                x[j][4 * i + 1] = act_apply(x[j][4 * i + 1] * (1.0f + sc.y) + sh.y, CFB_ACT_SILU);
+                x[j][4 * i + 2] = act_apply(x[j][4 * i + 2] * (1.0f + sc.z) + sh.z, CFB_ACT_SILU);
+                x[j][4 * i + 3] = act_apply(x[j][4 * i + 3] * (1.0f + sc.w) + sh.w, CFB_ACT_SILU);
+              }
+            }
+            if (r < M) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 t0 = __floats2bfloat162_rn(x[j][4 * i], x[j][4 * i + 1]);
+                const __nv_bfloat162 t1 = __floats2bfloat162_rn(x[j][4 * i + 2], x[j][4 * i + 3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+                *reinterpret_cast<uint2*>(ep.ln_out + (size_t)r * LD + i * 128 + lane * 4) = pk;
+              }
+            }
+          }
+        }
+      }
+    }
   }
   if (warp == 2 && lane == 0) trace(8);
   tc_fence_before();
@@ -576,6 +650,9 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   CFB_TRY(check_epilogue(ep));
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
+  if (ep.ln_out)
+    CFB_CHECK(N == 512 && ep.ldo == 512 && !ep.out_bf16 && ep.replicate == 1 && ep.ln_counters && ep.ln_g && ep.ln_b,
+              "gemm_tc: fused LayerNorm needs a float [M,512] output and a counter buffer");
   if (w_rows <= 0 || w_rows > N) w_rows = N;
   if (N % 128 == 0) {
     // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.

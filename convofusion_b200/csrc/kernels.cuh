@@ -37,6 +37,7 @@ struct CrossArgs {
   long long att_step_stride[CFB_N_STREAMS];   // added per *step_ptr (graph replay)
   const int* step_ptr;
   int skip_slot0;                       // 1: (batch entry, stream) pairs on slot 0 are handled by the shared path
+  int bs_offset;                        // first batch entry handled by this launch (blockIdx.x is relative to it)
 };
 // Shared-slot path: scores of every row against slot 0 of every stream come from ONE GEMM (S, fp32, stream x
 // at columns s_off[x] .. +len[x]); this turns them into bf16 probabilities P (stream x at p_off[x] .. +kp[x],
@@ -46,6 +47,7 @@ struct SharedAttnArgs {
   const int* slot[CFB_N_STREAMS];       // [n_batch]
   const uint8_t* mask[CFB_N_STREAMS];   // key padding mask of slot 0 or nullptr
   int ld_s, ld_p;
+  int bs_offset;                        // batch entry of row 0 of S / P as passed to the launch
 };
 int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st);
 int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
