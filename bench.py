@@ -43,16 +43,27 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------ flops
-def denoiser_flops(n_clips, n_branch, mem_tokens, d=512, ff=1024, L=9, ntok=16, lat=128):
-    """Executed FLOPs of one denoiser evaluation (2*m*n*k over every GEMM + attention contraction) in the folded
-    form this implementation issues, and the as-written reference-equivalent figure."""
+def denoiser_flops(n_clips, n_branch, mem_len=(32, 161, 32, 8, 1), d=512, ff=1024, L=9, ntok=16, lat=128):
+    """FLOPs of one denoiser evaluation (2*m*n*k over every GEMM and attention contraction).
+    `executed`: what this implementation issues in the shared-slot plan: per layer the
+    full-batch GEMMs in_proj / out_proj / 2 x TimeBlock / shared scores (N = sum of 32-padded memory lengths) /
+    shared values (K = sum of 64-padded lengths) / FFN, the conditional row groups (one stream per single-modality
+    branch: query projection + fuser block), the per-pair and self attention, plus the per-step memory-side
+    pre-projection.  `as_written`: the reference's own count for 7 branches."""
     R = n_clips * n_branch * ntok
-    per_row_layer = 2 * d * (3 * d + d + d + 5 * d + 5 * d + d + 2 * ff)
-    gemm = R * (L * per_row_layer + 2 * lat * d) + n_clips * ntok * 2 * lat * d
-    self_att = n_clips * n_branch * L * 2 * 2 * ntok * ntok * d
-    cross = n_clips * n_branch * L * 2 * 2 * ntok * mem_tokens * d
-    as_written = n_clips * 7 * (L * (212.3e6 + 0.0328e6 * mem_tokens + 1.0486e6 * mem_tokens) + 5.2e6)
-    return {"gemm": gemm, "attention": self_att + cross, "executed": gemm + self_att + cross, "as_written": as_written}
+    n_tot = sum((m + 31) // 32 * 32 for m in mem_len)
+    k_tot = sum((m + 63) // 64 * 64 for m in mem_len)
+    M = sum(mem_len)
+    full = 2.0 * R * (3 * d * d + d * d + d * d + n_tot * d + d * k_tot + d * d + ff * d + d * ff)
+    n_cond_rows = min(n_branch - 1, len(mem_len)) * n_clips * ntok          # branches 1..5: one conditional stream each
+    cond = 2.0 * n_cond_rows * 2 * d * d
+    self_att = 2.0 * 2 * n_clips * n_branch * ntok * ntok * d
+    pair_att = 2.0 * 2 * n_clips * ntok * M * d                             # each clip's own memory, once per stream
+    per_step = 2.0 * (n_tot * L * d * d + L * d * k_tot * d)                # Z and Y^T for all layers
+    ends = 2.0 * (n_clips * ntok * lat * d + R * d * lat)                   # latent_embd (replicated) + latent_proj
+    executed = L * (full + cond + self_att + pair_att) + per_step + ends
+    as_written = n_clips * 7 * (L * (212.3e6 + 0.0328e6 * M + 1.0486e6 * M) + 5.2e6)
+    return {"executed": executed, "as_written": as_written}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -317,7 +328,7 @@ def run_ours(args):
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
         mem_tokens = 234
-        fl = denoiser_flops(B, n_branch, mem_tokens)
+        fl = denoiser_flops(B, n_branch)
         ms_den = parts["loop_ms"] / args.ddim_steps
         line = {
             "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
