@@ -69,6 +69,10 @@ struct cfb_denoiser {
   cudaStream_t chain_st[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
   int n_chains = 1;
+  // per chain: side stream for the conditional-pair sub-chain of every layer; per step: two streams that run the
+  // memory-side pre-projection (keys / values) while the chains are still in their self-attention blocks
+  cudaStream_t chain_st2[MAX_CHAINS] = {}, pre_st[2] = {};
+  cudaEvent_t ev_a[MAX_CHAINS] = {}, ev_b[MAX_CHAINS] = {}, ev_mh = nullptr, ev_pre[2] = {};
 };
 
 namespace {
@@ -110,30 +114,45 @@ int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaSt
   return gemm(h->xin.p, sizeof(T) == 2, h->lat, h->w.w_embed, sizeof(T) == 2, h->lat, rows, h->d, h->lat, 0, ep, st);
 }
 
-// Per-step memory-side precompute of the shared-slot plan: Z (keys), z0 (key bias) and Y^T (values) for all layers.
+// Per-step memory-side precompute of the shared-slot plan for all layers: keys Z + key bias z0 (which = 0) or values
+// Y^T (which = 1).  The two halves are independent and run on separate streams.
 int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml, const int len[CFB_N_STREAMS],
-                      cudaStream_t st) {
+                      int which, cudaStream_t st) {
   const int d = h->d, Ld = h->L * h->d;
   const bf16* mh = h->mem_hat.as<bf16>();
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     const bf16* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
-    const int rows_avail = ml.total_rows - ml.row_base[x];
-    Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = 1; ez.out = h->zall.as<bf16>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
-    CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
-    Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = 1; ey.out = h->ytall.as<bf16>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
-    const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
-    CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+    if (which == 0) {
+      Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = 1; ez.out = h->zall.as<bf16>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
+      CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
+    } else {
+      const int rows_avail = ml.total_rows - ml.row_base[x];
+      Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = 1; ey.out = h->ytall.as<bf16>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
+      const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
+      CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+    }
   }
-  return shared_key_bias(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
+  if (which == 0) return shared_key_bias(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
+  return CFB_OK;
 }
+
+// Optional concurrency inside one chain (all null = strictly sequential on `st`).
+struct ChainAux {
+  cudaStream_t st2 = nullptr;          // conditional-pair projection + attention run here, next to the shared-slot path
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_pre[2] = {nullptr, nullptr};   // memory-side pre-projection finished (waited before layer 0's attention)
+};
 
 // Runs the 9 layers + final projection for the batch entries [b0, b0 + n_batch) (a "chain").  Rows of different batch
 // entries never interact, so disjoint chains may run concurrently on different streams; they share only read-only
 // data (weights, mem_hat, zall / ytall / z0all).  n_batch_total = entries of the whole call (tensor-map extents).
 template <typename T>
 int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
-               float* eps_out_all, cudaStream_t st, const SharedPlan* sp = nullptr, int b0 = 0, int n_batch_total = 0) {
+               float* eps_out_all, cudaStream_t st, const SharedPlan* sp = nullptr, int b0 = 0, int n_batch_total = 0,
+               const ChainAux* aux = nullptr) {
   if (n_batch_total <= 0) n_batch_total = n_batch;
+  const ChainAux no_aux;
+  if (!aux) aux = &no_aux;
   const int R = n_batch * h->ntok, d = h->d, row0 = b0 * h->ntok, R_total = n_batch_total * h->ntok;
   const int tb = sizeof(T) == 2;
   float* hres = h->h.as<float>() + (size_t)row0 * d;
@@ -189,38 +208,51 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     if constexpr (sizeof(T) == 2) {
       if (sp && sp->on) {
         const int Ld = h->L * d;
-        if (sp->n_groups > 0) {   // conditional pairs: own-stream projection, per-pair attention, own-stream fuser block
-          // groups carry ABSOLUTE rows and base pointers; a chain takes the part of each group inside its row range
-          TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
-          int ground[TC_MAX_GROUPS], ng = 0;
-          bf16* uc = h->uc.as<bf16>();
-          float* h_abs = h->h.as<float>();
-          for (int z = 0; z < sp->n_groups; ++z) {
-            const int lo = sp->g_row_start[z] > row0 ? sp->g_row_start[z] : row0;
-            const int hi_g = sp->g_row_start[z] + sp->g_rows[z], hi = hi_g < row0 + R ? hi_g : row0 + R;
-            if (hi <= lo) continue;
-            const int x = sp->g_stream[z];
-            gq[ng] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx_abs + x * d, lo, hi - lo};
-            gg[ng] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, h_abs, lo, hi - lo};
-            ground[ng++] = sp->g_round[z];
-          }
-          if (ng > 0) {
-            Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
-            CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, st));
-            ca.skip_slot0 = 1;
-            CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, st));
-            Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
-            for (int r = 0; r < sp->n_rounds; ++r) {
-              TcGroup round[TC_MAX_GROUPS];
-              int n = 0;
-              for (int z = 0; z < ng; ++z)
-                if (ground[z] == r) round[n++] = gg[z];
-              if (n > 0) CFB_TRY(gemm_tc_grouped(round, n, R_total, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
-            }
-          }
+        if (l == 0)
+          for (int i = 0; i < 2; ++i)
+            if (aux->ev_pre[i]) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_pre[i], 0));
+        // conditional pairs: own-stream projection + per-pair attention (on the side stream when there is one: they
+        // only read `a` / mem_hat and write qx / uc), then -- after the shared path -- the own-stream fuser blocks
+        TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
+        int ground[TC_MAX_GROUPS], ng = 0;
+        bf16* uc = h->uc.as<bf16>();
+        float* h_abs = h->h.as<float>();
+        for (int z = 0; z < sp->n_groups; ++z) {   // groups carry ABSOLUTE rows; a chain takes the part inside its range
+          const int lo = sp->g_row_start[z] > row0 ? sp->g_row_start[z] : row0;
+          const int hi_g = sp->g_row_start[z] + sp->g_rows[z], hi = hi_g < row0 + R ? hi_g : row0 + R;
+          if (hi <= lo) continue;
+          const int x = sp->g_stream[z];
+          gq[ng] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx_abs + x * d, lo, hi - lo};
+          gg[ng] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, h_abs, lo, hi - lo};
+          ground[ng++] = sp->g_round[z];
         }
-        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h;
-        // issued last so that time_block2's LayerNorm can ride on the values GEMM
+        const bool side = ng > 0 && aux->st2 != nullptr;
+        cudaStream_t sc = side ? aux->st2 : st;
+        if (ng > 0) {
+          if (side) {
+            CFB_CUDA(cudaEventRecord(aux->ev_a, st));
+            CFB_CUDA(cudaStreamWaitEvent(sc, aux->ev_a, 0));
+          }
+          Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+          CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, sc));
+          ca.skip_slot0 = 1;
+          CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, sc));
+          if (side) CFB_CUDA(cudaEventRecord(aux->ev_b, sc));
+        }
+        auto cond_fuser = [&]() -> int {
+          if (ng == 0) return CFB_OK;
+          if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
+          Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+          for (int r = 0; r < sp->n_rounds; ++r) {
+            TcGroup round[TC_MAX_GROUPS];
+            int n = 0;
+            for (int z = 0; z < ng; ++z)
+              if (ground[z] == r) round[n++] = gg[z];
+            if (n > 0) CFB_TRY(gemm_tc_grouped(round, n, R_total, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
+          }
+          return CFB_OK;
+        };
+        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h
         float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
         bf16* sP = h->sP.as<bf16>() + (size_t)row0 * sp->k_tot;
         Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
@@ -234,12 +266,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
         CFB_TRY(softmax_shared(sS, sP, sa, n_batch, h->ntok, st));
         Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-        if (fuse_ln) {
+        if (fuse_ln) {   // the LayerNorm rides on the values GEMM, so every other update of h must precede it
+          CFB_TRY(cond_fuser());
           ey.ln_out = reinterpret_cast<bf16*>(a); ey.ln_g = w.tb2_g; ey.ln_b = w.tb2_b; ey.ln_mod = mod2; ey.ln_step = step_ptr;
           ey.ln_mod_stride = mod_stride; ey.ln_counters = h->lncnt.as<int>() + row0 / 128;
         }
         CFB_TRY(gemm_tc(sP, sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d, sp->k_tot, ey, st));
-        if (!fuse_ln) CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+        if (!fuse_ln) {
+          CFB_TRY(cond_fuser());
+          CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+        }
         shared_done = true;
       }
     }
@@ -334,7 +370,20 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
               float* const att_base[CFB_N_STREAMS], const StepArgs& sa, const SharedPlan& sp, cudaStream_t st) {
   const int* step_ptr = h->step.as<int>();
   CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
-  if (sp.on) CFB_TRY(shared_precompute(h, sp, ml, ca.len, st));
+  const bool overlap = sp.on && h->n_chains > 1 && h->pre_st[0] != nullptr;
+  if (sp.on) {
+    if (overlap) {   // keys and values of the shared slot on two side streams, hidden behind the self-attention blocks
+      CFB_CUDA(cudaEventRecord(h->ev_mh, st));
+      for (int i = 0; i < 2; ++i) {
+        CFB_CUDA(cudaStreamWaitEvent(h->pre_st[i], h->ev_mh, 0));
+        CFB_TRY(shared_precompute(h, sp, ml, ca.len, i, h->pre_st[i]));
+        CFB_CUDA(cudaEventRecord(h->ev_pre[i], h->pre_st[i]));
+      }
+    } else {
+      CFB_TRY(shared_precompute(h, sp, ml, ca.len, 0, st));
+      CFB_TRY(shared_precompute(h, sp, ml, ca.len, 1, st));
+    }
+  }
   CFB_TRY(embed<T>(h, h->x.as<float>(), n_clips, n_branch, st));   // torch.cat([latents] * 7), convofusion.py:499
   // The step is a chain of ~190 short kernels, bound by launch / prologue / epilogue latency rather than by
   // throughput.  Batch entries are independent through the whole denoiser, so they are cut into n_chains groups
@@ -343,14 +392,21 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
   const int per = ((n_batch + h->n_chains - 1) / h->n_chains + 7) & ~7;
   const int nc = (n_batch + per - 1) / per;
   if (nc <= 1) {
-    CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp));
+    ChainAux aux;
+    if (overlap) { aux.ev_pre[0] = h->ev_pre[0]; aux.ev_pre[1] = h->ev_pre[1]; }
+    CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp, 0, n_batch, &aux));
   } else {
     CFB_CUDA(cudaEventRecord(h->ev_fork, st));
     for (int c = 0; c < nc; ++c) {
       const int b0 = c * per, nb = (b0 + per <= n_batch ? per : n_batch - b0);
       cudaStream_t cs = c == 0 ? st : h->chain_st[c];
       if (c > 0) CFB_CUDA(cudaStreamWaitEvent(cs, h->ev_fork, 0));
-      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch));
+      ChainAux aux;
+      if (overlap) {
+        aux.ev_pre[0] = h->ev_pre[0]; aux.ev_pre[1] = h->ev_pre[1];
+        aux.st2 = h->chain_st2[c]; aux.ev_a = h->ev_a[c]; aux.ev_b = h->ev_b[c];
+      }
+      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux));
       if (c > 0) {
         CFB_CUDA(cudaEventRecord(h->ev_join[c], cs));
         CFB_CUDA(cudaStreamWaitEvent(st, h->ev_join[c], 0));
@@ -458,8 +514,16 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int c = 0; c < cfb_denoiser::MAX_CHAINS; ++c) {
     if (h->chain_st[c]) cudaStreamDestroy(h->chain_st[c]);
+    if (h->chain_st2[c]) cudaStreamDestroy(h->chain_st2[c]);
     if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+    if (h->ev_a[c]) cudaEventDestroy(h->ev_a[c]);
+    if (h->ev_b[c]) cudaEventDestroy(h->ev_b[c]);
   }
+  for (int i = 0; i < 2; ++i) {
+    if (h->pre_st[i]) cudaStreamDestroy(h->pre_st[i]);
+    if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+  }
+  if (h->ev_mh) cudaEventDestroy(h->ev_mh);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
                        &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->lncnt};
@@ -546,6 +610,19 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
     for (int c = 1; c < want; ++c) {
       if (!h->chain_st[c]) CFB_CUDA(cudaStreamCreateWithFlags(&h->chain_st[c], cudaStreamNonBlocking));
       if (!h->ev_join[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+    }
+    const char* o = getenv("CFB_OVERLAP");
+    if (want > 1 && !(o && atoi(o) == 0)) {
+      for (int c = 0; c < want; ++c) {
+        if (!h->chain_st2[c]) CFB_CUDA(cudaStreamCreateWithFlags(&h->chain_st2[c], cudaStreamNonBlocking));
+        if (!h->ev_a[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_a[c], cudaEventDisableTiming));
+        if (!h->ev_b[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_b[c], cudaEventDisableTiming));
+      }
+      for (int i = 0; i < 2; ++i) {
+        if (!h->pre_st[i]) CFB_CUDA(cudaStreamCreateWithFlags(&h->pre_st[i], cudaStreamNonBlocking));
+        if (!h->ev_pre[i]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+      }
+      if (!h->ev_mh) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_mh, cudaEventDisableTiming));
     }
   }
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
