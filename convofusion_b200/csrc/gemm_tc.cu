@@ -143,7 +143,8 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int STATS_OFF = BAR_OFF + 128;                             // 128 rows x (sum, sumsq) floats
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024 + 1024;                   // barriers, row stats, alignment slack
 };
 
 // One 128 x BN output tile: rows [m0, min(m0+128, m_end)), columns [n0, n0+BN).
@@ -155,12 +156,20 @@ struct Smem {
 // memory (same offset, each sharer's own `full` barrier).  A stage may be overwritten only when every CTA that
 // receives data from this producer has consumed it, so consumers release a stage with a multicast tcgen05.commit to
 // the `empty` barrier of all CN + CM - 1 CTAs that feed them.
-template <int BN, int STAGES, int CN = 1, int CM = 1>
+//
+// LNC (LayerNorm over a cluster): the four n-tile CTAs of one 128-row block of a [M,512] residual update form a
+// cluster.  Each CTA keeps its updated 128x128 sub-block in shared memory, publishes per-row (sum, sum of squares) of
+// its 128 columns, and after one cluster barrier reads the other three CTAs' partials through distributed shared
+// memory (mapa + ld.shared::cluster).  Every CTA then normalises its own sub-block and writes the next GEMM's bf16
+// operand: the LayerNorm costs no global read and no kernel launch on the critical path.
+template <int BN, int STAGES, int CN = 1, int CM = 1, bool LNC = false>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const int m0,
                                           const int M /* first row NOT to store */, const int n0, const int N,
                                           const int K, const Epilogue& ep) {
   using S = Smem<BN, STAGES>;
   constexpr int CL = CN * CM;
+  constexpr bool CLUSTERED = CL > 1 || LNC;
+  static_assert(!LNC || (CL == 1 && BN == 128), "cluster LayerNorm: 4 x (128x128) tiles, no multicast");
   uint32_t crank = 0;
   if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const uint32_t rn = crank % CN, rm = crank / CN;
@@ -230,6 +239,11 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
       }
       trace(3);
     }
+    if constexpr (LNC) {   // see warp 1
+      __syncwarp();
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
@@ -252,6 +266,11 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
       }
       umma_commit(bar_acc);
       trace(5);
+    }
+    if constexpr (LNC) {   // matches the epilogue warps' barrier between publishing and reading the row statistics
+      __syncwarp();
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   } else {
     // ---- epilogue.  tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
@@ -350,6 +369,19 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
 #pragma unroll
           for (int c = 0; c < CPL; ++c) v[i][c] += res[i][c];
       }
+      if constexpr (LNC) {   // keep the updated values on chip and publish this CTA's share of the row statistics
+        float* stats = reinterpret_cast<float*>(gen_base + S::STATS_OFF);
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) { s1 += v[i][c]; s2 = fmaf(v[i][c], v[i][c], s2); }
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          if (lane == 0) { stats[(q * 32 + rb + i) * 2] = s1; stats[(q * 32 + rb + i) * 2 + 1] = s2; }
+          *reinterpret_cast<float4*>(stg + (rb + i) * PITCH + lane * 4) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        }
+      }
       for (int rep = 0; rep < ep.replicate; ++rep) {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
@@ -378,6 +410,47 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         }
       }
     }
+    if constexpr (LNC) {
+      // ---- LayerNorm over the cluster: statistics of the other three column blocks through DSMEM
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      const uint32_t my_stats = base + S::STATS_OFF + (uint32_t)(q * 32 + lane) * 8;
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (uint32_t peer = 0; peer < 4; ++peer) {
+        uint32_t ra;
+        float a1, a2;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(my_stats), "r"(peer));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a1) : "r"(ra) : "memory");
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a2) : "r"(ra + 4) : "memory");
+        t1 += a1; t2 += a2;
+      }
+      const float mean_l = t1 * (1.0f / 512.0f);
+      const float rstd_l = rsqrtf(fmaxf(t2 * (1.0f / 512.0f) - mean_l * mean_l, 0.f) + 1e-5f);   // row q*32+lane
+      const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
+      const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_g + n);
+      const float4 b4 = *reinterpret_cast<const float4*>(ep.ln_b + n);
+      float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
+      if (mod) { sc4 = *reinterpret_cast<const float4*>(mod + n); sh4 = *reinterpret_cast<const float4*>(mod + 512 + n); }
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const float mu = __shfl_sync(0xffffffffu, mean_l, rr), rs = __shfl_sync(0xffffffffu, rstd_l, rr);
+        const float4 x = *reinterpret_cast<const float4*>(stg + rr * PITCH + lane * 4);
+        float y0 = (x.x - mu) * rs * g4.x + b4.x, y1 = (x.y - mu) * rs * g4.y + b4.y;
+        float y2 = (x.z - mu) * rs * g4.z + b4.z, y3 = (x.w - mu) * rs * g4.w + b4.w;
+        if (mod) {
+          y0 = act_apply(y0 * (1.0f + sc4.x) + sh4.x, CFB_ACT_SILU); y1 = act_apply(y1 * (1.0f + sc4.y) + sh4.y, CFB_ACT_SILU);
+          y2 = act_apply(y2 * (1.0f + sc4.z) + sh4.z, CFB_ACT_SILU); y3 = act_apply(y3 * (1.0f + sc4.w) + sh4.w, CFB_ACT_SILU);
+        }
+        const int r = r0 + rr;
+        if (r < M) {
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(ep.ln_out + (size_t)r * 512 + n) = pk;
+        }
+      }
+    } else
     // ---- fused LayerNorm of this 128-row block by the CTA that completes it (see Epilogue::ln_out)
     if (ep.ln_out != nullptr) {
       __shared__ int s_last;
@@ -455,7 +528,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
   }
   if (warp == 2 && lane == 0) trace(8);
   tc_fence_before();
-  if constexpr (CL > 1) {   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
+  if constexpr (CLUSTERED) {   // no CTA may exit while a peer can still multicast into it, arrive on its barriers or read its statistics
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   } else {
@@ -474,6 +547,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
                                                            const __grid_constant__ CUtensorMap tmB, int M, int N,
                                                            int K, Epilogue ep) {
   gemm_tile<BN, STAGES, CN, CM>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, int M, int N,
+                                                                  int K, Epilogue ep) {
+  gemm_tile<BN, STAGES, 1, 1, true>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 // Grouped launch: blockIdx.z picks a group = (A map, B map, row block, bias, output).  All groups share N, K and
@@ -584,6 +664,25 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, in
   return CFB_OK;
 }
 
+// [M,512] residual update + cluster LayerNorm: one 4-CTA cluster per 128-row block, PDL allowed.
+int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+  using S = Smem<128, 3>;
+  CUtensorMap ta, tb;
+  CFB_TRY(get_map(A, M, K, lda, BM, &ta));
+  CFB_TRY(get_map(W, N, K, ldw, 128, &tb));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4, ceil_div(M, BM)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_ln_kernel<128, 3>, ta, tb, M, N, K, ep));
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
 template <int BN, int STAGES>
 int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
                    const Epilogue& ep, cudaStream_t st) {
@@ -626,6 +725,7 @@ int init_gemm_tc_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
   if (const char* e = getenv("CFB_TC_CLUSTER")) g_tc_cluster = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_ln_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   done = true;
   return CFB_OK;
 }
@@ -650,9 +750,11 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   CFB_TRY(check_epilogue(ep));
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
-  if (ep.ln_out)
-    CFB_CHECK(N == 512 && ep.ldo == 512 && !ep.out_bf16 && ep.replicate == 1 && ep.ln_counters && ep.ln_g && ep.ln_b,
-              "gemm_tc: fused LayerNorm needs a float [M,512] output and a counter buffer");
+  if (ep.ln_out) {
+    CFB_CHECK(N == 512 && ep.ldo == 512 && !ep.out_bf16 && ep.replicate == 1 && ep.ln_g && ep.ln_b,
+              "gemm_tc: fused LayerNorm needs a float [M,512] output");
+    if (ep.ln_counters == nullptr) return launch_ln(A, lda, W, ldw, M, N, K, ep, st);   // cluster / DSMEM variant
+  }
   if (w_rows <= 0 || w_rows > N) w_rows = N;
   if (N % 128 == 0) {
     // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.

@@ -1,0 +1,56 @@
+"""Optional execution strategies (read from the environment when the library initialises, hence subprocesses):
+cluster TMA multicast GEMMs, the two fused-LayerNorm variants, single-chain / no-PDL execution.  Each must
+reproduce the default configuration's bf16 sampling run (same arithmetic up to summation order / statistics
+formula), and the default run must be bit-identical across processes."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import convofusion_b200 as cf
+from convofusion_b200.synthetic import synthetic_clip, to_device
+from helpers import state_dict
+s = cf.ConvoFusionSampler(precision="bf16", num_inference_timesteps=2)
+s.load_state_dict(state_dict()); s = s.to("cuda:0").eval()
+syn = to_device(synthetic_clip(9, seed=41, dyadic=True), "cuda:0")
+enc, masks = s.encode_conditions(syn["clip"], syn["uncond_text"], syn["uncond_text_attn"])
+init = torch.randn(9, 16, 128, generator=torch.Generator().manual_seed(42)).cuda()
+z, rec, _ = s.sample(enc, masks, 9, init, record=True)
+torch.save(rec.cpu(), sys.argv[1])
+""" % (str(ROOT), str(ROOT / "tests"))
+
+
+def run(tmp_path, name, env):
+    out = tmp_path / f"{name}.pt"
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT, str(out)], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(out, weights_only=True)
+
+
+def test_optional_paths_agree_with_default(tmp_path):
+    base = run(tmp_path, "base", {})
+    again = run(tmp_path, "again", {})
+    assert torch.equal(base, again)                      # deterministic across processes
+    scale = float(base[0].abs().max())
+    for name, env in (("cluster42", {"CFB_TC_CLUSTER": "42"}), ("cluster21", {"CFB_TC_CLUSTER": "21"}),
+                      ("ln_counter", {"CFB_FUSE_LN": "1"}), ("ln_cluster", {"CFB_FUSE_LN": "2"}),
+                      ("serial", {"CFB_CHAINS": "1", "CFB_PDL": "0", "CFB_OVERLAP": "0"})):
+        got = run(tmp_path, name, env)
+        err = float((got[0] - base[0]).abs().max()) / scale
+        print(f"{name}: first-step max deviation from default {err:.2e}")
+        # multicast / chains / PDL change no arithmetic at all; the fused LayerNorms change the statistics formula
+        if name in ("cluster42", "cluster21", "serial"):
+            assert torch.equal(got, base), name
+        else:
+            assert err < 2e-2, name
