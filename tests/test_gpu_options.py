@@ -48,9 +48,11 @@ def test_optional_paths_agree_with_default(tmp_path):
                       ("serial", {"CFB_CHAINS": "1", "CFB_PDL": "0", "CFB_OVERLAP": "0"})):
         got = run(tmp_path, name, env)
         err = float((got[0] - base[0]).abs().max()) / scale
-        print(f"{name}: first-step max deviation from default {err:.2e}")
-        # multicast / chains / PDL change no arithmetic at all; the fused LayerNorms change the statistics formula
+        l2 = float((got[0] - base[0]).norm() / base[0].norm())
+        print(f"{name}: first-step deviation from default: max {err:.2e}, L2 {l2:.2e}")
+        # multicast / chains / PDL change no arithmetic at all; the fused LayerNorms change rounding inside the
+        # statistics, which flips a few bf16 roundings of the GEMM operand (amplified ~74x by the guidance weights)
         if name in ("cluster42", "cluster21", "serial"):
             assert torch.equal(got, base), name
         else:
-            assert err < 2e-2, name
+            assert l2 < 6e-2, name   # same scale as the bf16-vs-fp32 first-step error (test_gpu_parity)
