@@ -56,9 +56,23 @@ class VaeDecoder(C.Structure):
                 ("n_out", C.c_int32)]
 
 
+VAE_ENC_LAYER_FIELDS = ["ln1_g", "ln1_b", "w_in", "b_in", "w_so", "b_so", "ln2_g", "ln2_b", "w_ff1", "b_ff1", "w_ff2", "b_ff2"]
+
+
+class VaeEncLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in VAE_ENC_LAYER_FIELDS]
+
+
+class VaeEncoder(C.Structure):
+    _fields_ = [("layers", C.POINTER(VaeEncLayer)), ("w_skip", C.c_void_p * 4), ("b_skip", C.c_void_p * 4),
+                ("lnf_g", C.c_void_p), ("lnf_b", C.c_void_p), ("tokens", C.c_void_p), ("w_emb", C.c_void_p),
+                ("b_emb", C.c_void_p), ("n_in", C.c_int32), ("col0", C.c_int32)]
+
+
 class VaeWeights(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("d_model", "n_layers", "n_heads", "ff_size", "precision", "pe_len")] +
-                [("pe_query", C.c_void_p), ("pe_mem", C.c_void_p), ("part", VaeDecoder * 2)])
+                [("pe_query", C.c_void_p), ("pe_mem", C.c_void_p), ("part", VaeDecoder * 2),
+                 ("pe_enc", C.c_void_p), ("enc", VaeEncoder * 2)])
 
 
 # name -> (restype, argtypes); every symbol include/convofusion_b200.h declares.
@@ -77,6 +91,7 @@ PROTOTYPES = {
     "cfb_vae_create": (C.c_int, [C.POINTER(VaeWeights), C.POINTER(_P)]),
     "cfb_vae_destroy": (None, [_P]),
     "cfb_vae_decode": (C.c_int, [_P, _P, _I, _I, _I, C.POINTER(C.c_int32), _P, _P]),
+    "cfb_vae_encode": (C.c_int, [_P, _P, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _P]),
     "cfb_linear": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cfb_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfb_mha": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -187,7 +187,64 @@ __global__ void mask_frames_kernel(float* __restrict__ out, const int* __restric
   if (l >= lengths[b]) out[i] = 0.f;
 }
 
+// vae.py:176-186: per 16-frame chunk, subtract the first frame's root x and z from every frame of the chunk.
+__global__ void chunk_root_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, int nf, int chunk) {
+  pdl_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long r = i / nf;
+  const int c = (int)(i % nf);
+  float v = in[i];
+  if (c < 3) v = __fsub_rn(v, __fmul_rn(in[(r - r % chunk) * nf + c], c == 1 ? 0.f : 1.f));
+  out[i] = v;
+}
+
+// vae.py:204-224: token rows of one part, sample-major: [n_tok distribution tokens ; chunk frame embeddings] + pe.
+__global__ void enc_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ tokens,
+                                    const float* __restrict__ pe, float* __restrict__ h, int n, int n_tok, int chunk, int d) {
+  pdl_sync();
+  const int L = n_tok + chunk;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * L * d) return;
+  const int c = (int)(i % d);
+  const int l = (int)((i / d) % L);
+  const long long s = i / ((long long)d * L);
+  const float v = l < n_tok ? tokens[(size_t)l * d + c] : emb[((size_t)s * chunk + (l - n_tok)) * d + c];
+  h[i] = v + pe[(size_t)l * d + c];
+}
+
+// vae.py:250-260: mu = token 0, logvar = token 1 of the normalised encoder output; std = exp(logvar)^0.5.
+__global__ void enc_dist_kernel(const float* __restrict__ y, float* __restrict__ mu, float* __restrict__ sd, int n, int L, int d) {
+  pdl_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * d) return;
+  const long long s = i / d;
+  const int c = (int)(i % d);
+  mu[i] = y[(s * L) * d + c];
+  sd[i] = sqrtf(expf(y[(s * L + 1) * d + c]));
+}
+
 }  // namespace
+
+int chunk_root(const float* in, float* out, long long n_rows, int nf, int chunk, cudaStream_t st) {
+  const long long n = n_rows * nf;
+  launch_k(chunk_root_kernel, (unsigned)((n + 255) / 256), 256, 0, st, in, out, n, nf, chunk);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+int enc_assemble(const float* emb, const float* tokens, const float* pe, float* h, int n, int n_tok, int chunk, int d,
+                 cudaStream_t st) {
+  const long long t = (long long)n * (n_tok + chunk) * d;
+  launch_k(enc_assemble_kernel, (unsigned)((t + 255) / 256), 256, 0, st, emb, tokens, pe, h, n, n_tok, chunk, d);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStream_t st) {
+  const long long t = (long long)n * d;
+  launch_k(enc_dist_kernel, (unsigned)((t + 255) / 256), 256, 0, st, y, mu, sd, n, L, d);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
 
 template <typename T>
 int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,

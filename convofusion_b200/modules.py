@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -349,7 +349,7 @@ class _Skip(nn.Module):   # cross_attention.py:18-39 / 66-87
 
 
 class ConvoFusionVae(_CudaModule):
-    """Drop-in for convofusion.models.architectures.vae.ConvoFusionVae (decode side on the B200).
+    """Drop-in for convofusion.models.architectures.vae.ConvoFusionVae (encode and decode on the B200).
     The class name is load-bearing: convofusion.py:67-71 derives vae_type from it."""
 
     def __init__(self, ablation=None, nfeats: int = 189, latent_dim: list = [1, 256], ff_size: int = 1024,
@@ -417,10 +417,46 @@ class ConvoFusionVae(_CudaModule):
                                                  out.data_ptr(), _lib.stream_ptr()))
         return out
 
+    def encode_params(self, features: Tensor, lengths: Optional[List[int]] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """Deterministic part of encode (vae.py:162-260): (mu, std [2, B*T/16, d], root-subtracted features)."""
+        dev = self._device()
+        if self._handle is None:
+            self.pack()
+        if features.dim() != 3 or features.shape[-1] != self.body_nfeats + self.hands_nfeats:
+            raise ValueError(f"features must be [B, T, {self.body_nfeats + self.hands_nfeats}], got {tuple(features.shape)}")
+        bs, nframes, nfeats = features.shape
+        if lengths is None:
+            lengths = [len(f) for f in features]
+        lengths = [int(l) for l in lengths]
+        if len(lengths) != bs:
+            raise ValueError(f"{len(lengths)} lengths for batch {bs}")
+        if nframes % 16 or max(lengths) != nframes:
+            # the reference reshapes lengths_to_mask(lengths) ([B, max(lengths)]) to [B*T/16, 16] (vae.py:173,187)
+            raise ValueError("encode needs T to be a multiple of 16 and max(lengths) == T")
+        x = features.detach().to(device=dev, dtype=torch.float32).contiguous()
+        n = bs * (nframes // 16)
+        mu = torch.empty(2 * self.latent_size, n, self.latent_dim, device=dev, dtype=torch.float32)
+        std = torch.empty_like(mu)
+        feats = torch.empty_like(x)
+        lens = (C.c_int32 * bs)(*lengths)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cfb_vae_encode(self._handle, x.data_ptr(), bs, nframes, lens, mu.data_ptr(),
+                                                 std.data_ptr(), feats.data_ptr(), _lib.stream_ptr()))
+        return mu, std, feats
+
     def encode(self, features: Tensor, lengths: Optional[List[int]] = None):
-        # vae.py:162-266 is adjacent to the hot path: not built yet, and there is no
-        # silent torch fallback.
-        raise NotImplementedError("ConvoFusionVae.encode is not part of the B200 hot path yet (SURVEY 8f)")
+        """vae.py:162-266: returns (latent [2, B, T/16, d], Normal(mu, std), root-subtracted features)."""
+        if self.latent_size != 1:
+            raise ValueError("latent_size != 1 is not implemented")
+        mu, std, feats = self.encode_params(features, lengths)
+        dist = torch.distributions.Normal(mu, std)
+        latent = dist.rsample()                                   # vae.py:261-262 (torch RNG, like the reference)
+        bs = features.shape[0]
+        return latent.reshape(-1, bs, features.shape[1] // 16, self.latent_dim), dist, feats
 
     def forward(self, features: Tensor, lengths: Optional[List[int]] = None):
-        raise NotImplementedError("ConvoFusionVae.forward (encode + decode) is not part of the B200 hot path")
+        """vae.py:145-160: encode, then decode the sampled latent."""
+        z, dist, _ = self.encode(features, lengths)
+        if lengths is None:
+            lengths = [len(f) for f in features]
+        return self.decode(z, lengths), z, dist

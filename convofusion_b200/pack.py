@@ -158,4 +158,30 @@ def pack_vae(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: int, ff
         D.w_final = pk.mat(sd[p + f"{part}_final_layer.weight"])
         D.b_final = pk.vec(sd[p + f"{part}_final_layer.bias"])
         D.n_out = sd[p + f"{part}_final_layer.weight"].shape[0]
+    # encode side (vae.py:162-266)
+    w.pe_enc = pk.vec(sd[p + "query_pos_encoder.pe"].detach().float().cpu()[:, 0])
+    col0 = 0
+    for pi, part in enumerate(("body", "hands")):
+        ep = f"{p}{part}_encoder."
+        names = [f"input_blocks.{i}." for i in range(nb)] + ["middle_block."] + [f"output_blocks.{i}." for i in range(nb)]
+        layers = (_lib.VaeEncLayer * n_layers)()
+        for li, nm in enumerate(names):
+            lp, L = ep + nm, layers[li]
+            L.ln1_g, L.ln1_b = pk.vec(sd[lp + "norm1.weight"]), pk.vec(sd[lp + "norm1.bias"])
+            L.w_in, L.b_in = pk.mat(sd[lp + "self_attn.in_proj_weight"]), pk.vec(sd[lp + "self_attn.in_proj_bias"])
+            L.w_so, L.b_so = pk.mat(sd[lp + "self_attn.out_proj.weight"]), pk.vec(sd[lp + "self_attn.out_proj.bias"])
+            L.ln2_g, L.ln2_b = pk.vec(sd[lp + "norm2.weight"]), pk.vec(sd[lp + "norm2.bias"])
+            L.w_ff1, L.b_ff1 = pk.mat(sd[lp + "linear1.weight"]), pk.vec(sd[lp + "linear1.bias"])
+            L.w_ff2, L.b_ff2 = pk.mat(sd[lp + "linear2.weight"]), pk.vec(sd[lp + "linear2.bias"])
+        arrays.append(layers)
+        E = w.enc[pi]
+        E.layers = C.cast(layers, C.POINTER(_lib.VaeEncLayer))
+        for i in range(nb):
+            E.w_skip[i] = pk.mat(sd[ep + f"linear_blocks.{i}.weight"])
+            E.b_skip[i] = pk.vec(sd[ep + f"linear_blocks.{i}.bias"])
+        E.lnf_g, E.lnf_b = pk.vec(sd[ep + "norm.weight"]), pk.vec(sd[ep + "norm.bias"])
+        E.tokens = pk.vec(sd[p + f"{part}_global_motion_token"])
+        E.w_emb, E.b_emb = pk.vec(sd[p + f"{part}_skel_embedding.weight"]), pk.vec(sd[p + f"{part}_skel_embedding.bias"])
+        E.n_in, E.col0 = sd[p + f"{part}_skel_embedding.weight"].shape[1], col0
+        col0 += E.n_in
     return {"struct": w, "layers": arrays, "keep": pk.keep}

@@ -181,10 +181,30 @@ typedef struct {
   const void  *w_final; const float *b_final; int32_t n_out;   /* {body,hands}_final_layer [n_out, d] */
 } cfb_vae_decoder;
 
+/* Encode side (architectures/vae.py:162-266): SkipTransformerEncoder of pre-norm TransformerEncoderLayers
+ * (cross_attention.py:41-64, 288-300) over 2 distribution tokens + 16 frames per 16-frame chunk. */
+typedef struct {
+  const float *ln1_g, *ln1_b; const void *w_in; const float *b_in;   /* self_attn.in_proj [3d,d] */
+  const void  *w_so; const float *b_so;
+  const float *ln2_g, *ln2_b; const void *w_ff1; const float *b_ff1;
+  const void  *w_ff2; const float *b_ff2;
+} cfb_vae_enc_layer;
+
+typedef struct {
+  const cfb_vae_enc_layer *layers;  /* host [n_layers] or NULL when the encode side is not provided */
+  const void  *w_skip[4]; const float *b_skip[4];
+  const float *lnf_g, *lnf_b;       /* encoder.norm */
+  const float *tokens;              /* {body,hands}_global_motion_token [2, d] */
+  const float *w_emb, *b_emb;       /* {body,hands}_skel_embedding [d, n_in] (always float) */
+  int32_t n_in, col0;               /* feature columns [col0, col0 + n_in) of the 189-wide input */
+} cfb_vae_encoder;
+
 typedef struct {
   int32_t d_model, n_layers, n_heads, ff_size, precision, pe_len;
   const float *pe_query, *pe_mem;   /* query_pos_decoder.pe / mem_pos_decoder.pe [pe_len, d] */
   cfb_vae_decoder part[2];          /* body, hands */
+  const float *pe_enc;              /* query_pos_encoder.pe [pe_len, d] */
+  cfb_vae_encoder enc[2];           /* body, hands */
 } cfb_vae_weights;
 
 typedef struct cfb_vae cfb_vae;
@@ -193,6 +213,11 @@ void cfb_vae_destroy(cfb_vae *h);
 /* z [2, B, n_chunks, d] float; lengths host [B]; out [B, n_frames, n_out_body+n_out_hands]. */
 int cfb_vae_decode(cfb_vae *h, const float *z, int n_clips, int n_chunks, int n_frames,
                    const int32_t *lengths_host, float *out, cfb_stream stream);
+/* Replaces the deterministic part of ConvoFusionVae.encode (vae.py:162-258): features [B, T, 189] (T a multiple of
+ * 16) -> mu, std [2, B*T/16, d] (body then hands; torch.distributions.Normal(mu, std) is built by the caller) and the
+ * chunk-root-subtracted features [B, T, 189] (third return value of encode). */
+int cfb_vae_encode(cfb_vae *h, const float *features, int n_clips, int n_frames, const int32_t *lengths_host,
+                   float *mu_out, float *std_out, float *feats_out, cfb_stream stream);
 
 /* ------------------------------------------------------------------ unit ops ----- */
 /* Exposed so tests/ can check each kernel against the oracle through the same ABI.

@@ -240,6 +240,62 @@ def vae_decode(sd: Dict[str, Tensor], z: Tensor, lengths: Sequence[int], prefix:
     return output.permute(1, 0, 2)
 
 
+def vae_encoder_layer(sd, pfx, src, kpm, nheads):
+    """cross_attention.py:288-300 TransformerEncoderLayer.forward_pre (pos None)."""
+    s2 = _ln(sd, pfx + "norm1.", src)
+    s2, _ = _mha_sd(sd, pfx + "self_attn.", s2, s2, s2, nheads, kpm)
+    src = src + s2
+    s2 = _ln(sd, pfx + "norm2.", src)
+    s2 = _lin(sd, pfx + "linear2.", F.gelu(_lin(sd, pfx + "linear1.", s2)))
+    return src + s2
+
+
+def skip_encoder(sd, pfx, src, kpm, nheads, num_layers=5):
+    """cross_attention.py:41-64 SkipTransformerEncoder.forward."""
+    nb = (num_layers - 1) // 2
+    x, xs = src, []
+    for i in range(nb):
+        x = vae_encoder_layer(sd, pfx + f"input_blocks.{i}.", x, kpm, nheads)
+        xs.append(x)
+    x = vae_encoder_layer(sd, pfx + "middle_block.", x, kpm, nheads)
+    for i in range(nb):
+        x = torch.cat([x, xs.pop()], dim=-1)
+        x = _lin(sd, pfx + f"linear_blocks.{i}.", x)
+        x = vae_encoder_layer(sd, pfx + f"output_blocks.{i}.", x, kpm, nheads)
+    return _ln(sd, pfx + "norm.", x)
+
+
+def vae_encode(sd: Dict[str, Tensor], features: Tensor, lengths: Sequence[int], prefix: str = "",
+               num_layers: int = 5, num_heads: int = 2):
+    """vae.py:162-258 (MLP_DIST False, pe_type convofusion) up to the distribution parameters:
+    returns (mu, std [2, B*T/16, d], chunk-root-subtracted features [B, T, 189])."""
+    p = prefix
+    bs, nframes, _ = features.shape
+    mask = lengths_to_mask(lengths, nframes)
+    n_chunks = nframes // 16
+    mf = features.clone().reshape(bs * n_chunks, 16, -1)
+    root = mf[:, :1, :3] * torch.tensor([1.0, 0.0, 1.0], dtype=features.dtype)          # :182-184
+    mf[:, :, :3] = mf[:, :, :3] - root
+    mask = mask.reshape(bs * n_chunks, 16)
+    n = bs * n_chunks
+    pe = sd[p + "query_pos_encoder.pe"][:, 0]
+    mus, lvs = [], []
+    nb_feats = sd[p + "body_skel_embedding.weight"].shape[1]
+    for part, xs_ in (("body", mf[:, :, :nb_feats]), ("hands", mf[:, :, nb_feats:])):
+        x = _lin(sd, p + f"{part}_skel_embedding.", xs_).permute(1, 0, 2)               # [16, n, d]
+        tok = sd[p + f"{part}_global_motion_token"]
+        dist = torch.tile(tok[:, None, :], (1, n, 1))                                   # :204-205
+        aug = torch.cat((torch.ones(n, tok.shape[0], dtype=torch.bool), mask), 1)        # :208-216
+        xseq = torch.cat((dist, x), 0)
+        xseq = xseq + pe[: xseq.shape[0], None]                                         # :224
+        out = skip_encoder(sd, p + f"{part}_encoder.", xseq, ~aug, num_heads, num_layers)[: tok.shape[0]]
+        mus.append(out[0:1])
+        lvs.append(out[1:2])
+    mu, logvar = torch.cat(mus, 0), torch.cat(lvs, 0)                                   # :250-257
+    std = logvar.exp().pow(0.5)                                                          # :260
+    return mu, std, mf.reshape(bs, nframes, -1)
+
+
 # --------------------------------------------------------------------------- conditioning
 def audio_encoder(sd, mel: Tensor, prefix: str = "text_audio_encoder.audio_encoder.") -> Tensor:
     """audioenc.py:13-34: Linear -> LeakyReLU(0.1) -> Linear -> LeakyReLU(0.1) -> out_net."""

@@ -139,6 +139,36 @@ def test_vae_decode_fp32_vs_reference(lengths_key):
         s.vae.decode(z.to(DEV), [0] * z.shape[1])
 
 
+def test_vae_encode_vs_reference():
+    """ConvoFusionVae.encode on the device against the reference module's outputs (vae.py:162-266)."""
+    g = golden("vae_encode.pt")
+    x = torch.randn(3, 128, 189, generator=torch.Generator().manual_seed(6))
+    s = gpu_sampler("fp32")
+    mu, std, feats = s.vae.encode_params(x.to(DEV), g["lengths"])
+    assert mu.shape == g["mu"].shape
+    assert max_rel(mu.cpu(), g["mu"]) < 1e-4 and max_rel(std.cpu(), g["std"]) < 1e-4
+    assert torch.equal(feats.cpu(), g["feats"])                      # byte-exact: one subtraction per element
+    mu2, std2, _ = s.vae.encode_params(x[:2, :32].contiguous().to(DEV), g["short_lengths"])
+    assert max_rel(mu2.cpu(), g["short_mu"]) < 1e-4 and max_rel(std2.cpu(), g["short_std"]) < 1e-4
+    # public surface: (latent [2,B,8,128], Normal, feats); rsample = mu + std * N(0,1) from torch's generator
+    torch.manual_seed(3)
+    z, dist, f2 = s.vae.encode(x.to(DEV), g["lengths"])
+    assert z.shape == (2, 3, 8, 128) and torch.equal(dist.loc, mu) and torch.equal(dist.scale, std)
+    torch.manual_seed(3)
+    assert torch.equal(z.reshape(2, 24, 128), torch.distributions.Normal(mu, std).rsample())
+    # encode -> decode round trip runs and keeps the padding contract
+    rec = s.vae.decode(z, g["lengths"])
+    assert rec.shape == (3, 128, 189) and float(rec[2, 37:].abs().max().cpu()) == 0.0
+    with pytest.raises(ValueError):
+        s.vae.encode(x[:, :120].to(DEV), [120, 100, 37])
+    # bf16 tolerance (operands rounded to bf16, fp32 accumulation and residual stream)
+    sb = gpu_sampler("bf16")
+    mub, stdb, featsb = sb.vae.encode_params(x.to(DEV), g["lengths"])
+    eb = max(max_rel(mub.cpu(), g["mu"]), max_rel(stdb.cpu(), g["std"]))
+    print(f"bf16 vae encode max-rel error {eb:.3e}")
+    assert eb < 5e-2 and torch.equal(featsb.cpu(), g["feats"])
+
+
 def test_vae_decode_bf16_tolerance():
     s = gpu_sampler("bf16")
     g = golden("vae_decode.pt")
@@ -199,6 +229,31 @@ def test_ddpm_with_step_noise_vs_reference():
         s.sample(enc, masks, 1, init)
     _, rec, _ = s.sample(enc, masks, 1, init, step_noise=noise, record=True)
     assert min(frac_within(rec[i].cpu(), g["record"][i], 1e-4) for i in range(10)) >= 0.9
+
+
+def test_ddim_eta_with_step_noise_vs_oracle():
+    """Stochastic DDIM (eta = 0.7): prev = ... + sigma_t * variance_noise, oracle on the same noise (4 steps)."""
+    s = gpu_sampler("fp32", 4, cf.DDIMScheduler(clip_sample=True, **SCHED_KW))
+    s.eta = 0.7
+    try:
+        syn = synthetic_clip(1, seed=1235, dyadic=False)
+        enc, masks = gpu_batch(s, syn)
+        init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(100))
+        noise = torch.randn(4, 1, 16, 128, generator=torch.Generator().manual_seed(102))
+        with pytest.raises(ValueError):
+            s.sample(enc, masks, 1, init.to(DEV))
+        _, rec, _ = s.sample(enc, masks, 1, init.to(DEV), step_noise=noise.to(DEV), record=True)
+        enc_o, masks_o = oracle_batch(syn)
+        want = []
+        O.diffusion_reverse(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW), enc_o, masks_o, init,
+                            4, eta=0.7, step_noise=noise, record=want)
+        assert min(frac_within(rec[i].cpu(), want[i], 1e-4) for i in range(4)) >= 0.9
+        # eta actually changes the trajectory
+        s.eta = 0.0
+        _, rec0, _ = s.sample(enc, masks, 1, init.to(DEV), record=True)
+        assert max_rel(rec0[0].cpu(), want[0]) > 1e-2
+    finally:
+        s.eta = 0.0
 
 
 def test_unbounded_synthesis_vs_reference():

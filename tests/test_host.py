@@ -144,7 +144,10 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.Schedule) == 16 + 16
     assert ctypes.sizeof(_lib.VaeLayer) == 20 * 8
     assert ctypes.sizeof(_lib.VaeDecoder) == 8 + 32 + 32 + 32 + 8
-    assert ctypes.sizeof(_lib.VaeWeights) == 24 + 16 + 2 * ctypes.sizeof(_lib.VaeDecoder)
+    assert ctypes.sizeof(_lib.VaeEncLayer) == 12 * 8
+    assert ctypes.sizeof(_lib.VaeEncoder) == 8 + 32 + 32 + 5 * 8 + 8
+    assert ctypes.sizeof(_lib.VaeWeights) == (24 + 16 + 2 * ctypes.sizeof(_lib.VaeDecoder) + 8 +
+                                              2 * ctypes.sizeof(_lib.VaeEncoder))
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks behaviour on a box without a GPU")

@@ -47,6 +47,20 @@ def test_denoiser_dyadic_matches_reference():
     _denoiser_case("dyad_b2", 2, True)
 
 
+def test_vae_encode_matches_reference_ragged():
+    """ConvoFusionVae.encode (vae.py:162-266): distribution parameters and root-subtracted features."""
+    sd = state_dict()
+    g = golden("vae_encode.pt")
+    x = torch.randn(3, 128, 189, generator=torch.Generator().manual_seed(6))
+    mu, std, feats = O.vae_encode(sd, x, g["lengths"], prefix="vae.")
+    assert mu.shape == (2, 24, 128) and feats.shape == (3, 128, 189)
+    assert max_rel(mu, g["mu"]) < TOL and max_rel(std, g["std"]) < TOL
+    assert torch.equal(feats, g["feats"])
+    assert torch.equal(feats[:, :, 3:], x[:, :, 3:]) and float(feats[:, ::16, [0, 2]].abs().max()) == 0.0
+    mu2, std2, _ = O.vae_encode(sd, x[:2, :32], g["short_lengths"], prefix="vae.")   # a fully padded second chunk
+    assert max_rel(mu2, g["short_mu"]) < TOL and max_rel(std2, g["short_std"]) < TOL
+
+
 def test_vae_decode_matches_reference_ragged():
     sd = state_dict()
     z = torch.randn(2, 3, 8, 128, generator=torch.Generator().manual_seed(5))

@@ -126,6 +126,14 @@ with torch.no_grad():
     save("vae_decode.pt", {"lengths": [128, 100, 37], "out": ref_vae.decode(z, [128, 100, 37])})
     save("vae_decode_short.pt", {"lengths": [64, 33], "out": ref_vae.decode(z[:, :2], [64, 33])})
 
+# 3b - VAE encode (distribution parameters + root-subtracted features), ragged lengths ------------
+xf = torch.randn(3, 128, 189, generator=torch.Generator().manual_seed(6))
+with torch.no_grad():
+    _, dist_e, feats_e = ref_vae.encode(xf, [128, 100, 37])
+    _, dist_s, feats_s = ref_vae.encode(xf[:2, :32], [32, 5])
+    save("vae_encode.pt", {"lengths": [128, 100, 37], "mu": dist_e.loc, "std": dist_e.scale, "feats": feats_e,
+                           "short_lengths": [32, 5], "short_mu": dist_s.loc, "short_std": dist_s.scale})
+
 # 4 -- full sampling run, config 1 of BASELINE.json: B=1, DDIM-50, guidance 7.5, then decode ------
 syn = synthetic_clip(1, seed=1235, dyadic=False)
 enc, masks = ref_guidance_batch(syn)
