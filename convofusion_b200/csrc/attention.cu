@@ -409,43 +409,187 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
   }
 }
 
-constexpr int ATT_MAX_SMEM = 160 * 1024;
 
-// Denoiser self-attention (cross_attention.py:570): 16 tokens, head_dim 128.  One warp owns one
-// (sample, head); lane = (query i, parity p).  q/k/v of the head are staged as float in shared memory
+// Tensor-core multi-head attention core for bf16 (mma.sync.m16n8k16, fp32 accumulation): one warp owns 16 query rows
+// of one (sample, head); K, V (zero-padded to NKT 16-key tiles) and the block's Q rows are staged once in shared
+// memory with cp.async.  Scores stay in registers: the accumulator layout of S = Q K^T is exactly the A-fragment
+// layout of the second product, so softmax(S) is normalised, rounded to bf16 and fed to P V without leaving the
+// warp.  Used for the denoiser self-attention (16 x 16, head_dim 128) and the VAE attentions (head_dim 64; 128 x 128
+// self, 128 x 8 cross, 18 x 18 encoder).
+template <int HD, int NKT>
+__global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
+                                                      const bf16* __restrict__ v, int ldk, bf16* __restrict__ out, int ldo,
+                                                      int Lq, int Lk, const int* __restrict__ kv_len, float scale) {
+  pdl_sync();
+  constexpr int P = HD + 8;                    // bf16 row pitch: rows shift by 16 B -> conflict-free ldmatrix
+  constexpr int CH = HD / 8;                   // 16-byte chunks per row
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int b = blockIdx.x, h = blockIdx.y, q0 = blockIdx.z * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nq = blockDim.x >> 1;              // query rows staged by this block (16 per warp)
+  bf16* Ks = reinterpret_cast<bf16*>(smraw);   // [NKT*16][P]
+  bf16* Vs = Ks + NKT * 16 * P;
+  bf16* Qs = Vs + NKT * 16 * P;                // [nq][P]
+  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks);
+  const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(Qs);
+  const int valid = kv_len ? min(kv_len[b], Lk) : Lk;
+  for (int i = threadIdx.x; i < NKT * 16 * CH; i += blockDim.x) {
+    const int r = i / CH, ch = i % CH;
+    if (r < Lk) {
+      cp_async16(ks_addr + (uint32_t)((r * P + ch * 8) * 2), k + (size_t)(b * Lk + r) * ldk + h * HD + ch * 8);
+      cp_async16(vs_addr + (uint32_t)((r * P + ch * 8) * 2), v + (size_t)(b * Lk + r) * ldk + h * HD + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + r * P + ch * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + r * P + ch * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int i = threadIdx.x; i < nq * CH; i += blockDim.x) {
+    const int r = i / CH, ch = i % CH;
+    if (q0 + r < Lq) cp_async16(qs_addr + (uint32_t)((r * P + ch * 8) * 2), q + (size_t)(b * Lq + q0 + r) * ldq + h * HD + ch * 8);
+    else *reinterpret_cast<uint4*>(Qs + r * P + ch * 8) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int row0 = q0 + warp * 16;
+  if (row0 >= Lq) return;
+  // ---- S = Q K^T
+  float s[NKT * 2][4];
+#pragma unroll
+  for (int n = 0; n < NKT * 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < HD / 16; ++kk) {
+    uint32_t af[4];
+    ldsm_x4(af, qs_addr + (uint32_t)(((warp * 16 + (lane & 15)) * P + kk * 16 + (lane >> 4) * 8) * 2));
+#pragma unroll
+    for (int j = 0; j < NKT; ++j) {
+      uint32_t bf[4];
+      ldsm_x4(bf, ks_addr + (uint32_t)(((j * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * P + kk * 16 + ((lane >> 3) & 1) * 8) * 2));
+      mma_bf16_16816(s[2 * j], af, bf[0], bf[1]);
+      mma_bf16_16816(s[2 * j + 1], af, bf[2], bf[3]);
+    }
+  }
+  // ---- softmax over the valid keys (rows g and g + 8 of this warp's tile; a row lives in one quad)
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < NKT * 2; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool dead = n * 8 + 2 * t + e >= valid;
+      s[n][e] = dead ? -INFINITY : s[n][e] * scale;
+      s[n][2 + e] = dead ? -INFINITY : s[n][2 + e] * scale;
+      mx0 = fmaxf(mx0, s[n][e]);
+      mx1 = fmaxf(mx1, s[n][2 + e]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NKT * 2; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s[n][e] = expf(s[n][e] - mx0); sum0 += s[n][e];
+      s[n][2 + e] = expf(s[n][2 + e] - mx1); sum1 += s[n][2 + e];
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  // ---- O = P V
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NKT; ++j) {
+    uint32_t af[4];
+    {
+      const __nv_bfloat162 a0 = __floats2bfloat162_rn(s[2 * j][0] * inv0, s[2 * j][1] * inv0);
+      const __nv_bfloat162 a1 = __floats2bfloat162_rn(s[2 * j][2] * inv1, s[2 * j][3] * inv1);
+      const __nv_bfloat162 a2 = __floats2bfloat162_rn(s[2 * j + 1][0] * inv0, s[2 * j + 1][1] * inv0);
+      const __nv_bfloat162 a3 = __floats2bfloat162_rn(s[2 * j + 1][2] * inv1, s[2 * j + 1][3] * inv1);
+      af[0] = *reinterpret_cast<const uint32_t*>(&a0); af[1] = *reinterpret_cast<const uint32_t*>(&a1);
+      af[2] = *reinterpret_cast<const uint32_t*>(&a2); af[3] = *reinterpret_cast<const uint32_t*>(&a3);
+    }
+    const int brow = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int nn = 0; nn < HD / 16; ++nn) {
+      uint32_t bf[4];
+      ldsm_x4_trans(bf, vs_addr + (uint32_t)((brow * P + nn * 16 + (lane >> 4) * 8) * 2));
+      mma_bf16_16816(o[2 * nn], af, bf[0], bf[1]);
+      mma_bf16_16816(o[2 * nn + 1], af, bf[2], bf[3]);
+    }
+  }
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    const int col = h * HD + n * 8 + 2 * t;
+    if (r_lo < Lq) *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(b * Lq + r_lo) * ldo + col) = __floats2bfloat162_rn(o[n][0], o[n][1]);
+    if (r_hi < Lq) *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(b * Lq + r_hi) * ldo + col) = __floats2bfloat162_rn(o[n][2], o[n][3]);
+  }
+}
+
+template <int HD, int NKT>
+int launch_mha_mma(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
+                   int n_heads, const int* kv_len, cudaStream_t st) {
+  const int warps = Lq >= 64 ? 4 : ceil_div(Lq, 16);
+  const size_t smem = (size_t)(2 * NKT * 16 + warps * 16) * (HD + 8) * 2;
+  dim3 grid(n, n_heads, ceil_div(Lq, 64));
+  launch_k(mha_mma_kernel<HD, NKT>, grid, warps * 32, smem, st, q, ldq, k, v, ldk, out, ldo, Lq, Lk, kv_len,
+           sqrtf(1.0f / (float)HD));
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+constexpr int ATT_MAX_SMEM = 160 * 1024;
+int g_mha_simt = 0;   // env CFB_MHA_SIMT=1: CUDA-core attention kernels in bf16 mode too
+
+// Denoiser self-attention (cross_attention.py:570): 16 tokens, head_dim 128.  One single-warp block owns one
+// (sample, head) -- 25 KB of shared memory, so the blocks slot in beside resident GEMM CTAs instead of waiting for a
+// whole SM; lane = (query i, parity p).  q/k/v of the head are staged as float in shared memory
 // with a 132-float row pitch so every 128-bit access below is conflict-free per quarter-warp: lane
 // (i,p) scores keys j = 2*jj+p (adjacent rows -> banks +4) and accumulates output chunks 2*c+p.
 constexpr int SA_L = 16, SA_HD = 128, SA_PITCH = 132;
 
 template <typename T>
-__global__ void __launch_bounds__(128) self_attn16_kernel(const T* __restrict__ qkv, int ld, int E,
-                                                          T* __restrict__ out, int ldo, int n_heads) {
+__global__ void __launch_bounds__(32) self_attn16_kernel(const T* __restrict__ qkv, int ld, int E,
+                                                         T* __restrict__ out, int ldo, int n_heads) {
   pdl_sync();
   extern __shared__ float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y * 4 + warp;
-  if (h >= n_heads) return;
+  const int lane = threadIdx.x;
+  const int h = blockIdx.y;
   const int b = blockIdx.x;
-  float* Q = sm + warp * 3 * SA_L * SA_PITCH;
+  float* Q = sm;
   float* K = Q + SA_L * SA_PITCH;
   float* V = K + SA_L * SA_PITCH;
-  for (int r = 0; r < 3 * SA_L; ++r) {           // 48 rows of 128 elements, 4 per lane: coalesced
-    const int which = r / SA_L, row = r % SA_L;
-    const T* src = qkv + (size_t)(b * SA_L + row) * ld + which * E + h * SA_HD + lane * 4;
-    float4 v;
-    if constexpr (sizeof(T) == 4) {
-      v = *reinterpret_cast<const float4*>(src);
-    } else {
-      const uint2 t = *reinterpret_cast<const uint2*>(src);
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-      v = make_float4(__low2float(a), __high2float(a), __low2float(c), __high2float(c));
+  // 48 rows of 128 elements, 4 per lane (coalesced); 12 rows are in flight per round trip
+  constexpr int RBATCH = 12;
+#pragma unroll 1
+  for (int r0 = 0; r0 < 3 * SA_L; r0 += RBATCH) {
+    float4 v[RBATCH];
+#pragma unroll
+    for (int k = 0; k < RBATCH; ++k) {
+      const int r = r0 + k, which = r / SA_L, row = r % SA_L;
+      const T* src = qkv + (size_t)(b * SA_L + row) * ld + which * E + h * SA_HD + lane * 4;
+      if constexpr (sizeof(T) == 4) {
+        v[k] = *reinterpret_cast<const float4*>(src);
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(src);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        v[k] = make_float4(__low2float(a), __high2float(a), __low2float(c), __high2float(c));
+      }
     }
-    if (which == 0) {                            // torch scales q by sqrt(1/head_dim) before q k^T
-      const float s = sqrtf(1.0f / (float)SA_HD);
-      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+#pragma unroll
+    for (int k = 0; k < RBATCH; ++k) {
+      const int r = r0 + k, which = r / SA_L, row = r % SA_L;
+      if (which == 0) {                          // torch scales q by sqrt(1/head_dim) before q k^T
+        const float s = sqrtf(1.0f / (float)SA_HD);
+        v[k].x *= s; v[k].y *= s; v[k].z *= s; v[k].w *= s;
+      }
+      *reinterpret_cast<float4*>(Q + which * SA_L * SA_PITCH + row * SA_PITCH + lane * 4) = v[k];
     }
-    *reinterpret_cast<float4*>(Q + which * SA_L * SA_PITCH + row * SA_PITCH + lane * 4) = v;
   }
   __syncwarp();
   const int i = lane >> 1, p = lane & 1;
@@ -505,7 +649,7 @@ __global__ void __launch_bounds__(128) self_attn16_kernel(const T* __restrict__ 
   }
 }
 
-constexpr int SA_SMEM = 4 * 3 * SA_L * SA_PITCH * (int)sizeof(float);   // 101,376 B per 4-warp block
+constexpr int SA_SMEM = 3 * SA_L * SA_PITCH * (int)sizeof(float);   // 25,344 B per one-warp block: fits beside two GEMM CTAs
 
 // One warp per query row; see SharedAttnArgs.
 __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __restrict__ S, bf16* __restrict__ P,
@@ -598,7 +742,7 @@ int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_
 
 int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
   const int rows = n_batch * n_tokens;
-  if (rows <= 0) return CFB_OK;
+  if (rows <= 0 || debug_skip(4)) return CFB_OK;
   launch_k(softmax_shared_kernel, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
@@ -611,6 +755,7 @@ namespace {
 int init_attention_kernels() {
   static bool done = false;
   if (done) return CFB_OK;
+  if (const char* e = getenv("CFB_MHA_SIMT")) g_mha_simt = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
@@ -625,13 +770,23 @@ int init_attention_kernels() {
 template <typename T>
 int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, int n, int Lq, int Lk, int n_heads,
         int head_dim, const int* kv_len, cudaStream_t st) {
-  if (n <= 0) return CFB_OK;
+  if (n <= 0 || debug_skip(2)) return CFB_OK;
   CFB_CHECK(Lq > 0 && Lk > 0 && head_dim > 0 && n_heads > 0, "mha: bad shape");
+  if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernel (CFB_GEMM_SIMT keeps the CUDA-core engines for cross-checks)
+    const bool aligned = ldq % 8 == 0 && ldk % 8 == 0 && ldo % 2 == 0 && ((uintptr_t)q % 16 == 0) &&
+                         ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 4 == 0);
+    if (aligned && g_gemm_backend != CFB_GEMM_SIMT && !g_mha_simt) {
+      if (head_dim == 128 && Lk <= 16) return launch_mha_mma<128, 1>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
+      if (head_dim == 64 && Lk <= 16) return launch_mha_mma<64, 1>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
+      if (head_dim == 64 && Lk <= 32) return launch_mha_mma<64, 2>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
+      if (head_dim == 64 && Lk <= 128) return launch_mha_mma<64, 8>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
+    }
+  }
   // packed self-attention of the denoiser: q, k, v are column blocks of one [rows, 3E] matrix
   if (Lq == SA_L && Lk == SA_L && head_dim == SA_HD && kv_len == nullptr && ldq == ldk &&
       k == q + n_heads * head_dim && v == q + 2 * n_heads * head_dim && ldq % 4 == 0 && ldo % 4 == 0) {
-    dim3 grid(n, ceil_div(n_heads, 4));
-    launch_k(self_attn16_kernel<T>, grid, 128, SA_SMEM, st, q, ldq, n_heads * head_dim, out, ldo, n_heads);
+    dim3 grid(n, n_heads);
+    launch_k(self_attn16_kernel<T>, grid, 32, SA_SMEM, st, q, ldq, n_heads * head_dim, out, ldo, n_heads);
     CFB_LAUNCH_CHECK();
     return CFB_OK;
   }
@@ -649,7 +804,7 @@ template int mha<bf16>(const bf16*, int, const bf16*, const bf16*, int, bf16*, i
 template <typename T>
 int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,
                     cudaStream_t st) {
-  if (n_batch <= 0) return CFB_OK;
+  if (n_batch <= 0 || debug_skip(8)) return CFB_OK;
   CFB_CHECK(d == CROSS_D && n_tokens <= CROSS_MAXQ, "cross_attention: d=%d n_tokens=%d unsupported", d, n_tokens);
   int maxM = 0;
   for (int x = 0; x < CFB_N_STREAMS; ++x) {

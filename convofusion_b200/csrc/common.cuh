@@ -51,6 +51,20 @@ extern unsigned long long g_launches;
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Diagnosis only (build with -DCFB_DEBUG_SKIP): env CFB_SKIP is a bit mask of kernel classes whose launches are
+// dropped (1 LayerNorm rows, 2 self-attention / MHA, 4 shared softmax, 8 per-pair cross-attention, 16 tcgen05 GEMM,
+// 32 grouped GEMM) to measure what each class costs inside the concurrent step.  Results are garbage.
+#ifdef CFB_DEBUG_SKIP
+#include <cstdlib>
+static inline bool debug_skip(int bit) {
+  static int mask = -1;
+  if (mask < 0) { const char* e = getenv("CFB_SKIP"); mask = e ? atoi(e) : 0; }
+  return (mask & bit) != 0;
+}
+#else
+static inline bool debug_skip(int) { return false; }
+#endif
+
 // Programmatic dependent launch.  Every kernel of this library starts with pdl_sync() (tcgen05 GEMM: after its
 // shared-memory/TMEM prologue): `launch_dependents` lets the NEXT kernel's CTAs be scheduled as soon as all of this
 // kernel's CTAs have started, `wait` blocks until the PREVIOUS kernel has completed and its writes are visible.
@@ -120,7 +134,9 @@ struct Epilogue {
   const float* ln_mod;       // [scale(512) | shift(512)] or nullptr
   const int* ln_step;        // device step counter selecting the modulation row, or nullptr
   long long ln_mod_stride;
-  int* ln_counters;          // one int per 128-row block, zero before the launch; reset by the kernel
+  int* ln_counters;          // per 128-row block, zero before the launch; reset by the kernel (2 ints per block with ln_tail)
+  int ln_tail;               // 1: every CTA of a block normalises its share of the rows after the block completes
+  int tma_out;               // set by gemm_tc: output tile leaves through TMA store / reduce-add (internal)
 };
 
 // GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.

@@ -177,7 +177,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // tcgen05 path the LayerNorm runs inside the GEMM (last-arriving CTA of each 128-row block); otherwise it is a
   // separate row kernel.  `a` may be the GEMM's own A operand: a block is normalised only after all its tiles are done.
   // measured slower than the separate row kernel (one SM normalising 128 rows is bound by its own L2 port): opt-in
-  // CFB_FUSE_LN: 0 = separate row kernel, 1 = last-arriving CTA normalises the block (slower), 2 = cluster / DSMEM
+  // CFB_FUSE_LN: 0 = separate row kernel, 1 = last-arriving CTA normalises the block (slower), 2 = cluster / DSMEM,
+  // 3 = LayerNorm tail: every CTA of a completed block normalises its share of the rows (TMA-epilogue kernel)
   static const int fuse_mode = getenv("CFB_FUSE_LN") ? atoi(getenv("CFB_FUSE_LN")) : 0;
   const bool fuse_ln = fuse_mode != 0 && tb && g_gemm_backend != CFB_GEMM_SIMT && row0 % 128 == 0;
   auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
@@ -186,7 +187,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     const bool fuse = fuse_ln && gemm_tc_supported(R, d, K, K, K);
     if (fuse) {
       ep.ln_out = reinterpret_cast<bf16*>(a); ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_mod = mod; ep.ln_step = mod ? step_ptr : nullptr;
-      ep.ln_mod_stride = mod_stride; ep.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : nullptr;
+      ep.ln_mod_stride = mod_stride; ep.ln_tail = fuse_mode == 3;
+      ep.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : fuse_mode == 3 ? h->lncnt.as<int>() + 2 * (row0 / 128) : nullptr;
     }
     CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
     if (!fuse) CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
@@ -270,7 +272,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         if (fuse_ln) {   // the LayerNorm rides on the values GEMM, so every other update of h must precede it
           CFB_TRY(cond_fuser());
           ey.ln_out = reinterpret_cast<bf16*>(a); ey.ln_g = w.tb2_g; ey.ln_b = w.tb2_b; ey.ln_mod = mod2; ey.ln_step = step_ptr;
-          ey.ln_mod_stride = mod_stride; ey.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : nullptr;
+          ey.ln_mod_stride = mod_stride; ey.ln_tail = fuse_mode == 3;
+          ey.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : fuse_mode == 3 ? h->lncnt.as<int>() + 2 * (row0 / 128) : nullptr;
         }
         CFB_TRY(gemm_tc(sP, sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d, sp->k_tot, ey, st));
         if (!fuse_ln) {
@@ -323,8 +326,8 @@ int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
   CFB_TRY(h->xin.reserve((size_t)n_in * h->ntok * h->lat * es, &h->epoch));
   CFB_TRY(h->eps.reserve(R * h->lat * 4, &h->epoch));
-  if (h->lncnt.cap < (R / 128 + 2) * 4) {   // fused-LayerNorm block counters: zero once, the kernels re-arm them
-    CFB_TRY(h->lncnt.reserve((R / 128 + 2) * 4, &h->epoch));
+  if (h->lncnt.cap < (R / 128 + 2) * 8) {   // fused-LayerNorm block counters: zero once, the kernels re-arm them
+    CFB_TRY(h->lncnt.reserve((R / 128 + 2) * 8, &h->epoch));
     CFB_CUDA(cudaMemset(h->lncnt.p, 0, h->lncnt.cap));
   }
   return CFB_OK;

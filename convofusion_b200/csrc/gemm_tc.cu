@@ -12,6 +12,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two CTAs fit per SM (<=113 KB smem,
 // BN<=256 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
 #include "common.cuh"
+#include "rowvec.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -69,6 +70,27 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
+}
+// Bulk tensor store / reduce-add of one shared-memory box (async proxy); completion tracked by bulk groups.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -162,8 +184,8 @@ struct Smem {
 // its 128 columns, and after one cluster barrier reads the other three CTAs' partials through distributed shared
 // memory (mapa + ld.shared::cluster).  Every CTA then normalises its own sub-block and writes the next GEMM's bf16
 // operand: the LayerNorm costs no global read and no kernel launch on the critical path.
-template <int BN, int STAGES, int CN = 1, int CM = 1, bool LNC = false>
-__device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const int m0,
+template <int BN, int STAGES, int CN = 1, int CM = 1, bool LNC = false, bool TMA_ONLY = false>
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const CUtensorMap* tmO_p, const int m0,
                                           const int M /* first row NOT to store */, const int n0, const int N,
                                           const int K, const Epilogue& ep) {
   using S = Smem<BN, STAGES>;
@@ -278,6 +300,85 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     // fired, so each warp transposes its 32 x BN slab through that shared memory and then walks its rows with the
     // lanes spread across the columns: every global access of the bias / residual / output is row-contiguous.
     const int q = warp & 3;
+    if (TMA_ONLY || (!LNC && ep.tma_out)) {
+      // ---- TMA epilogue.  Each warp owns a 32-row slab of the tile.  Per 32 accumulator columns it adds bias /
+      // activation in registers, writes the values into a 128B-swizzled [32 rows x 128 B] box in the (now idle)
+      // pipeline shared memory and lets one lane hand that box to the TMA unit: a plain tensor store, or an f32
+      // reduce-add performed at the L2 for residual updates (out += v), so the SM never reads the residual and no
+      // thread waits on a global load or store.  Rows past M are clipped by the tensor map.
+      float* bias_s = reinterpret_cast<float*>(gen_base + S::STATS_OFF);
+      const int te = threadIdx.x - 64;
+      if (te < BN) bias_s[te] = ep.bias ? ep.bias[n0 + te] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      if (warp == 2 && lane == 0) trace(6);
+      const int r0w = m0 + q * 32;
+      if (r0w < M) {
+        const uint32_t stg_w = base + (uint32_t)q * (BN / 32) * 4096u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const bool out_bf = ep.out_bf16 != 0;
+        const int act = ep.act;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+          if (act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
+          }
+          if (!out_bf) {
+            const uint32_t box = stg_w + (uint32_t)c * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(box + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (ep.accumulate) tma_reduce_add_2d(tmO_p, n0 + c * 32, r0w, stg_w + (uint32_t)c * 4096u);
+              else tma_store_2d(tmO_p, n0 + c * 32, r0w, stg_w + (uint32_t)c * 4096u);
+              tma_commit();
+            }
+          } else {
+            const uint32_t box = stg_w + (uint32_t)(c >> 1) * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&t);
+              }
+              st_shared_v4(box + (((uint32_t)((c & 1) * 4 + j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (c & 1) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(tmO_p, n0 + (c >> 1) * 64, r0w, stg_w + (uint32_t)(c >> 1) * 4096u);
+                tma_commit();
+              }
+            }
+          }
+        }
+        if (lane == 0) {
+          if (ep.ln_out) {                 // a LayerNorm tail reads these rows back: the updates must have landed
+            tma_wait_all0();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+          } else {
+            tma_wait_read0();              // the boxes must stay intact until the TMA unit has read them
+          }
+        }
+      }
+      if (warp == 2 && lane == 0) trace(7);
+    } else if constexpr (!TMA_ONLY) {
     constexpr int PITCH = BN + 4;              // floats; +4 keeps the 128-bit transposed stores conflict-free
     constexpr int CPL = BN / 32;               // columns per lane: 4 (BN=128), 2, 1
     static_assert(4 * 32 * PITCH * 4 <= STAGES * S::STAGE_BYTES, "epilogue staging does not fit in the pipeline smem");
@@ -525,6 +626,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         }
       }
     }
+    }   // staged (non-TMA) epilogue
   }
   if (warp == 2 && lane == 0) trace(8);
   tc_fence_before();
@@ -540,20 +642,80 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     tmem_dealloc(tmem_acc, BN);
     if (lane == 0) trace(10);
   }
+  if constexpr (TMA_ONLY) {
+    // ---- LayerNorm tail (Epilogue::ln_out, float [M,512] residual output).  The gridDim.x CTAs of a 128-row block
+    // signal a per-block counter once their updates are globally visible; each then waits for the whole block and
+    // normalises its own share of the rows with all six warps, writing the next GEMM's bf16 operand.  CTAs are
+    // dispatched in block-id order, so the CTAs a spinning CTA waits for are already resident or ahead of every
+    // undispatched CTA: no deadlock.  The second counter re-arms both once every CTA of the block has passed.
+    if (ep.ln_out != nullptr) {
+      int* cnt = ep.ln_counters + 2 * blockIdx.y;
+      const int n_cta = (int)gridDim.x;
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(cnt, 1);
+        trace(11);
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_gpu(cnt) < n_cta) {
+          __nanosleep(40);
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 2000000ull) break;   // 2 ms: never hang the device on a protocol error
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) trace(12);
+      const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
+      const int per = (BM + n_cta - 1) / n_cta;
+      const int r_lo = m0 + (int)blockIdx.x * per;
+      const int r_hi = min(min(r_lo + per, m0 + BM), M);
+      const float* hbase = reinterpret_cast<const float*>(ep.out);
+      constexpr int NR = 3;                                   // rows in flight per warp
+#pragma unroll 1
+      for (int r = r_lo + warp * NR; r < r_hi; r += (NTHREADS / 32) * NR) {
+        RowVec<512> rv[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) rv[j].load_cg(hbase + (size_t)min(r + j, r_hi - 1) * 512, lane);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          ln_row_finish<512>(rv[j], ep.ln_g, ep.ln_b, mod, lane);
+          if (r + j < r_hi) rv[j].store(ep.ln_out + (size_t)(r + j) * 512, lane);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        trace(13);
+        const int old = atomicAdd(cnt + 1, 1);
+        if (old == n_cta - 1) { cnt[1] = 0; __threadfence(); cnt[0] = 0; }
+      }
+    }
+  }
 }
 
 template <int BN, int STAGES, int CN, int CM>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, int M, int N,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmO, int M, int N,
                                                            int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, CN, CM>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, CN, CM>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+}
+
+// TMA-epilogue-only instantiation: no staged ld/st epilogue in the binary, so it fits 3 CTAs per SM (<=112 registers,
+// 2-stage ring = 68 KB of shared memory): the phases of co-resident CTAs (prologue, operand latency, main loop,
+// epilogue) overlap on one SM.
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmO, int M, int N,
+                                                                  int K, Epilogue ep) {
+  gemm_tile<BN, STAGES, 1, 1, false, true>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB, int M, int N,
                                                                   int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, 1, 1, true>(&tmA, &tmB, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, 1, 1, true>(&tmA, &tmB, nullptr, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 // Grouped launch: blockIdx.z picks a group = (A map, B map, row block, bias, output).  All groups share N, K and
@@ -562,6 +724,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_ln_kernel(const __grid_co
 struct GroupedArgs {
   CUtensorMap tmA[TC_MAX_GROUPS];
   CUtensorMap tmB[TC_MAX_GROUPS];
+  CUtensorMap tmO[TC_MAX_GROUPS];
   int row_start[TC_MAX_GROUPS];
   int rows[TC_MAX_GROUPS];
   const float* bias[TC_MAX_GROUPS];
@@ -577,7 +740,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_kernel(const __gr
   if (m0 >= m_end) return;   // uniform for the whole CTA, before any barrier / TMEM allocation
   ep.bias = g.bias[z];
   ep.out = g.out[z];
-  gemm_tile<BN, STAGES>(&g.tmA[z], &g.tmB[z], m0, m_end, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
+}
+
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tc_grouped_tma_kernel(const __grid_constant__ GroupedArgs g, int N,
+                                                                          int K, Epilogue ep) {
+  const int z = blockIdx.z;
+  const int m0 = g.row_start[z] + blockIdx.y * BM;
+  const int m_end = g.row_start[z] + g.rows[z];
+  if (m0 >= m_end) return;
+  ep.bias = g.bias[z];
+  ep.out = g.out[z];
+  gemm_tile<BN, STAGES, 1, 1, false, true>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
 }
 
 // ---------------------------------------------------------------- host side
@@ -598,42 +773,47 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+enum MapKind { MAP_OPERAND = 0, MAP_OUT_F32 = 1, MAP_OUT_BF16 = 2 };
 struct MapKey {
-  const void* p; int rows, cols, ld, box_rows;
+  const void* p; int rows, cols, ld, box_rows, kind;
   bool operator==(const MapKey& o) const {
-    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && kind == o.kind;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.p);
     h = h * 1000003u ^ (size_t)k.rows; h = h * 1000003u ^ (size_t)k.cols;
-    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)k.box_rows;
+    h = h * 1000003u ^ (size_t)k.ld;   h = h * 1000003u ^ (size_t)(k.box_rows * 4 + k.kind);
     return h;
   }
 };
 
 // Descriptors are pure functions of (pointer, shape), so they are cached for the process lifetime.
-int get_map(const bf16* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+// MAP_OPERAND: bf16 [rows, cols] K-major operand, box 64 x box_rows.  MAP_OUT_*: output tile boxes of one warp's
+// 32 rows x 128 bytes (32 floats / 64 bf16), same 128-byte swizzle.
+int get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int kind = MAP_OPERAND) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{p, rows, cols, ld, box_rows};
+  MapKey key{p, rows, cols, ld, box_rows, kind};
   std::lock_guard<std::mutex> g(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return CFB_OK; }
   EncodeTiledFn enc = get_encode();
   CFB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const int esz = kind == MAP_OUT_F32 ? 4 : 2;
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(kind == MAP_OUT_F32 ? 32 : BK), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap tm;
-  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(p), gdim, gstr, box, estr,
+  CUresult r = enc(&tm, kind == MAP_OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(p), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%d cols=%d ld=%d box=%d", (int)r, (const void*)p,
-              rows, cols, ld, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%d cols=%d ld=%d box=%d kind=%d", (int)r, p,
+              rows, cols, ld, box_rows, kind);
     return CFB_ERR_CUDA;
   }
   cache.emplace(key, tm);
@@ -641,16 +821,35 @@ int get_map(const bf16* p, int rows, int cols, int ld, int box_rows, CUtensorMap
   return CFB_OK;
 }
 
+int g_tc_tma_epi = 1;   // env CFB_TC_TMA_EPI=0 keeps the shared-memory-staged ld/st epilogue
+int g_tc_occ3 = 0;      // env CFB_TC_OCC3=0: 3-stage ring, 2 CTAs per SM instead of 2-stage ring, 3 CTAs per SM
+
+// The TMA epilogue takes a plain bias vector, one output copy and (for bf16) tiles at least one 64-column box wide.
+bool tma_epilogue_ok(const Epilogue& ep, int BN_) {
+  const bool tail = ep.ln_out != nullptr && ep.ln_counters != nullptr && ep.ln_tail;
+  return g_tc_tma_epi && ep.replicate == 1 && ep.bias_period == 1 && (ep.ln_out == nullptr || tail) &&
+         (BN_ >= 64 || !ep.out_bf16);
+}
+
 template <int BN, int STAGES, int CN, int CM>
-int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep,
+int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep_in,
            cudaStream_t st) {
   using S = Smem<BN, STAGES>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
+  Epilogue ep = ep_in;
   CFB_TRY(get_map(A, M, K, lda, BM / CN, &ta));          // each CTA loads (and multicasts) a 1/CN slice of the A tile
   CFB_TRY(get_map(W, w_rows, K, ldw, BN / CM, &tb));     // rows past w_rows read as zeros (TMA out-of-bounds fill)
+  ep.tma_out = tma_epilogue_ok(ep, BN);
+  if (ep.tma_out) CFB_TRY(get_map(ep.out, M, N, ep.ldo, 32, &to, ep.out_bf16 ? MAP_OUT_BF16 : MAP_OUT_F32));
+  else to = ta;
   dim3 grid(ceil_div(N, BN), ceil_div(ceil_div(M, BM), CM) * CM);   // whole clusters; surplus m-tiles store nothing
   if constexpr (CN * CM == 1) {
-    launch_k(gemm_tc_kernel<BN, STAGES, 1, 1>, grid, NTHREADS, S::TOTAL, st, ta, tb, M, N, K, ep);
+    if (ep.tma_out && g_tc_occ3)
+      launch_k(gemm_tc_tma_kernel<BN, 2, 3>, grid, NTHREADS, Smem<BN, 2>::TOTAL, st, ta, tb, to, M, N, K, ep);
+    else if (ep.tma_out)
+      launch_k(gemm_tc_tma_kernel<BN, STAGES, 2>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
+    else
+      launch_k(gemm_tc_kernel<BN, STAGES, 1, 1>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
@@ -658,7 +857,7 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, in
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CN; attr[0].val.clusterDim.y = CM; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CN, CM>, ta, tb, M, N, K, ep));
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CN, CM>, ta, tb, to, M, N, K, ep));
   }
   CFB_LAUNCH_CHECK();
   return CFB_OK;
@@ -685,21 +884,31 @@ int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int 
 
 template <int BN, int STAGES>
 int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
-                   const Epilogue& ep, cudaStream_t st) {
+                   const Epilogue& ep_in, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   GroupedArgs g;
   memset(&g, 0, sizeof(g));
+  Epilogue ep = ep_in;
+  ep.tma_out = tma_epilogue_ok(ep, BN);
   int max_rows = 0;
   for (int z = 0; z < n_groups; ++z) {
     CFB_TRY(get_map(groups[z].A, a_rows_total, K, lda, BM, &g.tmA[z]));
     CFB_TRY(get_map(groups[z].W, N, K, ldw, BN, &g.tmB[z]));
+    if (ep.tma_out && groups[z].rows > 0)   // rows past the group's block are clipped by the map
+      CFB_TRY(get_map(groups[z].out, groups[z].row_start + groups[z].rows, N, ep.ldo, 32, &g.tmO[z],
+                      ep.out_bf16 ? MAP_OUT_BF16 : MAP_OUT_F32));
     g.row_start[z] = groups[z].row_start; g.rows[z] = groups[z].rows;
     g.bias[z] = groups[z].bias; g.out[z] = groups[z].out;
     if (groups[z].rows > max_rows) max_rows = groups[z].rows;
   }
   if (max_rows <= 0) return CFB_OK;
   dim3 grid(ceil_div(N, BN), ceil_div(max_rows, BM), n_groups);
-  launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  if (ep.tma_out && g_tc_occ3)
+    launch_k(gemm_tc_grouped_tma_kernel<BN, 2, 3>, grid, NTHREADS, Smem<BN, 2>::TOTAL, st, g, N, K, ep);
+  else if (ep.tma_out)
+    launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES, 2>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  else
+    launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -724,6 +933,16 @@ int init_gemm_tc_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
   if (const char* e = getenv("CFB_TC_CLUSTER")) g_tc_cluster = atoi(e);
+  if (const char* e = getenv("CFB_TC_TMA_EPI")) g_tc_tma_epi = atoi(e);
+  if (const char* e = getenv("CFB_TC_OCC3")) g_tc_occ3 = atoi(e);
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 2>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 2>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_ln_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   done = true;
@@ -744,6 +963,7 @@ static int check_epilogue(Epilogue& ep) {
 
 int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep_in,
             cudaStream_t st, int w_rows) {
+  if (debug_skip(16)) return CFB_OK;
   CFB_CHECK(gemm_tc_supported(M, N, K, lda, ldw), "gemm_tc: unsupported shape %dx%dx%d", M, N, K);
   CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_tc: operands must be 16-byte aligned");
   Epilogue ep = ep_in;
@@ -756,6 +976,7 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
     if (ep.ln_counters == nullptr) return launch_ln(A, lda, W, ldw, M, N, K, ep, st);   // cluster / DSMEM variant
   }
   if (w_rows <= 0 || w_rows > N) w_rows = N;
+  if (ep.ln_out && ep.ln_tail) return launch<128, 3, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);   // tail needs plain CTAs
   if (N % 128 == 0) {
     // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.
     // Multicast pays when several tiles share an operand; a single m-tile (tiny M) gains nothing from CM.
@@ -775,6 +996,7 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
 
 int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
                     const Epilogue& ep_in, cudaStream_t st) {
+  if (debug_skip(32)) return CFB_OK;
   CFB_CHECK(n_groups > 0 && n_groups <= TC_MAX_GROUPS, "gemm_tc_grouped: %d groups (max %d)", n_groups, TC_MAX_GROUPS);
   CFB_CHECK(N % 128 == 0 && K % BK == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_tc_grouped: unsupported shape N=%d K=%d", N, K);
   Epilogue ep = ep_in;

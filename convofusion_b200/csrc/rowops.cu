@@ -4,69 +4,11 @@
 // shuffle, two-pass variance (mean first, then sum of squared deviations) like ATen's LayerNorm.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rowvec.cuh"
 
 namespace cfb {
 
 namespace {
-
-constexpr float LN_EPS = 1e-5f;
-
-template <int D>
-struct RowVec {
-  static constexpr int PER_LANE = D / 32;  // 16 (D=512) or 4 (D=128)
-  static constexpr int NV = PER_LANE / 4;
-  float v[PER_LANE];
-  // lane owns columns {i*128 + lane*4 .. +3} for i in [0, NV): coalesced float4 accesses
-  __device__ __forceinline__ void load(const float* __restrict__ row, int lane) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float4 t = *reinterpret_cast<const float4*>(row + i * 128 + lane * 4);
-      v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
-    }
-  }
-  __device__ __forceinline__ void add(const float* __restrict__ row, int lane) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float4 t = *reinterpret_cast<const float4*>(row + i * 128 + lane * 4);
-      v[i * 4] += t.x; v[i * 4 + 1] += t.y; v[i * 4 + 2] += t.z; v[i * 4 + 3] += t.w;
-    }
-  }
-  __device__ __forceinline__ void normalize() {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) s += v[i];
-    const float mu = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) { v[i] -= mu; q += v[i] * v[i]; }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) v[i] *= rstd;
-  }
-  __device__ __forceinline__ void affine(const float* __restrict__ g, const float* __restrict__ b, int lane) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float4 gg = *reinterpret_cast<const float4*>(g + i * 128 + lane * 4);
-      float4 bb = *reinterpret_cast<const float4*>(b + i * 128 + lane * 4);
-      v[i * 4] = v[i * 4] * gg.x + bb.x; v[i * 4 + 1] = v[i * 4 + 1] * gg.y + bb.y;
-      v[i * 4 + 2] = v[i * 4 + 2] * gg.z + bb.z; v[i * 4 + 3] = v[i * 4 + 3] * gg.w + bb.w;
-    }
-  }
-  template <typename T>
-  __device__ __forceinline__ void store(T* __restrict__ row, int lane) const {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if constexpr (sizeof(T) == 4) {
-        *reinterpret_cast<float4*>(row + i * 128 + lane * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-      } else {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[i * 4], v[i * 4 + 1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(v[i * 4 + 2], v[i * 4 + 3]);
-        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(row + i * 128 + lane * 4) = pk;
-      }
-    }
-  }
-};
 
 // out = LN(x) * g + b  [ * (1 + scale) + shift -> SiLU ]           (cross_attention.py:437-438)
 template <typename T, int D>
@@ -79,19 +21,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   if (row >= rows) return;
   RowVec<D> r;
   r.load(x + (size_t)row * D, lane);
-  r.normalize();
-  r.affine(g, b, lane);
-  if (mod) {
-    const float* m = mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0);
-#pragma unroll
-    for (int i = 0; i < RowVec<D>::NV; ++i) {
-      float4 sc = *reinterpret_cast<const float4*>(m + i * 128 + lane * 4);
-      float4 sh = *reinterpret_cast<const float4*>(m + D + i * 128 + lane * 4);
-      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r.v[i * 4 + j] = act_apply(r.v[i * 4 + j] * (1.0f + scv[j]) + shv[j], CFB_ACT_SILU);
-    }
-  }
+  ln_row_finish<D>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
   r.store(out + (size_t)row * D, lane);
 }
 
@@ -249,7 +179,7 @@ int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStre
 template <typename T>
 int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
             long long mod_step_stride, T* out, int rows, int d, cudaStream_t st) {
-  if (rows <= 0) return CFB_OK;
+  if (rows <= 0 || debug_skip(1)) return CFB_OK;
   dim3 grid(ceil_div(rows, 8));
   if (d == 512) launch_k(ln_rows_kernel<T, 512>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
   else if (d == 128) launch_k(ln_rows_kernel<T, 128>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);

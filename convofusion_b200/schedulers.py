@@ -73,16 +73,23 @@ class _Base:
         raise NotImplementedError
 
     def step_table(self, num_steps: int, eta: float = 0.0, noise_scheduler=None) -> dict:
+        """Per-step coefficient rows for the fused loop.  O(steps) scalar work on the host (a few ms of torch scalar
+        ops), so the table is memoised per (steps, eta, noise schedule): repeated sampling calls pay it once."""
         self.set_timesteps(num_steps)
-        ts = self.timesteps.cpu().numpy().astype(np.int64)
         ns = noise_scheduler if noise_scheduler is not None else self
+        key = (int(num_steps), float(eta), ns.kind, repr(sorted(vars(ns.config).items())))
+        cache = self.__dict__.setdefault("_step_tables", {})
+        if key in cache:
+            return cache[key]
+        ts = self.timesteps.cpu().numpy().astype(np.int64)
         coef = np.zeros((len(ts), 8), dtype=np.float32)
         for i, t in enumerate(ts):
             coef[i, :5] = self._row(int(t), eta)
             a = ns.alphas_cumprod[int(t)]
             coef[i, 5], coef[i, 6] = float(a ** 0.5), float((1 - a) ** 0.5)
-        return {"kind": self.kind, "timesteps": ts, "coef": coef, "clip_sample": bool(self.config.clip_sample),
-                "needs_noise": bool(np.any(coef[:, 4] != 0))}
+        cache[key] = {"kind": self.kind, "timesteps": ts, "coef": coef, "clip_sample": bool(self.config.clip_sample),
+                      "needs_noise": bool(np.any(coef[:, 4] != 0))}
+        return cache[key]
 
     def _device_step(self, model_output, sample, row, noise):
         if model_output.device.type != "cuda":

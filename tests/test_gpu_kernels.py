@@ -117,6 +117,28 @@ def test_mha_core(n, Lq, Lk, H, hd, ragged):
     assert max_rel(out.view(n, Lq, E).permute(1, 0, 2).cpu(), want) < 5e-6
 
 
+@pytest.mark.parametrize("n,Lq,Lk,H,hd,ragged", [(14, 16, 16, 4, 128, False), (5, 128, 128, 2, 64, True), (5, 128, 8, 2, 64, False),
+                                                 (24, 18, 18, 2, 64, True), (3, 37, 37, 2, 64, True), (2, 100, 77, 2, 64, True)])
+def test_mha_core_bf16_tensor_core(n, Lq, Lk, H, hd, ragged):
+    """bf16 cfb_mha (mma.sync kernel: scores in registers, probabilities rounded to bf16 for P.V) vs the fp32 oracle
+    on the same bf16-rounded inputs.  Tolerance: two bf16 roundings (P and the output), 2^-8 of the output scale."""
+    E = H * hd
+    g = torch.Generator().manual_seed(100 + n + Lq + Lk)
+    q, k, v = (torch.randn(L, n, E, generator=g).bfloat16().float() for L in (Lq, Lk, Lk))
+    lens = torch.randint(1, Lk + 1, (n,), generator=g) if ragged else None
+    kpm = (torch.arange(Lk)[None] >= lens[:, None]) if ragged else None
+    eye = torch.eye(E)
+    want, _ = O.mha(q, k, v, torch.cat([eye, eye, eye]), torch.zeros(3 * E), eye, torch.zeros(E), H, kpm)
+    qd, kd, vd = (t.permute(1, 0, 2).contiguous().bfloat16().to(DEV) for t in (q, k, v))
+    out = torch.full((n * Lq, E), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lens_d = lens.int().to(DEV) if ragged else None
+    _lib.check(_lib.lib().cfb_mha(qd.data_ptr(), E, kd.data_ptr(), vd.data_ptr(), E, out.data_ptr(), E, 1, n, Lq, Lk, H, hd,
+                                  _lib.ptr(lens_d), _lib.stream_ptr()))
+    got = out.float().view(n, Lq, E).permute(1, 0, 2).cpu()
+    assert torch.isfinite(got).all()
+    assert max_rel(got, want) < 8e-3
+
+
 @pytest.mark.parametrize("kind", ["ddim", "ddpm"])
 def test_guidance_scheduler_step_is_bit_exact(kind):
     """Fused combine + step vs the oracle (torch eager fp32, same association order): identical bits."""

@@ -53,3 +53,53 @@ for M in (6144, 1024, 128):
                 continue
             us, tf = time_gemm(M, N, K, out_bf16, acc)
             print(f"{M:6d} {N:5d} {K:5d} {tag:>10} {us:8.2f} {tf:8.1f}")
+
+
+def time_concurrent(M, N, K, out_bf16, accumulate, n_streams, reps=10, iters=10):
+    """n_streams independent chains of `reps` dependent GEMMs each (distinct buffers per chain, shared weights),
+    forked/joined inside one CUDA graph: the aggregate throughput the sampler's concurrent chains can reach."""
+    W = torch.randn(N, K, device=dev).bfloat16()
+    b = torch.randn(N, device=dev)
+    As = [torch.randn(M, K, device=dev).bfloat16() for _ in range(n_streams)]
+    outs = [torch.zeros(M, N, device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32) for _ in range(n_streams)]
+    main = torch.cuda.Stream()
+    subs = [torch.cuda.Stream() for _ in range(n_streams)]
+
+    def body():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for s, A, o in zip(subs, As, outs):
+            s.wait_event(ev)
+            for _ in range(reps):
+                _lib.check(lib.cfb_linear(A.data_ptr(), 1, W.data_ptr(), b.data_ptr(), o.data_ptr(), int(out_bf16), M, N, K,
+                                          0, 0, int(accumulate), _lib.GEMM_TCGEN05, s.cuda_stream))
+            e = torch.cuda.Event()
+            e.record(s)
+            main.wait_event(e)
+
+    with torch.cuda.stream(main):
+        body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=main):
+            body()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    n = n_streams * reps
+    return us / reps, 2.0 * M * N * K * n / us / 1e6
+
+
+if "--concurrent" in sys.argv:
+    print(f"\n{'streams':>7} {'M':>6} {'N':>5} {'K':>5} {'epilogue':>10} {'us/round':>9} {'agg TFLOP/s':>12}")
+    for S in (1, 2, 4, 6, 12):
+        for (M, N, K) in ((1056, 512, 512), (1056, 1536, 512), (1056, 512, 1024)):
+            for out_bf16, acc, tag in ((1, 0, "bf16"), (0, 1, "f32+=")):
+                us, tf = time_concurrent(M, N, K, out_bf16, acc, S)
+                print(f"{S:7d} {M:6d} {N:5d} {K:5d} {tag:>10} {us:9.2f} {tf:12.1f}")
