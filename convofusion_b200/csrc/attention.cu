@@ -8,6 +8,7 @@
 //    softmax(qx . mem_hat^T) . mem_hat over head_dim = d_model = 512.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace cfb {
 
@@ -256,6 +257,8 @@ __global__ void __launch_bounds__(256) cross_kernel(const T* __restrict__ qx, co
 //           and read with ldmatrix.trans; warp w owns output columns [64w, 64w+64).
 // 16-query tiles are exactly one MMA row block, so nothing is wasted on padding.
 constexpr int XP = CROSS_D + 8;   // bf16 row pitch in shared memory: rows shift by 16 B -> conflict-free ldmatrix
+constexpr int CM_NBUF = 4;        // value-tile ring of the tensor-core cross-attention: three 16-key tiles in flight
+constexpr int QP = CROSS_D + 32;  // query rows shift by 64 B -> conflict-free 128-bit loads per quarter-warp (rows g, g+1 x 4 lanes)
 
 __device__ __forceinline__ void ldsm_x4(uint32_t r[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -286,9 +289,9 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
   const int ld = CFB_N_STREAMS * CROSS_D;
   const int slot = a.slot[x] ? a.slot[x][bs] : bs;
   if (a.skip_slot0 && slot == 0) return;   // block-uniform
-  bf16* Qs = reinterpret_cast<bf16*>(smraw);            // [16][XP]
-  bf16* Xs = Qs + 16 * XP;                              // [2][16][XP]
-  float* Ss = reinterpret_cast<float*>(Xs + 2 * 16 * XP);   // [16][Sp]
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);            // [16][QP]
+  bf16* Xs = Qs + 16 * QP;                              // [CM_NBUF][16][XP]
+  float* Ss = reinterpret_cast<float*>(Xs + CM_NBUF * 16 * XP);   // [16][Sp]
   bf16* Ps = reinterpret_cast<bf16*>(Ss + 16 * Sp);     // [16][Pp]
   const bf16* mem = mem_hat + ((size_t)a.row_base[x] + (size_t)slot * M) * CROSS_D;
   const uint8_t* msk = a.mask[x] ? a.mask[x] + (size_t)slot * M : nullptr;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
     const int r = i >> 6, ch = i & 63;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < n_tokens) v = *reinterpret_cast<const uint4*>(qx + (size_t)(bs * n_tokens + r) * ld + x * CROSS_D + ch * 8);
-    *reinterpret_cast<uint4*>(Qs + r * XP + ch * 8) = v;
+    *reinterpret_cast<uint4*>(Qs + r * QP + ch * 8) = v;
   }
   // first value tile in flight while the scores are computed
   const int nkt = (M + 15) >> 4;
@@ -313,29 +316,33 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stage_tile(0, 0);
+  // the first value tiles stream in while the scores are computed (a group is committed per tile, empty past the end)
+#pragma unroll
+  for (int i = 0; i < CM_NBUF - 1; ++i) {
+    if (i < nkt) stage_tile(i, i);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   __syncthreads();
 
-  // ---- scores
+  // ---- scores.  The reduction index of an mma is free to be permuted as long as both operands agree, so lane t
+  // takes the eight CONTIGUOUS columns 32 j + 8 t .. + 7 of its key row (one 128-bit load; two k-steps' worth of B
+  // fragments) and the matching eight columns of query rows g and g + 8 from shared memory.  All 16 key loads of an
+  // 8-key tile are in flight at once: one L2 round trip per tile instead of four.
   const int nnt = (M + 7) >> 3;
   for (int nt = warp; nt < nnt; nt += 8) {
     const int key0 = nt * 8;
-    const bf16* kp = mem + (size_t)min(key0 + g, M - 1) * CROSS_D + 2 * t;
+    const bf16* kp = mem + (size_t)min(key0 + g, M - 1) * CROSS_D + 8 * t;
+    uint4 kb[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) kb[j] = *reinterpret_cast<const uint4*>(kp + 32 * j);
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int kc = 0; kc < 4; ++kc) {            // 4 chunks of 8 k-steps: 16 B-fragment loads in flight per chunk
-      uint32_t b[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        b[2 * i] = *reinterpret_cast<const uint32_t*>(kp + (kc * 8 + i) * 16);
-        b[2 * i + 1] = *reinterpret_cast<const uint32_t*>(kp + (kc * 8 + i) * 16 + 8);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t af[4];
-        ldsm_x4(af, qs_addr + (uint32_t)(((lane & 15) * XP + (kc * 8 + i) * 16 + (lane >> 4) * 8) * 2));
-        mma_bf16_16816(c, af, b[2 * i], b[2 * i + 1]);
-      }
+    for (int j = 0; j < 16; ++j) {
+      const uint4 qa = *reinterpret_cast<const uint4*>(Qs + g * QP + 32 * j + 8 * t);
+      const uint4 qb = *reinterpret_cast<const uint4*>(Qs + (g + 8) * QP + 32 * j + 8 * t);
+      const uint32_t a0[4] = {qa.x, qb.x, qa.y, qb.y}, a1[4] = {qa.z, qb.z, qa.w, qb.w};
+      mma_bf16_16816(c, a0, kb[j].x, kb[j].y);
+      mma_bf16_16816(c, a1, kb[j].z, kb[j].w);
     }
     const int j0 = key0 + 2 * t, j1 = j0 + 1;
     const bool m0 = j0 >= M || (msk && msk[j0]), m1 = j1 >= M || (msk && msk[min(j1, M - 1)]);
@@ -383,10 +390,11 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
 #pragma unroll
   for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
   for (int kt = 0; kt < nkt; ++kt) {
-    const int buf = kt & 1;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int buf = kt % CM_NBUF;
+    asm volatile("cp.async.wait_group %0;" ::"n"(CM_NBUF - 2) : "memory");   // tiles 0..kt+NBUF-2 committed: tile kt is in
     __syncthreads();                         // tile kt landed for everyone; tile kt-1's buffer is free; P is visible
-    if (kt + 1 < nkt) stage_tile(kt + 1, buf ^ 1);
+    if (kt + CM_NBUF - 1 < nkt) stage_tile(kt + CM_NBUF - 1, (kt + CM_NBUF - 1) % CM_NBUF);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
     uint32_t af[4];
     ldsm_x4(af, ps_addr + (uint32_t)(((lane & 15) * Pp + kt * 16 + (lane >> 4) * 8) * 2));
     const int brow = (lane & 7) + ((lane >> 3) & 1) * 8;       // key row inside the tile
@@ -692,6 +700,55 @@ __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __rest
   }
 }
 
+
+// Register-resident variant: one warp per (query row, stream).  The stream's score segment (<= 32 * SMX_MAXJ keys)
+// is fetched in ONE round trip together with the slot id and the mask bytes, the softmax runs out of registers and
+// every probability is written once; five times as many warps as rows hide what latency is left.  The strided
+// kernel above walks each segment three times with dependent loads (max, sum, write): ~15 L2 round trips per row,
+// 12-15 us per launch for about a microsecond of work.
+constexpr int SMX_MAXJ = 8;
+__global__ void __launch_bounds__(256) softmax_shared_reg_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+                                                                 SharedAttnArgs a, int rows, int n_tokens) {
+  pdl_sync();
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int r = w / CFB_N_STREAMS, x = w % CFB_N_STREAMS;
+  if (r >= rows) return;
+  const int bs = r / n_tokens + a.bs_offset;
+  const int M = a.len[x], kp = a.kp[x];
+  const float* srow = S + (size_t)r * a.ld_s + a.s_off[x];
+  bf16* prow = P + (size_t)r * a.ld_p + a.p_off[x];
+  const uint8_t* msk = a.mask[x];
+  const int slot = a.slot[x][bs];
+  float s[SMX_MAXJ];
+#pragma unroll
+  for (int i = 0; i < SMX_MAXJ; ++i) {
+    const int j = lane + 32 * i;
+    s[i] = -INFINITY;
+    if (j < M) {
+      const float v = srow[j];
+      const bool dead = msk && msk[j];
+      s[i] = dead ? -INFINITY : v;
+    }
+  }
+  float mx = s[0];
+#pragma unroll
+  for (int i = 1; i < SMX_MAXJ; ++i) mx = fmaxf(mx, s[i]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMX_MAXJ; ++i) {
+    if (32 * i < M) { s[i] = expf(s[i] - mx); sum += s[i]; }   // warp-uniform test; masked / out-of-range -> exp(-inf) = 0
+  }
+  sum = warp_sum(sum);
+  const float inv = slot == 0 ? 1.0f / sum : 0.f;   // conditional pairs are handled by cross_attention(): zeros here
+#pragma unroll
+  for (int i = 0; i < SMX_MAXJ; ++i) {
+    const int j = lane + 32 * i;
+    if (j < kp) prow[j] = __float2bfloat16_rn(j < M ? s[i] * inv : 0.f);
+  }
+  for (int j = 32 * SMX_MAXJ + lane; j < kp; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+}
+
 // z0[l][s_off[x] + j] = a_{x,l} . xhat_{x,slot 0, j}: the key-dependent bias of the shared-slot scores.
 struct Z0Args {
   const float* a_zx[CFB_N_STREAMS];   // [L, 512]
@@ -743,7 +800,11 @@ int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_
 int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
   const int rows = n_batch * n_tokens;
   if (rows <= 0 || debug_skip(4)) return CFB_OK;
-  launch_k(softmax_shared_kernel, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
+  static const bool strided = getenv("CFB_SOFTMAX_STRIDED") && atoi(getenv("CFB_SOFTMAX_STRIDED"));
+  bool fits = true;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) fits = fits && a.len[x] <= 32 * SMX_MAXJ;
+  if (fits && !strided) launch_k(softmax_shared_reg_kernel, ceil_div(rows * CFB_N_STREAMS, 8), 256, 0, st, S, P, a, rows, n_tokens);
+  else launch_k(softmax_shared_kernel, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -813,7 +874,7 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
   }
   if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernel (in-place u == qx is fine: Q is staged before u is written)
     const int Sp = ((maxM + 7) & ~7) + 8, Pp = ((maxM + 15) & ~15) + 8;
-    const size_t smem_mma = (size_t)3 * 16 * XP * 2 + (size_t)16 * Sp * 4 + (size_t)16 * Pp * 2;
+    const size_t smem_mma = (size_t)(16 * QP + CM_NBUF * 16 * XP) * 2 + (size_t)16 * Sp * 4 + (size_t)16 * Pp * 2;
     // CFB_GEMM_SIMT selects the CUDA-core engines everywhere (tests cross-check the two implementations)
     if (smem_mma <= (size_t)ATT_MAX_SMEM && g_gemm_backend != CFB_GEMM_SIMT) {
       dim3 grid(n_batch, CFB_N_STREAMS);
