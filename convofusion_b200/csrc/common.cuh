@@ -104,6 +104,25 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   }
 }
 
+// Activations for values that are rounded to bf16 right afterwards: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// one ex2.approx and one rcp.approx instead of the ~25-instruction erff), SiLU through ex2.approx / rcp.approx.
+__device__ __forceinline__ float act_apply_fast(float v, int act) {
+  switch (act) {
+    case CFB_ACT_GELU: {
+      const float z = fabsf(v) * 0.70710678118654752440f;
+      const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+      float p = fmaf(1.061405429f, t, -1.453152027f);
+      p = fmaf(p, t, 1.421413741f);
+      p = fmaf(p, t, -0.284496736f);
+      p = fmaf(p, t, 0.254829592f);
+      const float e = 1.0f - p * t * __expf(-z * z);          // erf(|v| / sqrt 2)
+      return 0.5f * v * (1.0f + copysignf(e, v));
+    }
+    case CFB_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
+    default: return act_apply(v, act);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -103,6 +103,29 @@ struct SharedPlan {
   int g_round[TC_MAX_GROUPS], n_rounds = 0;
 };
 
+// Embedding of the batch entries [b0, b0 + nb) of the guidance batch (entry e = branch * n_clips + clip reads the
+// latents of `clip`): every chain embeds its own rows on its own stream instead of one replicated launch up front.
+// h->xin must hold the cast latents (embed_cast).
+template <typename T>
+int embed_cast(cfb_denoiser* h, const float* latents, int n_clips, cudaStream_t st) {
+  return cast_rows<T>(latents, h->xin.as<T>(), (long long)n_clips * h->ntok * h->lat, st);
+}
+template <typename T>
+int embed_rows(cfb_denoiser* h, int b0, int nb, int n_clips, cudaStream_t st) {
+  const int tb = sizeof(T) == 2;
+  for (int e = b0; e < b0 + nb;) {
+    const int clip = e % n_clips;
+    const int run = (n_clips - clip < b0 + nb - e) ? n_clips - clip : b0 + nb - e;   // stay inside one branch
+    Epilogue ep{};
+    ep.bias = h->w.tok_bias; ep.bias_period = h->ntok; ep.out = h->h.as<float>() + (size_t)e * h->ntok * h->d;
+    ep.ldo = h->d; ep.replicate = 1;
+    CFB_TRY(gemm(h->xin.as<T>() + (size_t)clip * h->ntok * h->lat, tb, h->lat, h->w.w_embed, tb, h->lat, run * h->ntok,
+                 h->d, h->lat, 0, ep, st));
+    e += run;
+  }
+  return CFB_OK;
+}
+
 template <typename T>
 int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaStream_t st) {
   // denoiser.py:183-187,316-326: latent_embd + body/hand embedding + SineBH positional encoding
@@ -388,7 +411,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
       CFB_TRY(shared_precompute(h, sp, ml, ca.len, 1, st));
     }
   }
-  CFB_TRY(embed<T>(h, h->x.as<float>(), n_clips, n_branch, st));   // torch.cat([latents] * 7), convofusion.py:499
+  CFB_TRY(embed_cast<T>(h, h->x.as<float>(), n_clips, st));       // torch.cat([latents] * 7), convofusion.py:499
   // The step is a chain of ~190 short kernels, bound by launch / prologue / epilogue latency rather than by
   // throughput.  Batch entries are independent through the whole denoiser, so they are cut into n_chains groups
   // (multiples of 8 entries = one 128-row tile) that run the layer stack concurrently on forked streams.
@@ -398,6 +421,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
   if (nc <= 1) {
     ChainAux aux;
     if (overlap) { aux.ev_pre[0] = h->ev_pre[0]; aux.ev_pre[1] = h->ev_pre[1]; }
+    CFB_TRY(embed_rows<T>(h, 0, n_batch, n_clips, st));
     CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp, 0, n_batch, &aux));
   } else {
     CFB_CUDA(cudaEventRecord(h->ev_fork, st));
@@ -410,6 +434,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
         aux.ev_pre[0] = h->ev_pre[0]; aux.ev_pre[1] = h->ev_pre[1];
         aux.st2 = h->chain_st2[c]; aux.ev_a = h->ev_a[c]; aux.ev_b = h->ev_b[c];
       }
+      CFB_TRY(embed_rows<T>(h, b0, nb, n_clips, cs));
       CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux));
       if (c > 0) {
         CFB_CUDA(cudaEventRecord(h->ev_join[c], cs));

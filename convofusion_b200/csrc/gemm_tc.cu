@@ -308,7 +308,8 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
       // thread waits on a global load or store.  Rows past M are clipped by the tensor map.
       float* bias_s = reinterpret_cast<float*>(gen_base + S::STATS_OFF);
       const int te = threadIdx.x - 64;
-      if (te < BN) bias_s[te] = ep.bias ? ep.bias[n0 + te] : 0.f;
+      const bool row_bias = ep.bias && ep.bias_period != 1;   // bias[(row % period), :]: read per row below
+      if (te < BN) bias_s[te] = (ep.bias && !row_bias) ? ep.bias[n0 + te] : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(bar_acc, 0);
       tc_fence_after();
@@ -328,9 +329,22 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
             v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
-          if (act) {
+          if (row_bias) {
+            const float* brow = ep.bias + (size_t)((r0w + lane) % ep.bias_period) * N + n0 + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = *reinterpret_cast<const float4*>(brow + j * 4);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (act) {
+            if (out_bf) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], act);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
+            }
           }
           if (!out_bf) {
             const uint32_t box = stg_w + (uint32_t)c * 4096u + (uint32_t)lane * 128u;
@@ -678,7 +692,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         for (int j = 0; j < NR; ++j) rv[j].load_cg(hbase + (size_t)min(r + j, r_hi - 1) * 512, lane);
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-          ln_row_finish<512>(rv[j], ep.ln_g, ep.ln_b, mod, lane);
+          ln_row_finish<512, true>(rv[j], ep.ln_g, ep.ln_b, mod, lane);
           if (r + j < r_hi) rv[j].store(ep.ln_out + (size_t)(r + j) * 512, lane);
         }
       }
@@ -824,10 +838,10 @@ int get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap
 int g_tc_tma_epi = 1;   // env CFB_TC_TMA_EPI=0 keeps the shared-memory-staged ld/st epilogue
 int g_tc_occ3 = 0;      // env CFB_TC_OCC3=0: 3-stage ring, 2 CTAs per SM instead of 2-stage ring, 3 CTAs per SM
 
-// The TMA epilogue takes a plain bias vector, one output copy and (for bf16) tiles at least one 64-column box wide.
+// The TMA epilogue takes one output copy and (for bf16) tiles at least one 64-column box wide.
 bool tma_epilogue_ok(const Epilogue& ep, int BN_) {
   const bool tail = ep.ln_out != nullptr && ep.ln_counters != nullptr && ep.ln_tail;
-  return g_tc_tma_epi && ep.replicate == 1 && ep.bias_period == 1 && (ep.ln_out == nullptr || tail) &&
+  return g_tc_tma_epi && ep.replicate == 1 && (ep.ln_out == nullptr || tail) &&
          (BN_ >= 64 || !ep.out_bf16);
 }
 

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   if (row >= rows) return;
   RowVec<D> r;
   r.load(x + (size_t)row * D, lane);
-  ln_row_finish<D>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
+  ln_row_finish<D, sizeof(T) == 2>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
   r.store(out + (size_t)row * D, lane);
 }
 

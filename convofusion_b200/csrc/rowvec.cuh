@@ -76,7 +76,9 @@ struct RowVec {
 
 // LN(x) * g + b, then optionally the TimeBlock modulation * (1 + scale) + shift and SiLU (cross_attention.py:437-438);
 // m points at [scale(D) | shift(D)] or is null.
-template <int D>
+// FAST (bf16 outputs only): SiLU through ex2.approx / rcp.approx -- about 2 ulp of float, far below the bf16 rounding
+// that follows -- instead of expf and an IEEE division (6x the instructions of the LayerNorm itself).
+template <int D, bool FAST = false>
 __device__ __forceinline__ void ln_row_finish(RowVec<D>& r, const float* __restrict__ g, const float* __restrict__ b,
                                               const float* __restrict__ m, int lane) {
   r.normalize();
@@ -88,7 +90,11 @@ __device__ __forceinline__ void ln_row_finish(RowVec<D>& r, const float* __restr
       float4 sh = *reinterpret_cast<const float4*>(m + D + i * 128 + lane * 4);
       const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r.v[i * 4 + j] = act_apply(r.v[i * 4 + j] * (1.0f + scv[j]) + shv[j], CFB_ACT_SILU);
+      for (int j = 0; j < 4; ++j) {
+        const float y = r.v[i * 4 + j] * (1.0f + scv[j]) + shv[j];
+        if constexpr (FAST) r.v[i * 4 + j] = __fdividef(y, 1.0f + __expf(-y));
+        else r.v[i * 4 + j] = act_apply(y, CFB_ACT_SILU);
+      }
     }
   }
 }
