@@ -363,7 +363,7 @@ def run_ours(args):
             tfile = ROOT / "profiles" / "r01_traffic.json"
             if tfile.exists():
                 traffic = json.loads(tfile.read_text())
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": tf, "peak": peak_tf,
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)", "achieved": tf, "peak": peak_tf,
                                 "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
                                 "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
                                 "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf}

@@ -10,7 +10,8 @@ from .modules import ConvoFusionVae, Denoiser
 from .schedulers import DDIMScheduler, DDPMScheduler
 from .conditioning import AudioConvEncoder, T5TextEncoder, TextAudioController, TextAudioMotionFuser
 from .sampler import ConvoFusionSampler, default_denoiser, default_scheduler, default_vae
+from .postprocess import keypoints3d
 
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
-           "default_denoiser", "default_vae", "default_scheduler"]
+           "default_denoiser", "default_vae", "default_scheduler", "keypoints3d"]

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "cfb_linear": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cfb_layernorm": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "cfb_mha": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "cfb_keypoints3d": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "cfb_audio_encoder": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
 }
 

@@ -76,6 +76,13 @@ int cfb_linear(const void* A, int a_bf16, const void* W, const float* bias, void
   return gemm(A, a_bf16, K, W, a_bf16, K, M, N, K, a_act, ep, st);
 }
 
+int cfb_keypoints3d(const float* feats, long long rows, float* out, cfb_stream stream) {
+  CFB_CHECK(feats && out && rows >= 0, "cfb_keypoints3d: bad argument");
+  CFB_CHECK(feats != out, "cfb_keypoints3d: in-place use is not supported (finger joints read their wrist)");
+  CFB_TRY(ensure_device());
+  return keypoints3d(feats, rows, out, (cudaStream_t)stream);
+}
+
 int cfb_layernorm(const float* x, const float* g, const float* b, void* out, int out_bf16, int rows, int d,
                   cfb_stream stream) {
   CFB_CHECK(x && g && b && out, "cfb_layernorm: null argument");

@@ -476,7 +476,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
 #pragma unroll
         for (int i = 0; i < RB; ++i)
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) v[i][c] = act_apply(v[i][c], ep.act);
+          for (int c = 0; c < CPL; ++c) v[i][c] = out_f32 ? act_apply(v[i][c], ep.act) : act_apply_fast(v[i][c], ep.act);
       }
       if (do_acc) {
 #pragma unroll

@@ -17,6 +17,7 @@ template <typename T> int cast_rows(const float* in, T* out, long long n, cudaSt
 template <typename T> int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st);
 template <typename T> int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d, cudaStream_t st);
 int mask_frames(float* out, const int* lengths, int n_batch, int L, int d, cudaStream_t st);
+int keypoints3d(const float* feats, long long rows, float* out, cudaStream_t st);
 // VAE encode side (vae.py:176-260)
 int chunk_root(const float* in, float* out, long long n_rows, int nf, int chunk, cudaStream_t st);
 int enc_assemble(const float* emb, const float* tokens, const float* pe, float* h, int n, int n_tok, int chunk, int d,

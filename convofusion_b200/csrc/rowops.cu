@@ -154,7 +154,30 @@ __global__ void enc_dist_kernel(const float* __restrict__ y, float* __restrict__
   sd[i] = sqrtf(expf(y[(s * L + 1) * d + c]));
 }
 
+// base.py:204-209: p = f / 3; p[43:] += p[11]; p[23:43] += p[7]; p[1:] += p[0]   (in that order, fp32)
+__global__ void keypoints3d_kernel(const float* __restrict__ f, float* __restrict__ out, long long n) {
+  pdl_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long row = i / 189;
+  const int c = (int)(i % 189), j = c / 3, a = c % 3;
+  const float* fr = f + row * 189;
+  float v = __fdiv_rn(fr[c], 3.0f);
+  if (j >= 43) v = __fadd_rn(v, __fdiv_rn(fr[11 * 3 + a], 3.0f));
+  else if (j >= 23) v = __fadd_rn(v, __fdiv_rn(fr[7 * 3 + a], 3.0f));
+  if (j >= 1) v = __fadd_rn(v, __fdiv_rn(fr[a], 3.0f));
+  out[i] = v;
+}
+
 }  // namespace
+
+int keypoints3d(const float* feats, long long rows, float* out, cudaStream_t st) {
+  const long long n = rows * 189;
+  if (n <= 0) return CFB_OK;
+  launch_k(keypoints3d_kernel, (unsigned)((n + 255) / 256), 256, 0, st, feats, out, n);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
 
 int chunk_root(const float* in, float* out, long long n_rows, int nf, int chunk, cudaStream_t st) {
   const long long n = n_rows * nf;

@@ -236,6 +236,11 @@ int cfb_audio_encoder(const float *mel, int rows, const float *w0, const float *
                       const float *b1, const float *w2, const float *b2, int n_mel, int hidden,
                       int d_out, float *tmp0, float *tmp1, float *out, cfb_stream stream);
 
+/* Output post-processing of the test / demo writers (models/modeltype/base.py:204-209): features [rows, 63*3]
+ * -> keypoints [rows, 63, 3] = feats / 3, fingers re-attached to their wrist (joints 43.. += joint 11,
+ * joints 23..42 += joint 7, both before the root is added), then every joint but the root += root. */
+int cfb_keypoints3d(const float *feats, long long rows, float *out, cfb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -296,6 +296,16 @@ def vae_encode(sd: Dict[str, Tensor], features: Tensor, lengths: Sequence[int], 
     return mu, std, mf.reshape(bs, nframes, -1)
 
 
+def feats_to_keypoints3d(feats: Tensor) -> Tensor:
+    """models/modeltype/base.py:204-209 (numpy there): [T, 189] -> [T, 63, 3], in-place order preserved."""
+    p = feats.reshape(-1, 63, 3).clone()
+    p = p / 3
+    p[:, 43:, :] = p[:, 43:, :] + p[:, [11], :]
+    p[:, 23:43, :] = p[:, 23:43, :] + p[:, [7], :]
+    p[:, 1:, :] = p[:, 1:, :] + p[:, :1, :]
+    return p
+
+
 # --------------------------------------------------------------------------- conditioning
 def audio_encoder(sd, mel: Tensor, prefix: str = "text_audio_encoder.audio_encoder.") -> Tensor:
     """audioenc.py:13-34: Linear -> LeakyReLU(0.1) -> Linear -> LeakyReLU(0.1) -> out_net."""

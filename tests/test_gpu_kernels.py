@@ -184,3 +184,13 @@ def test_conditioning_projections():
     assert max_rel(s.text_audio_encoder.audio_encoder(mel.to(DEV)).cpu(), O.audio_encoder(sd, mel)) < 5e-6
     txt, _, _ = s.text_audio_encoder.text_encoder(t5.to(DEV), torch.ones(2, 6, device=DEV))
     assert max_rel(txt.cpu(), O.text_projection(sd, t5)) < 5e-6
+
+
+def test_keypoints3d_is_bit_exact():
+    """base.py:204-209 post-processing (divide by 3, re-attach fingers to wrists, everything to the root)."""
+    x = torch.randn(5, 37, 189, generator=torch.Generator().manual_seed(8)) * 2
+    got = cf.keypoints3d(x.to(DEV))
+    want = O.feats_to_keypoints3d(x.reshape(-1, 189)).reshape(5, 37, 63, 3)
+    assert got.shape == (5, 37, 63, 3) and torch.equal(got.cpu(), want)
+    with pytest.raises(_lib.CfbError):
+        cf.keypoints3d(x)

@@ -60,5 +60,9 @@ def test_optional_paths_agree_with_default(tmp_path):
         # adds the conditional streams' contribution to the residual BEFORE the shared one (different fp32 order)
         if name in ("cluster42", "cluster21", "serial", "ln_separate", "staged_epilogue", "occ3", "softmax_strided"):
             assert torch.equal(got, base), name
+        elif name == "mha_simt":
+            # CUDA-core attention keeps the probabilities in fp32, the tensor-core kernel rounds them to bf16 before
+            # P.V: one more bf16 rounding site per attention, amplified like every other one
+            assert l2 < 0.12, name
         else:
             assert l2 < 6e-2, name   # same scale as the bf16-vs-fp32 first-step error (test_gpu_parity)

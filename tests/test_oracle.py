@@ -146,3 +146,15 @@ def test_forecast_aliasing_quirk():
     assert torch.allclose(calls[0][:, :8], first)
     assert torch.allclose(calls[1][:, :8], nsch.add_noise(pre, first, t1))
     assert not torch.allclose(calls[1][:, :8], nsch.add_noise(pre, init[:, :8], t1))
+
+
+def test_keypoints_postprocessing_matches_numpy_semantics():
+    """base.py:204-209 written with numpy in-place slices there; the restatement keeps order and aliasing."""
+    import numpy as np
+    f = torch.randn(9, 189, generator=torch.Generator().manual_seed(3))
+    p = f.numpy().copy().reshape(-1, 63, 3)
+    p = p / 3
+    p[:, 43:, :] = p[:, 43:, :] + p[:, [11], :]
+    p[:, 23:43, :] = p[:, 23:43, :] + p[:, [7], :]
+    p[:, 1:, :] = p[:, 1:, :] + p[:, :1, :]
+    assert np.array_equal(O.feats_to_keypoints3d(f).numpy(), p)
