@@ -396,17 +396,22 @@ template <typename T>
 int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, const CrossArgs& ca,
               float* const att_base[CFB_N_STREAMS], const StepArgs& sa, const SharedPlan& sp, cudaStream_t st) {
   const int* step_ptr = h->step.as<int>();
-  CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
   const bool overlap = sp.on && h->n_chains > 1 && h->pre_st[0] != nullptr;
-  if (sp.on) {
-    if (overlap) {   // keys and values of the shared slot on two side streams, hidden behind the self-attention blocks
-      CFB_CUDA(cudaEventRecord(h->ev_mh, st));
-      for (int i = 0; i < 2; ++i) {
-        CFB_CUDA(cudaStreamWaitEvent(h->pre_st[i], h->ev_mh, 0));
-        CFB_TRY(shared_precompute(h, sp, ml, ca.len, i, h->pre_st[i]));
-        CFB_CUDA(cudaEventRecord(h->ev_pre[i], h->pre_st[i]));
-      }
-    } else {
+  if (overlap) {
+    // The per-step memory normalisation and the keys / values of the shared slot are needed first by layer 0's
+    // cross-attention, so they leave the critical path entirely: two side streams, joined by ev_pre in run_layers.
+    CFB_CUDA(cudaEventRecord(h->ev_fork, st));
+    CFB_CUDA(cudaStreamWaitEvent(h->pre_st[0], h->ev_fork, 0));
+    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, h->pre_st[0]));
+    CFB_CUDA(cudaEventRecord(h->ev_mh, h->pre_st[0]));
+    CFB_CUDA(cudaStreamWaitEvent(h->pre_st[1], h->ev_mh, 0));
+    for (int i = 0; i < 2; ++i) {
+      CFB_TRY(shared_precompute(h, sp, ml, ca.len, i, h->pre_st[i]));
+      CFB_CUDA(cudaEventRecord(h->ev_pre[i], h->pre_st[i]));
+    }
+  } else {
+    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
+    if (sp.on) {
       CFB_TRY(shared_precompute(h, sp, ml, ca.len, 0, st));
       CFB_TRY(shared_precompute(h, sp, ml, ca.len, 1, st));
     }
@@ -636,14 +641,23 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
     if (want > cfb_denoiser::MAX_CHAINS) want = cfb_denoiser::MAX_CHAINS;
     h->n_chains = want;
     if (!h->ev_fork) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    // Chains are not equally long: the chain of the audio-only branch carries the 161-key per-pair attention.
+    // CFB_PRIO_CHAINS (bit mask of chain indices) / CFB_PRIO_SIDE give those streams the highest launch priority.
+    int prio_lo = 0, prio_hi = 0;
+    CFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const int prio_mask = getenv("CFB_PRIO_CHAINS") ? atoi(getenv("CFB_PRIO_CHAINS")) : 0;
+    const int prio_side = getenv("CFB_PRIO_SIDE") ? atoi(getenv("CFB_PRIO_SIDE")) : 0;
     for (int c = 1; c < want; ++c) {
-      if (!h->chain_st[c]) CFB_CUDA(cudaStreamCreateWithFlags(&h->chain_st[c], cudaStreamNonBlocking));
+      if (!h->chain_st[c])
+        CFB_CUDA(cudaStreamCreateWithPriority(&h->chain_st[c], cudaStreamNonBlocking, (prio_mask >> c) & 1 ? prio_hi : prio_lo));
       if (!h->ev_join[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
     }
     const char* o = getenv("CFB_OVERLAP");
     if (want > 1 && !(o && atoi(o) == 0)) {
       for (int c = 0; c < want; ++c) {
-        if (!h->chain_st2[c]) CFB_CUDA(cudaStreamCreateWithFlags(&h->chain_st2[c], cudaStreamNonBlocking));
+        if (!h->chain_st2[c])
+          CFB_CUDA(cudaStreamCreateWithPriority(&h->chain_st2[c], cudaStreamNonBlocking,
+                                                (prio_side || ((prio_mask >> c) & 1)) ? prio_hi : prio_lo));
         if (!h->ev_a[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_a[c], cudaEventDisableTiming));
         if (!h->ev_b[c]) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_b[c], cudaEventDisableTiming));
       }
