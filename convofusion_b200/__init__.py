@@ -4,6 +4,7 @@ Public surface (mirrors the reference's operator surface):
   Denoiser, ConvoFusionVae            drop-in modules (identical state_dict keys and call signatures)
   DDIMScheduler, DDPMScheduler        diffusers-0.14-compatible scheduler mirrors
   ConvoFusionSampler                  test_diffusion_forward / unbounded synthesis orchestration
+  SamplerPool                         several independent batches in flight on one GPU (one handle + stream per lane)
 All arithmetic runs in lib/libconvofusion_b200.so (hand-written CUDA, C ABI in include/convofusion_b200.h).
 """
 from .modules import ConvoFusionVae, Denoiser
@@ -11,7 +12,8 @@ from .schedulers import DDIMScheduler, DDPMScheduler
 from .conditioning import AudioConvEncoder, T5TextEncoder, TextAudioController, TextAudioMotionFuser
 from .sampler import ConvoFusionSampler, default_denoiser, default_scheduler, default_vae
 from .postprocess import keypoints3d
+from .pool import SamplerPool
 
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
-           "default_denoiser", "default_vae", "default_scheduler", "keypoints3d"]
+           "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool"]

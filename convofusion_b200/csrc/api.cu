@@ -6,7 +6,8 @@
 namespace cfb {
 
 static thread_local char g_err[1024] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
+thread_local bool t_capturing = false;
 int g_use_pdl = getenv("CFB_PDL") ? atoi(getenv("CFB_PDL")) : 1;
 
 void set_error(const char* fmt, ...) {
@@ -52,7 +53,7 @@ int cfb_debug_linear_ln_tail(const void* A, const void* W, const float* bias, fl
 
 int cfb_abi_version(void) { return CFB_ABI_VERSION; }
 const char* cfb_last_error(void) { return g_err; }
-unsigned long long cfb_launch_count(void) { return g_launches; }
+unsigned long long cfb_launch_count(void) { return g_launches.load(); }
 
 int cfb_set_gemm_backend(int backend) {
   CFB_CHECK(backend >= CFB_GEMM_AUTO && backend <= CFB_GEMM_TCGEN05, "unknown gemm backend %d", backend);

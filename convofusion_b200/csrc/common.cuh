@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <string>
+#include <atomic>
 #include "../../include/convofusion_b200.h"
 
 namespace cfb {
@@ -13,7 +14,8 @@ namespace cfb {
 typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;   // kernels launched (graph replays included)
+extern thread_local bool t_capturing;                    // launches recorded into a graph are counted per replay
 
 #define CFB_CUDA(expr)                                                                   \
   do {                                                                                   \
@@ -41,7 +43,7 @@ extern unsigned long long g_launches;
 // Every kernel launch goes through this so gpu_launches is an honest count.
 #define CFB_LAUNCH_CHECK()                                                               \
   do {                                                                                   \
-    ++cfb::g_launches;                                                                   \
+    if (!cfb::t_capturing) ++cfb::g_launches;                                            \
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess) {                                                             \
       cfb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -714,10 +714,10 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       h->graph_valid = false;
       cudaGraph_t graph = nullptr;
       CFB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const unsigned long long launches_before = g_launches;
+      t_capturing = true;   // captured, not launched
       int rc = body();
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      g_launches = launches_before;   // captured, not launched
+      t_capturing = false;
       if (rc != CFB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
       if (ce != cudaSuccess) { set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce)); return CFB_ERR_CUDA; }
       size_t n_nodes = 0;

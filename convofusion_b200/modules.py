@@ -12,8 +12,10 @@ nothing falls back to torch ops: a missing library or a CPU tensor raises.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
+import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -101,23 +103,68 @@ def _precision_id(p: str) -> int:
     return _lib.F32 if p == "fp32" else _lib.BF16
 
 
+_lane_state = threading.local()
+_lane_lock = threading.RLock()   # handle creation (module-level: nn.Modules must stay deep-copyable)
+
+
+@contextlib.contextmanager
+def lane(index: int):
+    """Selects the device handle the calling thread's Denoiser / ConvoFusionVae calls run on.
+
+    A handle owns one workspace and one captured step graph, so it serves one call at a time.  Lane k > 0 is an
+    extra handle over the SAME packed weights, created on first use; `SamplerPool` (pool.py) runs one host thread +
+    one stream per lane to keep several independent batches in flight on one GPU."""
+    prev = getattr(_lane_state, "index", 0)
+    _lane_state.index = int(index)
+    try:
+        yield
+    finally:
+        _lane_state.index = prev
+
+
+def current_lane() -> int:
+    return getattr(_lane_state, "index", 0)
+
+
 class _CudaModule(nn.Module):
     """Shared handle management: weights are (re)packed lazily whenever parameters may have changed."""
 
     def __init__(self):
         super().__init__()
-        self._handle = None
+        self._handle = None      # lane 0
+        self._lanes = {}         # lane k > 0 -> handle over the same packed weights
         self._packed = None      # keeps packed device tensors + ctypes structs alive
         self._pack_key = None
         self.precision = os.environ.get("CONVOFUSION_B200_PRECISION", "bf16")
 
-    def _destroy(self):
+    def _destroy(self, handle):
+        raise NotImplementedError
+
+    def _create(self, packed):
         raise NotImplementedError
 
     def _invalidate(self):
         if self._handle is not None:
-            self._destroy()
+            self._destroy(self._handle)
+        for h in getattr(self, "_lanes", {}).values():
+            self._destroy(h)
         self._handle, self._packed, self._pack_key = None, None, None
+        self._lanes = {}
+
+    def _ensure(self):
+        """Handle of the calling thread's lane (packs the weights / creates the handle on first use)."""
+        k = current_lane()
+        if k == 0 and self._handle is not None:
+            return self._handle
+        with _lane_lock:
+            if self._handle is None:
+                self.pack()
+            if k == 0:
+                return self._handle
+            if k not in self._lanes:
+                with torch.cuda.device(self._device()):
+                    self._lanes[k] = self._create(self._packed)
+            return self._lanes[k]
 
     def _apply(self, fn, *a, **k):   # .to() / .cuda() / .float()
         self._invalidate()
@@ -196,8 +243,13 @@ class Denoiser(_CudaModule):
             self.set_precision(precision)
 
     # ---- handle
-    def _destroy(self):
-        _lib.lib().cfb_denoiser_destroy(self._handle)
+    def _destroy(self, handle):
+        _lib.lib().cfb_denoiser_destroy(handle)
+
+    def _create(self, packed):
+        h = C.c_void_p()
+        _lib.check(_lib.lib().cfb_denoiser_create(C.byref(packed["struct"]), C.byref(h)))
+        return h
 
     def pack(self):
         """(Re)build the packed weights and the device handle.  Called lazily by forward()/sample()."""
@@ -205,16 +257,10 @@ class Denoiser(_CudaModule):
         self._invalidate()
         packed = pack_denoiser(self.state_dict(), "", self.num_layers, self.num_heads, self.n_tokens,
                                _precision_id(self.precision), dev)
-        h = C.c_void_p()
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().cfb_denoiser_create(C.byref(packed["struct"]), C.byref(h)))
+            h = self._create(packed)
         self._handle, self._packed = h, packed
         return self
-
-    def _ensure(self):
-        if self._handle is None:
-            self.pack()
-        return self._handle
 
     # ---- memory description
     @staticmethod
@@ -384,24 +430,27 @@ class ConvoFusionVae(_CudaModule):
         if precision is not None:
             self.set_precision(precision)
 
-    def _destroy(self):
-        _lib.lib().cfb_vae_destroy(self._handle)
+    def _destroy(self, handle):
+        _lib.lib().cfb_vae_destroy(handle)
+
+    def _create(self, packed):
+        h = C.c_void_p()
+        _lib.check(_lib.lib().cfb_vae_create(C.byref(packed["struct"]), C.byref(h)))
+        return h
 
     def pack(self):
         dev = self._device()
         self._invalidate()
         packed = pack_vae(self.state_dict(), "", self.num_layers, self.num_heads, self.ff_size,
                           _precision_id(self.precision), dev)
-        h = C.c_void_p()
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().cfb_vae_create(C.byref(packed["struct"]), C.byref(h)))
+            h = self._create(packed)
         self._handle, self._packed = h, packed
         return self
 
     def decode(self, z: Tensor, lengths: List[int]) -> Tensor:
         dev = self._device()
-        if self._handle is None:
-            self.pack()
+        handle = self._ensure()
         if z.dim() != 4 or z.shape[0] != 2 or z.shape[-1] != self.latent_dim:
             raise ValueError(f"z must be [2, B, n_chunks, {self.latent_dim}], got {tuple(z.shape)}")
         _, bs, n_chunks, _ = z.shape
@@ -413,15 +462,14 @@ class ConvoFusionVae(_CudaModule):
         out = torch.empty(bs, nframes, self.body_nfeats + self.hands_nfeats, device=dev, dtype=torch.float32)
         lens = (C.c_int32 * bs)(*lengths)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().cfb_vae_decode(self._handle, zc.data_ptr(), bs, n_chunks, nframes, lens,
+            _lib.check(_lib.lib().cfb_vae_decode(handle, zc.data_ptr(), bs, n_chunks, nframes, lens,
                                                  out.data_ptr(), _lib.stream_ptr()))
         return out
 
     def encode_params(self, features: Tensor, lengths: Optional[List[int]] = None) -> Tuple[Tensor, Tensor, Tensor]:
         """Deterministic part of encode (vae.py:162-260): (mu, std [2, B*T/16, d], root-subtracted features)."""
         dev = self._device()
-        if self._handle is None:
-            self.pack()
+        handle = self._ensure()
         if features.dim() != 3 or features.shape[-1] != self.body_nfeats + self.hands_nfeats:
             raise ValueError(f"features must be [B, T, {self.body_nfeats + self.hands_nfeats}], got {tuple(features.shape)}")
         bs, nframes, nfeats = features.shape
@@ -440,7 +488,7 @@ class ConvoFusionVae(_CudaModule):
         feats = torch.empty_like(x)
         lens = (C.c_int32 * bs)(*lengths)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().cfb_vae_encode(self._handle, x.data_ptr(), bs, nframes, lens, mu.data_ptr(),
+            _lib.check(_lib.lib().cfb_vae_encode(handle, x.data_ptr(), bs, nframes, lens, mu.data_ptr(),
                                                  std.data_ptr(), feats.data_ptr(), _lib.stream_ptr()))
         return mu, std, feats
 

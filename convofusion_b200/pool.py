@@ -1,0 +1,102 @@
+"""Several independent batches in flight on one GPU.
+
+One guided sampling pass (`ConvoFusionSampler.generate`) is a chain of ~150 dependent short kernels per step: at the
+reference's batch of 64 clips it is bound as much by that chain's latency as by throughput, and the
+clips of different batches never interact (clips / streams are the independent units).  `SamplerPool`
+therefore runs `lanes` passes side by side: every lane owns a device handle (workspace + captured step graph) over the
+SAME packed weights, a CUDA stream and a host thread.  The host thread matters: a thread blocks inside
+`cudaGraphLaunch` once its stream's launch queue is full (50 replays of a ~1000-node graph), so a single host thread
+would not get the next batch enqueued before the first one has almost drained.
+
+This is the data-parallel path of BASELINE.json configs[4] (4096 clips in batches of 64) inside one GPU; across GPUs
+the batches are partitioned by `distributed.shard_range`.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+from .modules import lane
+
+
+def _record_stream(obj: Any, stream: torch.cuda.Stream) -> None:
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream)
+
+
+class SamplerPool:
+    def __init__(self, sampler, lanes: int = 2):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.sampler = sampler
+        self.lanes = int(lanes)
+        self._streams: Optional[List[torch.cuda.Stream]] = None
+
+    def _device(self) -> torch.device:
+        return self.sampler.denoiser._device()      # raises on CPU parameters: there is no CPU path
+
+    def streams(self) -> List[torch.cuda.Stream]:
+        if self._streams is None:
+            dev = self._device()
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
+        return self._streams
+
+    def map(self, fn: Callable[[Any, int], Any], items: Sequence[Any]) -> List[Any]:
+        """Runs fn(item, lane_index) for every item, `lanes` at a time; results in item order.
+
+        Inside fn the calling thread's current stream is the lane's stream and Denoiser / ConvoFusionVae calls run
+        on the lane's handle.  Work already queued on the caller's current stream is visible to every lane, and the
+        caller's stream waits for all lanes before `map` returns (no host synchronisation of the device)."""
+        dev = self._device()
+        streams = self.streams()
+        caller = torch.cuda.current_stream(dev)
+        for s in streams:
+            s.wait_stream(caller)
+        todo: "queue.SimpleQueue" = queue.SimpleQueue()
+        for i, it in enumerate(items):
+            todo.put((i, it))
+        results: List[Any] = [None] * len(items)
+        errors: List[BaseException] = []
+
+        def worker(k: int):
+            try:
+                torch.cuda.set_device(dev)
+                with lane(k), torch.cuda.stream(streams[k]), torch.no_grad():
+                    while not errors:
+                        try:
+                            i, it = todo.get_nowait()
+                        except queue.Empty:
+                            return
+                        results[i] = fn(it, k)
+            except BaseException as exc:      # re-raised on the calling thread
+                errors.append(exc)
+
+        n = min(self.lanes, max(1, len(items)))
+        if n == 1:
+            worker(0)
+        else:
+            threads = [threading.Thread(target=worker, args=(k,), name=f"cfb-lane-{k}") for k in range(n)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        for s in streams:
+            caller.wait_stream(s)
+        if errors:
+            raise errors[0]
+        _record_stream(results, caller)      # allocated on a lane's stream, consumed on the caller's
+        return results
+
+    def generate_many(self, batches: Iterable[Dict[str, Any]]) -> List[Dict[str, Any]]:
+        """`ConvoFusionSampler.generate(**batch)` for every batch (dicts of its keyword arguments)."""
+        return self.map(lambda kw, _k: self.sampler.generate(**kw), list(batches))

@@ -343,3 +343,29 @@ def test_bf16_sampling_run_tolerance_and_properties_full_size():
     j32 = sf.decode(sf.sample(enc4, masks4, 4, init[:4])[0], [128] * 4)
     print(f"bf16 joints max-rel vs fp32: {max_rel(joints[:4].cpu(), j32.cpu()):.3e}")
     assert max_rel(joints[:4].cpu(), j32.cpu()) < BF16_TOL["joints"]
+
+
+def test_sampler_pool_equals_direct_calls():
+    """Independent batches in flight (SamplerPool: one handle over the same packed weights + stream + host thread per
+    lane) return, bit for bit, what one `generate` call per batch returns; lanes may outnumber or undercut batches."""
+    sb = gpu_sampler("bf16", steps=8)
+    U = None
+    jobs, direct = [], []
+    for i, B in enumerate([3, 8, 5, 8, 2]):
+        syn = synthetic_clip(B, seed=900 + i, dyadic=bool(i % 2))
+        clip = to_device(syn["clip"], DEV)
+        U, Ua = syn["uncond_text"].to(DEV), syn["uncond_text_attn"].to(DEV)
+        init = torch.randn(B, 16, 128, generator=torch.Generator().manual_seed(950 + i)).to(DEV)
+        jobs.append(dict(clip=clip, uncond_text=U, uncond_text_attn=Ua, lengths=[128] * B, init_latents=init))
+    for kw in jobs:
+        direct.append(sb.generate(**kw)["m_rst"].clone())
+    for lanes in (1, 2, 3):
+        outs = cf.SamplerPool(sb, lanes=lanes).generate_many(jobs)
+        torch.cuda.synchronize()
+        for o, d in zip(outs, direct):
+            assert torch.equal(o["m_rst"], d)
+    # an error inside a lane surfaces on the calling thread
+    bad = dict(jobs[0], lengths=[128])
+    with pytest.raises(ValueError):
+        cf.SamplerPool(sb, lanes=2).generate_many([jobs[1], bad, jobs[2]])
+    torch.cuda.synchronize()

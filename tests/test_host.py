@@ -166,6 +166,29 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in _lib.lib().cfb_last_error()
 
 
+def test_lane_context_and_pool_host_logic():
+    """modules.lane is a per-thread, re-entrant selector; SamplerPool validates its arguments and, like every other
+    entry point, refuses to run without a GPU."""
+    import threading
+    from convofusion_b200.modules import current_lane, lane
+    assert current_lane() == 0
+    seen = {}
+    with lane(2):
+        assert current_lane() == 2
+        with lane(1):
+            assert current_lane() == 1
+        assert current_lane() == 2
+        t = threading.Thread(target=lambda: seen.setdefault("other", current_lane()))
+        t.start(); t.join()
+    assert current_lane() == 0 and seen["other"] == 0
+    with pytest.raises(ValueError):
+        cf.SamplerPool(None, lanes=0)
+    if not torch.cuda.is_available():
+        pool = cf.SamplerPool(cf.ConvoFusionSampler(precision="fp32"), lanes=2)
+        with pytest.raises(_lib.CfbError):
+            pool.generate_many([{}])
+
+
 def test_state_dict_layout_is_the_reference_layout():
     """Spot-check the key convention of SURVEY 8b (full strict-load against the reference modules is done by
     tools/make_golden.py, which needs /root/reference)."""
