@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--windows", type=int, default=0,
                     help="configs[3]: unbounded synthesis, this many serial 128-frame windows at 50 %% overlap per stream "
                          "(latent inpainting of the previous window + decode per window); 0 = bounded clips")
-    ap.add_argument("--in-flight", type=int, default=1,
+    ap.add_argument("--in-flight", type=int, default=2,
                     help="independent batches kept in flight on one GPU (one sampler handle + stream each); every step "
                          "is still one full pass over one batch of --batch clips, steps of different handles overlap")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -312,6 +312,7 @@ def run_ours(args):
         return ms, launches, ck
 
     F = max(1, args.in_flight)
+    single = None
     if W > 0:
         F = 1      # windows of one stream are serial (preseq + root hand-off)
     if F > 1:
@@ -319,29 +320,38 @@ def run_ours(args):
         # one handle over the same packed weights + one stream + one host thread per lane).  The timed region is
         # still exactly K full passes over K batches of B clips.
         pool = cf.SamplerPool(sampler, lanes=F)
-        outs_host = [torch.empty(B, 128, 189).pin_memory() for _ in range(F)]
-        gath = [[torch.empty(B, 128, 189, device=dev) for _ in range(world)] if world > 1 else None for _ in range(F)]
+        # e2e: two pinned result buffers per lane; a buffer is waited for only when its turn comes again, so a lane
+        # enqueues its next pass while the previous pass's joints are still on their way to the host
+        outs_host = [[torch.empty(B, 128, 189).pin_memory() for _ in range(2)] for _ in range(F)]
+        landed = [[None, None] for _ in range(F)]
+        turn = [0] * F
 
         def lane_device(_i, k):
-            out = sampler.generate(dclip, Ud, Uad, lengths, dinit, use_graph=not args.no_graph)["m_rst"]
-            if world > 1:
-                dist.all_gather(gath[k], out)
-            return None
+            return sampler.generate(dclip, Ud, Uad, lengths, dinit, use_graph=not args.no_graph)["m_rst"]
 
         def lane_e2e(_i, k):
             c = {kk: v.to(dev, non_blocking=True) for kk, v in host.items()}
             c["lsn_id"] = clip["lsn_id"]
             x = host_init.to(dev, non_blocking=True)
             out = sampler.generate(c, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
-            if world > 1:
-                dist.all_gather(gath[k], out)
-            outs_host[k].copy_(out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the step's joints are on the host
-            return None
+            j = turn[k] & 1
+            turn[k] += 1
+            if landed[k][j] is not None:
+                landed[k][j].synchronize()                 # the joints written two passes ago are on the host
+            outs_host[k][j].copy_(out, non_blocking=True)
+            landed[k][j] = torch.cuda.Event()
+            landed[k][j].record()
+            return out
+
+        def run_steps(fn, n):
+            outs = pool.map(fn, list(range(n)))
+            if world > 1:      # the only collective: output motions, gathered by the main thread once the lanes are
+                for o in outs:  # done (a fixed order on every rank; NCCL calls are not issued from the lane threads)
+                    dist.all_gather(gathered, o)
 
         def timed_pool(fn, warmup, steps, sample_clocks):
             with torch.cuda.stream(stream):
-                pool.map(fn, list(range(max(warmup, 1) * F)))
+                run_steps(fn, max(warmup, 1) * F)
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()
@@ -352,7 +362,7 @@ def run_ours(args):
                 l0 = _lib.lib().cfb_launch_count()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                pool.map(fn, list(range(steps)))
+                run_steps(fn, steps)
                 e1.record()
                 torch.cuda.synchronize()
                 if world > 1:
@@ -369,6 +379,9 @@ def run_ours(args):
 
         ms_dev, launches, clocks = timed_pool(lane_device, args.warmup, args.steps, True)
         ms_e2e, _, _ = timed_pool(lane_e2e, 1, args.steps, False)
+        ms_one, _, _ = timed(pass_device, args.warmup, max(2, args.steps // 2), False)   # one batch in flight: the latency view
+        single = {"value": B * world * max(2, args.steps // 2) * MOTION_S_PER_CLIP / (ms_one * 1e-3), "unit": "motion-s/s",
+                  "ms_per_step": ms_one / max(2, args.steps // 2)}
     else:
         ms_dev, launches, clocks = timed(pass_device, args.warmup, args.steps, True)
         ms_e2e, _, _ = timed(pass_e2e, 1, args.steps, False)
@@ -410,11 +423,18 @@ def run_ours(args):
             "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": dict(workload_config(args, B), batches_in_flight=F),
+            "config": dict(workload_config(args, B), batches_in_flight=F,
+                           in_flight=("every step is one full pass over its own batch of %d clips; %d independent batches "
+                                      "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
+                                      % (B, F)) if F > 1 else "one batch at a time"),
             "e2e": {"value": e2e_value, "unit": "motion-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
+            "one_batch_in_flight": single,
             "ms_per_denoiser_step": ms_den, "pass_split_ms": parts,
+            # whole pass (conditioning + decode included) / DDIM steps at the measured throughput: with several batches
+            # in flight this is below the single-batch latency figure above
+            "ms_per_denoiser_step_at_throughput": ms_dev / args.steps / args.ddim_steps,
             "denoiser_step_tflops": {"executed": fl["executed"] / (ms_den * 1e-3) / 1e12,
                                      "reference_equivalent": fl["as_written"] / (ms_den * 1e-3) / 1e12,
                                      "executed_gflop_per_step": fl["executed"] / 1e9},
@@ -428,7 +448,9 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)", "achieved": tf, "peak": peak_tf,
                                 "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
                                 "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
-                                "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf}
+                                "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
+                                "whole_step_frac_at_throughput":
+                                    fl["executed"] * args.ddim_steps / (ms_dev / args.steps * 1e-3) / 1e12 / peak_tf}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             r = cpu_reference_run(2, args.ddim_steps, 4, args.dyadic, cores)

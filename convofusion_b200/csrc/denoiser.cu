@@ -69,6 +69,7 @@ struct cfb_denoiser {
   cudaStream_t chain_st[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
   int n_chains = 1;
+  int chains_override = 0;   // cfb_denoiser_set_chains (0 = CFB_CHAINS or 6)
   // per chain: side stream for the conditional-pair sub-chain of every layer; per step: two streams that run the
   // memory-side pre-projection (keys / values) while the chains are still in their self-attention blocks
   cudaStream_t chain_st2[MAX_CHAINS] = {}, pre_st[2] = {};
@@ -565,6 +566,13 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   delete h;
 }
 
+int cfb_denoiser_set_chains(cfb_denoiser* h, int n_chains) {
+  CFB_CHECK(h != nullptr, "cfb_denoiser_set_chains: null handle");
+  CFB_CHECK(n_chains >= 0 && n_chains <= cfb_denoiser::MAX_CHAINS, "n_chains %d outside 0..%d", n_chains, cfb_denoiser::MAX_CHAINS);
+  h->chains_override = n_chains;
+  return CFB_OK;
+}
+
 int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int64_t timestep, const cfb_memory* mem,
                          float* eps_out, float* const att_out[CFB_N_STREAMS], cfb_stream stream) {
   CFB_CHECK(h && sample && mem && eps_out && n_batch > 0, "cfb_denoiser_forward: bad argument");
@@ -636,7 +644,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_TRY(make_shared_plan(h, mem, n_batch, &sp, st));
   {
     const char* e = getenv("CFB_CHAINS");
-    int want = e ? atoi(e) : 6;
+    int want = h->chains_override > 0 ? h->chains_override : e ? atoi(e) : 6;
     if (want < 1) want = 1;
     if (want > cfb_denoiser::MAX_CHAINS) want = cfb_denoiser::MAX_CHAINS;
     h->n_chains = want;

@@ -112,6 +112,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants.  The pair shares one MMA: the leader (cluster rank 0) issues it, the operands
+// are read from BOTH CTAs' shared memory at the same offsets, each CTA's tensor memory receives its own 128 rows.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA (cluster-space address).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -732,6 +770,181 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_ln_kernel(const __grid_co
   gemm_tile<BN, STAGES, 1, 1, true>(&tmA, &tmB, nullptr, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
+// ---------------------------------------------------------------- cta_group::2: 256 x 256 tile per CTA pair
+// With 128x128 tiles a CTA pulls 32 KB from L2 per 64-deep K block for 1 M MACs; at full occupancy the L2 -> SM path
+// (not the tensor pipe) bounds the kernel (launch list at batch 256: 395 TFLOP/s).  A CTA pair on one TPC shares one
+// tcgen05.mma.cta_group::2 (M = 256, N = 256): CTA r holds rows [m0 + 128 r, +128) of A and rows [n0 + 128 r, +128) of W
+// -- the same 32 KB per K block as before -- and receives the accumulators of ITS 128 rows for all 256 columns in its
+// own tensor memory, i.e. twice the MACs per byte pulled from L2.
+//   * every barrier the MMA waits on lives in the leader (rank 0): both CTAs' TMA loads complete_tx on the leader's
+//     `full` barrier, the leader's producer thread expects the bytes of both;
+//   * a stage is released by ONE multicast tcgen05.commit that arrives on the `empty` barrier of both CTAs (the MMA
+//     reads both CTAs' shared memory), and the accumulator-ready commit is multicast the same way;
+//   * the epilogue is the TMA store / L2 reduce-add epilogue of gemm_tile, 256 columns in two passes of 128 so that the
+//     staging boxes fit in the idle 96 KB pipeline ring.
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  const __grid_constant__ CUtensorMap tmO, int M, int N,
+                                                                  int K, Epilogue ep) {
+  using S = Smem<128, STAGES>;          // per CTA: 128 x 64 of A + 128 x 64 of W per stage
+  constexpr int BN2 = 256;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const bool leader = crank == 0;
+  const int m0 = (int)(blockIdx.x >> 1) * 256 + (int)crank * 128;
+  const int n0 = (int)blockIdx.y * BN2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = base + S::BAR_OFF;
+  const uint32_t bar_empty = bar_full + STAGES * 8;
+  const uint32_t bar_acc = bar_empty + STAGES * 8;
+  const uint32_t tmem_slot = bar_acc + 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + S::BAR_OFF + (2 * STAGES + 1) * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);    // used in the leader only: its producer's arrive.expect_tx (+ both CTAs' bytes)
+      mbar_init(bar_empty + s * 8, 1);   // one multicast commit per round
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, BN2);   // the same warp of both CTAs, same shared-memory slot
+  tc_fence_before();
+  cluster_sync_all();                                // peer barriers initialised, allocation visible
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+  pdl_sync();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty + s * 8, ph ^ 1);
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        if (leader) mbar_expect_tx(bar_full + s * 8, 2 * S::STAGE_BYTES);
+        const uint32_t full_leader = mapa_shared(bar_full + s * 8, 0);
+        tma_load_2d_pair(sa, &tmA, kb * BK, m0, full_leader);
+        tma_load_2d_pair(sb, &tmB, kb * BK, n0 + (int)crank * 128, full_leader);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, BN2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16_pair(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit_pair(bar_empty + s * 8, (uint16_t)3);
+      }
+      umma_commit_pair(bar_acc, (uint16_t)3);
+    }
+  } else {
+    const int q = warp & 3;
+    float* bias_s = reinterpret_cast<float*>(gen_base + S::STATS_OFF);     // 256 floats
+    const int te = threadIdx.x - 64;
+    const bool row_bias = ep.bias && ep.bias_period != 1;
+    bias_s[te] = (ep.bias && !row_bias) ? ep.bias[n0 + te] : 0.f;
+    bias_s[te + 128] = (ep.bias && !row_bias) ? ep.bias[n0 + te + 128] : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int r0w = m0 + q * 32;
+    if (r0w < M) {
+      const uint32_t stg_w = base + (uint32_t)q * 4u * 4096u;     // 4 boxes of [32 rows x 128 B] per warp and pass
+      const uint32_t sw = (uint32_t)(lane & 7);
+      const bool out_bf = ep.out_bf16 != 0;
+      const int act = ep.act;
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        const int cb = c & 3;                                       // box slot inside the pass
+        if (c == 4) {                                               // second pass reuses the boxes of the first
+          if (lane == 0) tma_wait_read0();
+          __syncwarp();
+        }
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j * 4);
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+        if (row_bias) {
+          const float* brow = ep.bias + (size_t)((r0w + lane) % ep.bias_period) * N + n0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(brow + j * 4);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+        if (act) {
+          if (out_bf) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_apply_fast(v[j], act);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j], act);
+          }
+        }
+        if (!out_bf) {
+          const uint32_t box = stg_w + (uint32_t)cb * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(box + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (ep.accumulate) tma_reduce_add_2d(&tmO, n0 + c * 32, r0w, stg_w + (uint32_t)cb * 4096u);
+            else tma_store_2d(&tmO, n0 + c * 32, r0w, stg_w + (uint32_t)cb * 4096u);
+            tma_commit();
+          }
+        } else {
+          const uint32_t box = stg_w + (uint32_t)(cb >> 1) * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              pk[e] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            st_shared_v4(box + (((uint32_t)((c & 1) * 4 + j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+          if (c & 1) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmO, n0 + (c >> 1) * 64, r0w, stg_w + (uint32_t)(cb >> 1) * 4096u);
+              tma_commit();
+            }
+          }
+        }
+      }
+      if (lane == 0) tma_wait_read0();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();     // neither CTA may exit (or free tensor memory) while the pair's MMA / commits can still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_acc, BN2);
+  }
+}
+
 // Grouped launch: blockIdx.z picks a group = (A map, B map, row block, bias, output).  All groups share N, K and
 // the epilogue flags.  Used for the conditional rows of the guidance batch, where every branch owns one
 // contiguous row block and its own stream's weights.
@@ -877,6 +1090,31 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, in
   return CFB_OK;
 }
 
+int g_tc_pair = 0;            // env CFB_TC_2CTA: 1 = cta_group::2 256x256 tiles for N % 256 == 0
+int g_tc_pair_min_rows = 0;   // env CFB_TC_2CTA_MIN_ROWS: only for GEMMs with at least this many rows
+
+int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep_in,
+                cudaStream_t st) {
+  using S = Smem<128, 3>;
+  CUtensorMap ta, tb, to;
+  Epilogue ep = ep_in;
+  CFB_TRY(get_map(A, M, K, lda, 128, &ta));
+  CFB_TRY(get_map(W, w_rows, K, ldw, 128, &tb));          // rows past w_rows read as zeros
+  ep.tma_out = 1;
+  CFB_TRY(get_map(ep.out, M, N, ep.ldo, 32, &to, ep.out_bf16 ? MAP_OUT_BF16 : MAP_OUT_F32));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * ceil_div(M, 256), N / 256); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<3>, ta, tb, to, M, N, K, ep));
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
 // [M,512] residual update + cluster LayerNorm: one 4-CTA cluster per 128-row block, PDL allowed.
 int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
   using S = Smem<128, 3>;
@@ -949,6 +1187,9 @@ int init_gemm_tc_kernels() {
   if (const char* e = getenv("CFB_TC_CLUSTER")) g_tc_cluster = atoi(e);
   if (const char* e = getenv("CFB_TC_TMA_EPI")) g_tc_tma_epi = atoi(e);
   if (const char* e = getenv("CFB_TC_OCC3")) g_tc_occ3 = atoi(e);
+  if (const char* e = getenv("CFB_TC_2CTA")) g_tc_pair = atoi(e);
+  if (const char* e = getenv("CFB_TC_2CTA_MIN_ROWS")) g_tc_pair_min_rows = atoi(e);
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 2>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 2>::TOTAL));
@@ -991,6 +1232,8 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   }
   if (w_rows <= 0 || w_rows > N) w_rows = N;
   if (ep.ln_out && ep.ln_tail) return launch<128, 3, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);   // tail needs plain CTAs
+  if (g_tc_pair && N % 256 == 0 && M >= g_tc_pair_min_rows && ep.ln_out == nullptr && tma_epilogue_ok(ep, 256))
+    return launch_pair(A, lda, W, ldw, w_rows, M, N, K, ep, st);
   if (N % 128 == 0) {
     // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.
     // Multicast pays when several tiles share an operand; a single m-tile (tiny M) gains nothing from CM.

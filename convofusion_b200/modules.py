@@ -239,6 +239,7 @@ class Denoiser(_CudaModule):
         self.condition_embedding = nn.Embedding(5, d)
         self.cond_params = nn.Parameter(1 / 5 * torch.ones(5))
         self.decoder = _DecoderStack(d, ff_size, num_layers)
+        self.step_chains = 0     # concurrent chains of the captured sampling step (0 = library default)
         if precision is not None:
             self.set_precision(precision)
 
@@ -356,6 +357,7 @@ class Denoiser(_CudaModule):
             att = [torch.empty(len(ts), B, self.num_layers, self.n_tokens, mem.len[i], device=dev) for i in range(5)]
             att_ptrs = (C.c_void_p * 5)(*[a.data_ptr() for a in att])
         with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cfb_denoiser_set_chains(h, int(self.step_chains)))
             _lib.check(_lib.lib().cfb_sample(h, C.byref(sched), C.byref(mem), B, n_branch, x.data_ptr(),
                                              _lib.ptr(step_noise), _lib.ptr(preseq), pl, _lib.ptr(rec), att_ptrs,
                                              int(use_graph), _lib.stream_ptr()))

@@ -35,11 +35,15 @@ def _record_stream(obj: Any, stream: torch.cuda.Stream) -> None:
 
 
 class SamplerPool:
-    def __init__(self, sampler, lanes: int = 2):
+    def __init__(self, sampler, lanes: int = 2, chains: Optional[int] = None):
+        """chains: concurrent chains inside each lane's captured step (Denoiser.step_chains) while the pool runs;
+        default 3 with two or more lanes (the lanes already supply concurrency: measured 6.18 k vs 6.00 k motion-s/s
+        with 6), the library default otherwise."""
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
         self.sampler = sampler
         self.lanes = int(lanes)
+        self.chains = int(chains) if chains is not None else (3 if lanes > 1 else 0)
         self._streams: Optional[List[torch.cuda.Stream]] = None
 
     def _device(self) -> torch.device:
@@ -82,14 +86,19 @@ class SamplerPool:
                 errors.append(exc)
 
         n = min(self.lanes, max(1, len(items)))
-        if n == 1:
-            worker(0)
-        else:
-            threads = [threading.Thread(target=worker, args=(k,), name=f"cfb-lane-{k}") for k in range(n)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
+        den = self.sampler.denoiser
+        prev_chains, den.step_chains = den.step_chains, self.chains
+        try:
+            if n == 1:
+                worker(0)
+            else:
+                threads = [threading.Thread(target=worker, args=(k,), name=f"cfb-lane-{k}") for k in range(n)]
+                for t in threads:
+                    t.start()
+                for t in threads:
+                    t.join()
+        finally:
+            den.step_chains = prev_chains
         for s in streams:
             caller.wait_stream(s)
         if errors:

@@ -112,6 +112,11 @@ typedef struct cfb_denoiser cfb_denoiser;
 int cfb_denoiser_create(const cfb_denoiser_weights *w, cfb_denoiser **out);
 void cfb_denoiser_destroy(cfb_denoiser *h);
 
+/* Concurrent chains of one captured sampling step: the guidance batch is cut into n_chains independent
+ * row groups that run the layer stack side by side (1..8; 0 = library default: CFB_CHAINS or 6).
+ * No reference counterpart (execution strategy only; results do not depend on it). */
+int cfb_denoiser_set_chains(cfb_denoiser *h, int n_chains);
+
 /* One denoiser evaluation: sample [n_batch, n_tokens, latent] float -> eps (same shape).
  * att_out[x] (or NULL): [n_batch, n_layers, n_tokens, len[x]] float attention weights, the
  * second return value of Denoiser.forward (cross_attention.py:234). */
