@@ -29,7 +29,7 @@ SCHED_KW = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, be
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step (BASELINE.json configs[1])")

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace cfb {
 
@@ -815,6 +816,8 @@ namespace {
 // Opt in to large dynamic shared memory once, outside any stream capture.
 int init_attention_kernels() {
   static bool done = false;
+  static std::mutex mu;     // handles may be created from several host threads (SamplerPool lanes)
+  std::lock_guard<std::mutex> lock(mu);
   if (done) return CFB_OK;
   if (const char* e = getenv("CFB_MHA_SIMT")) g_mha_simt = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));

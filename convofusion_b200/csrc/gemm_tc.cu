@@ -1176,6 +1176,8 @@ int tc_trace_read(unsigned long long out[16]) {
 
 int init_gemm_tc_kernels() {
   static bool done = false;
+  static std::mutex mu;     // handles may be created from several host threads (SamplerPool lanes)
+  std::lock_guard<std::mutex> lock(mu);
   if (done) return CFB_OK;
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
