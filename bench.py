@@ -446,7 +446,9 @@ def run_ours(args):
             if tfile.exists():
                 traffic = json.loads(tfile.read_text())
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)", "achieved": tf, "peak": peak_tf,
-                                "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                                "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
+                                "peak_source": peak_src,
                                 "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
                                 "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
                                 "whole_step_frac_at_throughput":
