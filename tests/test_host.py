@@ -203,3 +203,22 @@ def test_state_dict_layout_is_the_reference_layout():
         assert k in keys, k
     assert state_dict()["text_audio_encoder.audio_time_proj.weight"].shape == (512, 161)
     assert sum(v.numel() for k, v in state_dict().items() if k.startswith("denoiser.") and not k.endswith(".pe")) == 92923013
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) runs without a GPU and prints one JSON line with
+    the contract's keys, on our arm's metric / unit / workload."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ddim-steps", "4"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "motion_seconds_per_second" and line["unit"] == "motion-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "motion-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["clips_per_gpu"] == 64 and "configs[1]" in line["config"]["workload"]
