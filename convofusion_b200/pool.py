@@ -13,6 +13,7 @@ the batches are partitioned by `distributed.shard_range`.
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
@@ -41,6 +42,9 @@ class SamplerPool:
         with 6), the library default otherwise."""
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
+        if lanes > 1 and os.environ.get("CFB_TC_2CTA", "0") not in ("", "0"):
+            # the opt-in CTA-pair GEMM is verified single-stream only; one run with two lanes never finished (DESIGN.md 5)
+            raise RuntimeError("CFB_TC_2CTA=1 (cta_group::2 GEMM) is not supported with more than one lane")
         self.sampler = sampler
         self.lanes = int(lanes)
         self.chains = int(chains) if chains is not None else (3 if lanes > 1 else 0)

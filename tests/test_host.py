@@ -1,6 +1,7 @@
 """CPU-side checks of the host logic: weight folding, scheduler mirrors, guidance slot tables, the C ABI's
 symbol table, and the fail-loudly contract when no GPU is present.  No kernel runs here."""
 import ctypes
+import os
 import math
 import re
 from pathlib import Path
@@ -183,6 +184,13 @@ def test_lane_context_and_pool_host_logic():
     assert current_lane() == 0 and seen["other"] == 0
     with pytest.raises(ValueError):
         cf.SamplerPool(None, lanes=0)
+    os.environ["CFB_TC_2CTA"] = "1"
+    try:
+        with pytest.raises(RuntimeError):
+            cf.SamplerPool(None, lanes=2)      # the opt-in CTA-pair GEMM is single-stream only
+        cf.SamplerPool(None, lanes=1)
+    finally:
+        del os.environ["CFB_TC_2CTA"]
     if not torch.cuda.is_available():
         pool = cf.SamplerPool(cf.ConvoFusionSampler(precision="fp32"), lanes=2)
         with pytest.raises(_lib.CfbError):
