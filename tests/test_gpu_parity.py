@@ -369,3 +369,22 @@ def test_sampler_pool_equals_direct_calls():
     with pytest.raises(ValueError):
         cf.SamplerPool(sb, lanes=2).generate_many([jobs[1], bad, jobs[2]])
     torch.cuda.synchronize()
+
+
+def test_generate_fp32_vs_reference_test_diffusion_forward():
+    """The CUDA path through `ConvoFusionSampler.generate` against the outputs of the reference's own
+    `Convofusion.test_diffusion_forward` (tests/golden/ref_loops.pt["forward"], produced by
+    tools/pin_reference_loops.py from the unmodified reference sources): dyadic conditioning, B = 2, DDIM, guidance
+    7.5, ragged decode lengths."""
+    g = golden("ref_loops.pt")
+    f, B = g["forward"], g["B"]
+    s = gpu_sampler("fp32", g["n_steps"], cf.DDIMScheduler(clip_sample=True, **SCHED_KW))
+    d = to_device(synthetic_clip(B, seed=f["clip_seed"], dyadic=True), DEV)
+    torch.manual_seed(g["seed"] + 2)                      # the reference draws its latents from the global CPU RNG
+    init = torch.randn(B, 16, 128).to(DEV)
+    out = s.generate(d["clip"], d["uncond_text"], d["uncond_text_attn"], list(f["lengths"]), init)
+    lat = O.latents_to_vae_input(out["lat_t"].cpu()).permute(1, 2, 0, 3)
+    print(f"generate vs test_diffusion_forward: latents L2 {rel_err(lat, f['lat_t']):.2e}, "
+          f"joints max-rel {max_rel(out['m_rst'].cpu(), f['m_rst']):.2e}")
+    assert rel_err(lat, f["lat_t"]) < 2e-4
+    assert max_rel(out["m_rst"].cpu(), f["m_rst"]) < 1e-3

@@ -158,3 +158,51 @@ def test_keypoints_postprocessing_matches_numpy_semantics():
     p[:, 23:43, :] = p[:, 23:43, :] + p[:, [7], :]
     p[:, 1:, :] = p[:, 1:, :] + p[:, :1, :]
     assert np.array_equal(O.feats_to_keypoints3d(f).numpy(), p)
+
+
+def test_reverse_loops_match_the_reference_loop_code():
+    """tests/golden/ref_loops.pt holds the outputs of the reference's OWN `Convofusion._diffusion_reverse`
+    (convofusion.py:391-549) and `diffusion_reverse_forecast` (unbounded_synthesis.py:28-187), imported unmodified by
+    tools/pin_reference_loops.py (which also asserts that the oracle loops driven by the reference Denoiser are
+    bit-identical to them).  Here the oracle replays them end to end with its own denoiser: loop structure, 7-way
+    guidance, attention-map selection, latent inpainting with the aliasing quirk."""
+    g = golden("ref_loops.pt")
+    B, n = g["B"], g["n_steps"]
+    enc, masks = oracle_batch(synthetic_clip(B, seed=3100, dyadic=True))
+    for tag, kw in (("clip", dict(clip_sample=True)), ("mld", dict(clip_sample=False, set_alpha_to_one=False, steps_offset=1))):
+        torch.manual_seed(g["seed"])                       # the reference draws its latents from the global RNG (:412)
+        init = torch.randn(B, 16, 128)
+        sch = O.DDIMSchedulerOracle(**SCHED_KW, **kw)
+        z, att = O.diffusion_reverse(oracle_denoise, sch, enc, masks, init, n, guidance_scale=7.5)
+        ref = g[f"reverse_{tag}"]
+        assert rel_err(z, ref["z"]) < 1e-4, tag
+        assert max_rel(att[ref["t_last"]][2], ref["att_last_tlsn"]) < 1e-3, tag
+    enc, masks = oracle_batch(synthetic_clip(B, seed=3200, dyadic=True))
+    preseq = torch.randn(B, 8, 128, generator=torch.Generator().manual_seed(g["preseq_seed"]))
+    for tag, pre in (("first", None), ("inpaint", preseq)):
+        torch.manual_seed(g["seed"] + 1)
+        init = torch.randn(B, 16, 128)
+        z, att = O.diffusion_reverse_forecast(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW),
+                                              O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init, n,
+                                              pre, guidance_scale=7.5)
+        ref = g[f"forecast_{tag}"]
+        assert rel_err(z, ref["z"]) < 1e-4, tag
+        assert max_rel(att[1], ref["att_last_alsn"]) < 1e-3, tag
+
+
+def test_generation_call_chain_matches_reference_test_diffusion_forward():
+    """golden["forward"]: outputs of the reference's own `Convofusion.test_diffusion_forward` (convofusion.py:817-1065:
+    7-branch batch assembly, TextAudioController / T5 projection / AudioConvEncoder / condition fuser forward code,
+    reverse loop, latent reshape, ConvoFusionVae.decode with ragged lengths) on a stand-in for the frozen T5 body
+    (tools/pin_reference_loops.py).  The oracle's restated chain must land on the same latents and joints."""
+    g = golden("ref_loops.pt")
+    f, B = g["forward"], g["B"]
+    enc, masks = oracle_batch(synthetic_clip(B, seed=f["clip_seed"], dyadic=True))
+    torch.manual_seed(g["seed"] + 2)
+    init = torch.randn(B, 16, 128)
+    z, _ = O.diffusion_reverse(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init,
+                               g["n_steps"], guidance_scale=7.5)
+    vin = O.latents_to_vae_input(z)
+    assert rel_err(vin.permute(1, 2, 0, 3), f["lat_t"]) < 1e-4
+    joints = O.vae_decode(state_dict(), vin, f["lengths"], prefix="vae.")
+    assert joints.shape == f["m_rst"].shape and max_rel(joints, f["m_rst"]) < 1e-3

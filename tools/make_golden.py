@@ -10,6 +10,8 @@ What is restated (cannot import: lightning/torchmetrics/kornia/nltk/diffusers mi
   the 7-branch batch assembly + reverse loops (oracle/convofusion_oracle.py, line-by-line from
   convofusion.py:391-549,909-973 and unbounded_synthesis.py:28-187) and the DDIM/DDPM schedulers.
   In the "sample_*" goldens the reference Denoiser/VAE run INSIDE those restated loops.
+  tools/pin_reference_loops.py closes that gap: it imports the reference's loop / test_diffusion_forward code itself
+  (stand-in modules for the absent packages) and shows the restated loops are bit-identical to it (ref_loops.pt).
 
 Usage: python tools/make_golden.py [--ref /root/reference]
 """
