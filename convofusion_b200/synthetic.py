@@ -65,3 +65,38 @@ def to_device(obj, device):
     if isinstance(obj, dict):
         return {k: to_device(v, device) for k, v in obj.items()}
     return obj
+
+
+def synthetic_text_features(text: str, text_len: int = 32):
+    """Stand-in for the frozen T5 body on an arbitrary string: (last hidden state [Lt,768], attention mask [Lt]),
+    a pure function of the string (seeded by its CRC32); the valid length grows with the word count."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(text.encode("utf-8")))
+    hid = torch.randn(text_len, 768, generator=g)
+    valid = min(text_len, 2 + len(text.split()))
+    return hid, (torch.arange(text_len) < valid).long()
+
+
+def synthetic_long_batch(n_streams: int, n_parts: int, seed: int = 1234) -> Dict[str, object]:
+    """A dataloader batch in the layout `process_samples` consumes (unbounded_synthesis.py:244-271): n_parts * 128
+    frames per stream, mel / active-passive bits / audio for the whole span, and word-level transcripts with
+    timestamps (`seg_*`: [((start, end), word), ...] or the unconditional prompt).  Stream 0's speaker is silent."""
+    g = torch.Generator().manual_seed(seed)
+    B, T = n_streams, n_parts * 128
+    words = lambda tag, b: [((0.5 * i, 0.5 * i + 0.45), f"{tag}{b}w{i}") for i in range(int(T / 25 / 0.5))]
+    return {
+        "length": [T] * B,
+        "motion_lsn": torch.randn(B, T, 189, generator=g),
+        "motion_spk": torch.randn(B, T, 189, generator=g),
+        "melspec_lsn": torch.rand(B, n_parts * 160 + 1, 80, generator=g) * 80.0 - 80.0,
+        "melspec_spk": torch.rand(B, n_parts * 160 + 1, 80, generator=g) * 80.0 - 80.0,
+        "active_passive_lsn": torch.randint(0, 2, (B, n_parts * 8), generator=g),
+        "lsn_id": [int(v) for v in torch.randint(1, 36, (B,), generator=g)],
+        "audio_lsn": torch.zeros(B, n_parts * 1000), "audio_spk": torch.zeros(B, n_parts * 1000),
+        "combined_audio": torch.zeros(B, n_parts * 1000),
+        "seg_lsn": [words("l", b) for b in range(B)],
+        "seg_spk": ["-" * 10 if b == 0 else words("s", b) for b in range(B)],
+        "text_lsn": [" ".join(w for _, w in words("l", b)) for b in range(B)],
+        "text_spk": [" ".join(w for _, w in words("s", b)) for b in range(B)],
+        "name": [f"stream{b}" for b in range(B)], "spk_name": ["spk"] * B, "lsn_name": ["lsn"] * B,
+    }

@@ -56,3 +56,24 @@ def frac_within(a, b, tol):
     fp32-reference outputs within tolerance at every DDIM step")."""
     a, b = a.double().cpu(), b.double().cpu()
     return float(((a - b).abs() <= tol * b.abs().max()).double().mean())
+
+
+def unbounded_windows(g_unbounded, n_streams):
+    """Featurised per-window conditioning for golden("ref_loops.pt")["unbounded"]: the long synthetic batch sliced the
+    way process_samples slices it (unbounded_synthesis.py:302-309: 161 mel frames / 8 active-passive bits per window at
+    half-window hops) plus the window texts the reference's process_text selected (stored in the golden), turned into
+    stand-in T5 features.  Returns (list of clip dicts, uncond_text, uncond_text_attn)."""
+    from convofusion_b200.synthetic import synthetic_long_batch, synthetic_text_features
+    long_batch = synthetic_long_batch(n_streams, g_unbounded["n_parts"], seed=g_unbounded["batch_seed"])
+    syn = synthetic_clip(n_streams, seed=g_unbounded["uncond_clip_seed"], dyadic=True)
+    uncond = (syn["uncond_text"], syn["uncond_text_attn"])
+    feat = lambda t: uncond if t == "-" * 10 else synthetic_text_features(t)
+    wins = []
+    for k, (tl, ts) in enumerate(zip(g_unbounded["texts_lsn"], g_unbounded["texts_spk"])):
+        fl, fs = [feat(t) for t in tl], [feat(t) for t in ts]
+        wins.append({"mel_lsn": long_batch["melspec_lsn"][:, int(k / 2 * 160):int((k / 2 + 1) * 160) + 1].contiguous(),
+                     "apb": long_batch["active_passive_lsn"][:, int(k / 2 * 8):int((k / 2 + 1) * 8)].contiguous(),
+                     "lsn_id": list(long_batch["lsn_id"]),
+                     "text_lsn": torch.stack([f[0] for f in fl]), "text_lsn_attn": torch.stack([f[1] for f in fl]),
+                     "text_spk": torch.stack([f[0] for f in fs]), "text_spk_attn": torch.stack([f[1] for f in fs])})
+    return wins, syn["uncond_text"], syn["uncond_text_attn"]

@@ -388,3 +388,20 @@ def test_generate_fp32_vs_reference_test_diffusion_forward():
           f"joints max-rel {max_rel(out['m_rst'].cpu(), f['m_rst']):.2e}")
     assert rel_err(lat, f["lat_t"]) < 2e-4
     assert max_rel(out["m_rst"].cpu(), f["m_rst"]) < 1e-3
+
+
+def test_synthesize_unbounded_fp32_vs_reference_process_samples():
+    """`ConvoFusionSampler.synthesize_unbounded` against the per-window joints written by the reference's own
+    `process_samples` (tests/golden/ref_loops.pt["unbounded"], tools/pin_reference_loops.py): 2 streams, 3 windows."""
+    from helpers import unbounded_windows
+    g = golden("ref_loops.pt")
+    u, B = g["unbounded"], g["B"]
+    s = gpu_sampler("fp32", g["n_steps"], cf.DDIMScheduler(clip_sample=True, **SCHED_KW))
+    wins, U, Ua = unbounded_windows(u, B)
+    torch.manual_seed(g["seed"] + 3)
+    inits = [torch.randn(B, 16, 128).to(DEV) for _ in wins]
+    outs = s.synthesize_unbounded([to_device(w, DEV) for w in wins], U.to(DEV), Ua.to(DEV), inits)
+    for k, o in enumerate(outs):
+        err = max_rel(o.cpu(), u["feats"][k])
+        print(f"window {k}: joints max-rel vs process_samples {err:.2e}")
+        assert err < 1e-3, k

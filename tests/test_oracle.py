@@ -206,3 +206,27 @@ def test_generation_call_chain_matches_reference_test_diffusion_forward():
     assert rel_err(vin.permute(1, 2, 0, 3), f["lat_t"]) < 1e-4
     joints = O.vae_decode(state_dict(), vin, f["lengths"], prefix="vae.")
     assert joints.shape == f["m_rst"].shape and max_rel(joints, f["m_rst"]) < 1e-3
+
+
+def test_window_driver_matches_reference_process_samples():
+    """golden["unbounded"]: per-window joints written by the reference's own `process_samples`
+    (unbounded_synthesis.py:244-512; 2 streams, 3 windows at 50 % overlap, text by timestamp, latent inpainting of the
+    previous window's last 8 tokens, root x/z stitching).  The oracle's driver with its own denoiser / VAE."""
+    from helpers import unbounded_windows
+    g = golden("ref_loops.pt")
+    u, B = g["unbounded"], g["B"]
+    wins, U, Ua = unbounded_windows(u, B)
+    torch.manual_seed(g["seed"] + 3)                       # one global-RNG draw of [B,16,128] per window, in order
+    preseq, prev = None, None
+    for k, clip in enumerate(wins):
+        clip = dict(clip)
+        clip["text_lsn_mask"], clip["text_spk_mask"] = ~clip["text_lsn_attn"].bool(), ~clip["text_spk_attn"].bool()
+        enc, masks = O.assemble_guidance_batch(state_dict(), clip, U, ~Ua.bool())
+        init = torch.randn(B, 16, 128)
+        z, _ = O.diffusion_reverse_forecast(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW),
+                                            O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init,
+                                            g["n_steps"], preseq, guidance_scale=7.5)
+        preseq = z[z.shape[0] // 2:].permute(1, 0, 2).clone()
+        feats = O.stitch_root(O.vae_decode(state_dict(), O.latents_to_vae_input(z), [128] * B, prefix="vae."), prev)
+        prev = feats[:, 64:, :]
+        assert max_rel(feats, u["feats"][k]) < 1e-3, k

@@ -234,6 +234,72 @@ assert d_lat < 2e-5 and d_j < 2e-5, "oracle's conditioning assembly / call chain
 assert rs["m_rst"].shape == (B, 128, 189) and rs["lat_m"].shape == rs["lat_t"].shape
 out["forward"] = {"m_rst": rs["m_rst"].clone(), "lat_t": rs["lat_t"].clone(), "lengths": lengths, "clip_seed": 3300}
 
+# ---- process_samples (unbounded_synthesis.py:244-512): serial windows at 50 % overlap over a long batch -- window
+# slicing of mel / active-passive bits, text by timestamp (process_text :189-241), 7-branch assembly per window,
+# diffusion_reverse_forecast with the previous window's last 8 latent tokens, decode, root x/z stitching.
+from convofusion_b200.synthetic import synthetic_long_batch, synthetic_text_features   # noqa: E402
+
+N_PARTS = 2
+long_batch = synthetic_long_batch(B, N_PARTS, seed=3400)
+uncond = (syn["uncond_text"], syn["uncond_text_attn"])
+encoder_calls = []
+
+
+def t5_body_any_string(texts, return_map=False):
+    encoder_calls.append(list(texts))
+    feats = [uncond if t == "-" * 10 else synthetic_text_features(t) for t in texts]
+    hid, attn = torch.stack([f[0] for f in feats]), torch.stack([f[1] for f in feats]).to(dtype=bool)
+    return hid, attn, ([t.split() for t in texts] if return_map else None)
+
+
+t5_self2 = types.SimpleNamespace(get_last_hidden_state=t5_body_any_string, projection=ref_proj)
+controller_self2 = types.SimpleNamespace(text_encoder=lambda texts, return_map=False: RefT5.forward(t5_self2, texts, return_map),
+                                         audio_encoder=ref_audio)
+saved = []
+model = stand_in_model(O.DDIMSchedulerOracle(clip_sample=True, **SCHED))
+model.condition, model.WEG_type, model.vae, model.condition_fuser = "text+audio", "no", ref_vae, ref_fuser
+model.device = torch.device("cpu")
+model.text_audio_encoder = lambda text, audio, person_type, return_textmap=False: RefController.forward(
+    controller_self2, text, audio, person_type, return_textmap)
+model.save_npy = lambda tup: saved.append(tup[1].clone())          # feats_rst of the window, after stitching
+with torch.no_grad():
+    torch.manual_seed(SEED + 3)
+    ref_script.process_samples(long_batch, model, None, None, None)
+n_windows = 2 * N_PARTS - 1
+assert len(saved) == n_windows and len(encoder_calls) == 2 * n_windows
+texts_spk = [encoder_calls[2 * k][3 * B:4 * B] for k in range(n_windows)]      # spk-only branch rows
+texts_lsn = [encoder_calls[2 * k + 1][B:2 * B] for k in range(n_windows)]      # text-only branch rows
+print("window texts (stream 1):", [t[1][:40] for t in texts_lsn])
+
+# the oracle's restatement of the same driver (what ConvoFusionSampler.synthesize_unbounded mirrors), reference modules inside
+with torch.no_grad():
+    torch.manual_seed(SEED + 3)
+    preseq, prev, feats_or = None, None, []
+    for k in range(n_windows):
+        mel = long_batch["melspec_lsn"][:, int(k / 2 * 160):int((k / 2 + 1) * 160) + 1]
+        apb = long_batch["active_passive_lsn"][:, int(k / 2 * 8):int((k / 2 + 1) * 8)]
+        fl = [uncond if t == "-" * 10 else synthetic_text_features(t) for t in texts_lsn[k]]
+        fs = [uncond if t == "-" * 10 else synthetic_text_features(t) for t in texts_spk[k]]
+        wclip = {"mel_lsn": mel, "apb": apb, "lsn_id": list(long_batch["lsn_id"]),
+                 "text_lsn": torch.stack([f[0] for f in fl]), "text_lsn_attn": torch.stack([f[1] for f in fl]),
+                 "text_spk": torch.stack([f[0] for f in fs]), "text_spk_attn": torch.stack([f[1] for f in fs])}
+        wclip["text_lsn_mask"], wclip["text_spk_mask"] = ~wclip["text_lsn_attn"].bool(), ~wclip["text_spk_attn"].bool()
+        enc, masks = O.assemble_guidance_batch(sd, wclip, syn["uncond_text"], ~syn["uncond_text_attn"].bool())
+        init = torch.randn(B, 16, 128)
+        zk, _ = O.diffusion_reverse_forecast(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED),
+                                             O.DDPMSchedulerOracle(clip_sample=True, **SCHED), enc, masks, init, N_STEPS,
+                                             preseq, guidance_scale=7.5)
+        preseq = zk[zk.shape[0] // 2:].permute(1, 0, 2).clone()
+        feats = O.stitch_root(ref_vae.decode(O.latents_to_vae_input(zk), [128] * B), prev)
+        prev = feats[:, 64:, :]
+        feats_or.append(feats)
+for k in range(n_windows):
+    dk = float((saved[k] - feats_or[k]).abs().max())
+    print(f"process_samples window {k}: oracle driver vs reference driver max |diff| {dk:.2e}")
+    assert dk == 0.0, "oracle's window driver differs from process_samples"
+out["unbounded"] = {"feats": torch.stack(saved), "texts_lsn": texts_lsn, "texts_spk": texts_spk, "n_parts": N_PARTS,
+                    "batch_seed": 3400, "uncond_clip_seed": 3300}
+
 path = ROOT / "tests" / "golden" / "ref_loops.pt"
 torch.save(out, path)
 print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")
