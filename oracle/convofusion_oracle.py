@@ -11,9 +11,14 @@ Pinning status
   the condition fuser are PINNED: tools/make_golden.py runs the unmodified reference
   modules from /root/reference on seeded weights/inputs and tests/test_oracle.py
   checks this restatement against those committed outputs (tests/golden/*.pt).
-* The 7-branch guidance loop (_diffusion_reverse / diffusion_reverse_forecast) cannot
-  be imported (lightning/torchmetrics/kornia/nltk missing), so it is restated line by
-  line and pinned only through the reference Denoiser inside it (golden "sample_*").
+* The 7-branch batch assembly, the two reverse loops (_diffusion_reverse /
+  diffusion_reverse_forecast), the generation call chain (test_diffusion_forward) and
+  the window driver (process_samples) are restated line by line AND PINNED to the
+  reference's own code: tools/pin_reference_loops.py imports those functions unmodified
+  (empty stand-in modules for the absent lightning / torchmetrics / kornia / nltk ...
+  packages they never call on this path, a stand-in for the frozen T5 body), runs them
+  with the reference Denoiser / VAE / encoders and asserts that the functions below
+  reproduce them bit for bit; tests/golden/ref_loops.pt + tests/test_oracle.py keep it so.
 * diffusers==0.14.0 (DDIM/DDPM schedulers; reference environment.yml:85) is absent
   from /root/reference and from this image: its published algorithm is restated
   below.  PARITY UNPINNED for the scheduler arithmetic.
