@@ -59,21 +59,20 @@ def frac_within(a, b, tol):
 
 
 def unbounded_windows(g_unbounded, n_streams):
-    """Featurised per-window conditioning for golden("ref_loops.pt")["unbounded"]: the long synthetic batch sliced the
-    way process_samples slices it (unbounded_synthesis.py:302-309: 161 mel frames / 8 active-passive bits per window at
-    half-window hops) plus the window texts the reference's process_text selected (stored in the golden), turned into
-    stand-in T5 features.  Returns (list of clip dicts, uncond_text, uncond_text_attn)."""
+    """Featurised per-window conditioning for golden("ref_loops.pt")["unbounded"]: the synthetic long batch cut by the
+    package's own window bookkeeping (convofusion_b200.windows.slice_windows), with the stand-in T5 features of
+    tools/pin_reference_loops.py.  Returns (list of clip dicts, uncond_text, uncond_text_attn)."""
     from convofusion_b200.synthetic import synthetic_long_batch, synthetic_text_features
+    from convofusion_b200.windows import slice_windows
     long_batch = synthetic_long_batch(n_streams, g_unbounded["n_parts"], seed=g_unbounded["batch_seed"])
     syn = synthetic_clip(n_streams, seed=g_unbounded["uncond_clip_seed"], dyadic=True)
     uncond = (syn["uncond_text"], syn["uncond_text_attn"])
-    feat = lambda t: uncond if t == "-" * 10 else synthetic_text_features(t)
-    wins = []
-    for k, (tl, ts) in enumerate(zip(g_unbounded["texts_lsn"], g_unbounded["texts_spk"])):
-        fl, fs = [feat(t) for t in tl], [feat(t) for t in ts]
-        wins.append({"mel_lsn": long_batch["melspec_lsn"][:, int(k / 2 * 160):int((k / 2 + 1) * 160) + 1].contiguous(),
-                     "apb": long_batch["active_passive_lsn"][:, int(k / 2 * 8):int((k / 2 + 1) * 8)].contiguous(),
-                     "lsn_id": list(long_batch["lsn_id"]),
-                     "text_lsn": torch.stack([f[0] for f in fl]), "text_lsn_attn": torch.stack([f[1] for f in fl]),
-                     "text_spk": torch.stack([f[0] for f in fs]), "text_spk_attn": torch.stack([f[1] for f in fs])})
+
+    def featurise(texts):
+        f = [uncond if t == "-" * 10 else synthetic_text_features(t) for t in texts]
+        return torch.stack([x[0] for x in f]), torch.stack([x[1] for x in f])
+
+    wins = slice_windows(long_batch, featurise)
+    for k, w in enumerate(wins):      # the texts the reference's process_text selected for the same windows
+        assert w["texts"]["lsn"] == g_unbounded["texts_lsn"][k] and w["texts"]["spk"] == g_unbounded["texts_spk"][k]
     return wins, syn["uncond_text"], syn["uncond_text_attn"]

@@ -197,6 +197,21 @@ def test_lane_context_and_pool_host_logic():
             pool.generate_many([{}])
 
 
+def test_window_bookkeeping_matches_reference_process_text():
+    """convofusion_b200.windows against strings produced by the reference's own process_text
+    (unbounded_synthesis.py:189-241) on random word timings, stored by tools/pin_reference_loops.py."""
+    from convofusion_b200.windows import slice_windows, window_spans, window_text
+    from helpers import golden, unbounded_windows
+    g = golden("ref_loops.pt")
+    assert len(g["window_text_cases"]) >= 50
+    for c in g["window_text_cases"]:
+        assert window_text(c["segments"], c["t0"], c["t1"]) == c["text"]
+    assert window_text("-" * 10, 0.0, 5.12) == "-" * 10
+    assert window_spans(256) == [(0.0, 5.12), (2.56, 7.68), (5.12, 10.24)] and len(window_spans(58 * 128)) == 115
+    wins, _, _ = unbounded_windows(g["unbounded"], g["B"])       # also asserts the window texts of the synthetic batch
+    assert [w["mel_lsn"].shape[1] for w in wins] == [161] * 3 and [w["apb"].shape[1] for w in wins] == [8] * 3
+
+
 def test_state_dict_layout_is_the_reference_layout():
     """Spot-check the key convention of SURVEY 8b (full strict-load against the reference modules is done by
     tools/make_golden.py, which needs /root/reference)."""

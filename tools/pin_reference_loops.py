@@ -297,6 +297,29 @@ for k in range(n_windows):
     dk = float((saved[k] - feats_or[k]).abs().max())
     print(f"process_samples window {k}: oracle driver vs reference driver max |diff| {dk:.2e}")
     assert dk == 0.0, "oracle's window driver differs from process_samples"
+# ---- the package's host-side window bookkeeping (convofusion_b200/windows.py) against process_text / process_samples
+from convofusion_b200.windows import slice_windows, window_spans, window_text           # noqa: E402
+import random                                                                           # noqa: E402
+
+wins = slice_windows(long_batch, lambda texts: t5_body_any_string(texts)[:2])
+assert len(wins) == n_windows
+for k, w in enumerate(wins):
+    assert w["texts"]["lsn"] == texts_lsn[k] and w["texts"]["spk"] == texts_spk[k], "window texts differ from process_samples"
+rng = random.Random(5)
+text_cases = []
+for case in range(60):                      # random word timings: gaps, overlaps, words longer than a window
+    t, segs = rng.uniform(0, 1.5), []
+    while t < 16.0:
+        dur = rng.choice([0.2, 0.4, 0.9, 2.5, 6.5])
+        segs.append(((round(t, 3), round(t + dur, 3)), f"w{len(segs)}"))
+        t += dur * rng.uniform(0.3, 1.4)
+    for (t0, t1) in window_spans(3 * 128):
+        ref_txt = ref_script.process_text([segs, "-" * 10], t0, t1)
+        assert [window_text(segs, t0, t1), window_text("-" * 10, t0, t1)] == ref_txt, "window_text differs from process_text"
+        if case < 12:
+            text_cases.append({"segments": segs, "t0": t0, "t1": t1, "text": ref_txt[0]})
+print(f"window_text == process_text on 60 random transcripts x 5 windows; slice_windows texts == process_samples")
+out["window_text_cases"] = text_cases
 out["unbounded"] = {"feats": torch.stack(saved), "texts_lsn": texts_lsn, "texts_spk": texts_spk, "n_parts": N_PARTS,
                     "batch_seed": 3400, "uncond_clip_seed": 3300}
 
