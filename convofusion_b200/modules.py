@@ -166,6 +166,13 @@ class _CudaModule(nn.Module):
                     self._lanes[k] = self._create(self._packed)
             return self._lanes[k]
 
+    def __getstate__(self):
+        # copy.deepcopy / pickle: device handles and packed weights belong to THIS object (a copied pointer would be
+        # destroyed twice); the copy re-packs lazily on its first call
+        state = self.__dict__.copy()
+        state["_handle"], state["_lanes"], state["_packed"], state["_pack_key"] = None, {}, None, None
+        return state
+
     def _apply(self, fn, *a, **k):   # .to() / .cuda() / .float()
         self._invalidate()
         return super()._apply(fn, *a, **k)

@@ -197,6 +197,19 @@ def test_lane_context_and_pool_host_logic():
             pool.generate_many([{}])
 
 
+def test_modules_copy_without_their_device_handles():
+    """deepcopy / pickle of a drop-in module must not duplicate the raw device handle (double free) nor trip over the
+    ctypes structs of the packed weights: the copy starts unpacked."""
+    import copy
+    import pickle
+    den = cf.default_denoiser("fp32")
+    den._handle, den._lanes, den._packed = ctypes.c_void_p(0), {1: ctypes.c_void_p(0)}, {"struct": _lib.DenoiserWeights()}
+    for clone in (copy.deepcopy(den), pickle.loads(pickle.dumps(den))):
+        assert clone._handle is None and clone._lanes == {} and clone._packed is None
+        assert torch.equal(clone.latent_embd.weight, den.latent_embd.weight)
+    den._handle, den._lanes, den._packed = None, {}, None
+
+
 def test_window_bookkeeping_matches_reference_process_text():
     """convofusion_b200.windows against strings produced by the reference's own process_text
     (unbounded_synthesis.py:189-241) on random word timings, stored by tools/pin_reference_loops.py."""
