@@ -175,6 +175,70 @@ def workload_config(args, batch, branches=6):
             "l2": "no flush: one pass streams 186 MB of bf16 weights 50x plus >150 MB of activations, above the 126 MB L2"}
 
 
+def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, clocks, parts, roof, single, h2d_bytes,
+                  d2h_bytes):
+    """The contract's JSON line from the measurements of run_ours (pure host arithmetic: unit-tested on the CPU)."""
+    W = args.windows
+    clips_total = B * world * args.steps
+    motion_s = MOTION_S_PER_CLIP if W == 0 else MOTION_S_PER_CLIP * (W + 1) / 2.0   # 50 % overlap between windows
+    value = clips_total * motion_s / (ms_dev * 1e-3)
+    e2e_value = clips_total * motion_s / (ms_e2e * 1e-3)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    # B200_PROFILING.md: burst peak for a kernel timed alone (the GEMM mix runs by itself for ~15 ms at full clocks),
+    # sustained peak for work timed inside a long step (the whole denoiser step)
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    peak_tf = peaks.get("bf16_tflops_sustained", peak_burst)
+    peak_src = ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) (of measured)" if peaks
+                else "fallback 1.59 PFLOP/s (of fallback)")
+    fl = denoiser_flops(B, n_branch)
+    ms_den = parts["loop_ms"] / args.ddim_steps          # `parts` times one sample() call = one window
+    line = {
+        "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+        "config": dict(workload_config(args, B), batches_in_flight=F,
+                       in_flight=("every step is one full pass over its own batch of %d clips; %d independent batches "
+                                  "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
+                                  % (B, F)) if F > 1 else "one batch at a time"),
+        "e2e": {"value": e2e_value, "unit": "motion-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "one_batch_in_flight": single,
+        "ms_per_denoiser_step": ms_den, "pass_split_ms": parts,
+        # whole pass (conditioning + decode included) / DDIM steps at the measured throughput: with several batches
+        # in flight this is below the single-batch latency figure above
+        "ms_per_denoiser_step_at_throughput": ms_dev / args.steps / args.ddim_steps / max(1, W),
+        "denoiser_step_tflops": {"executed": fl["executed"] / (ms_den * 1e-3) / 1e12,
+                                 "reference_equivalent": fl["as_written"] / (ms_den * 1e-3) / 1e12,
+                                 "executed_gflop_per_step": fl["executed"] / 1e9},
+    }
+    if roof:
+        tf, gemm_ms, n_gemm = roof
+        traffic = None
+        tfile = ROOT / "profiles" / "r01_traffic.json"
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text())
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)",
+                            "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
+                            "frac_of_sustained_peak": tf / peak_tf, "sustained_peak": peak_tf,
+                            "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
+                            "peak_source": peak_src, "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
+                            "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
+                            "whole_step_frac_at_throughput":
+                                fl["executed"] * args.ddim_steps * max(1, W) / (ms_dev / args.steps * 1e-3) / 1e12 / peak_tf}
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        r = cpu_reference_run(2, args.ddim_steps, 4, args.dyadic, cores)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
+                                "sample": f"2 clips (7x2 denoiser batch), 4 of {args.ddim_steps} DDIM steps timed and "
+                                          "extrapolated linearly + conditioning + decode; oracle port, torch fp32",
+                                "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
+    return line
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def gemm_roofline(torch, lib_mod, batch, n_branch, dev, iters=20):
     """Device time of the dominant kernel (gemm_tc_kernel) over exactly the GEMM shape mix of one denoiser
@@ -407,61 +471,9 @@ def run_ours(args):
             tf, gemm_ms, n_gemm = gemm_roofline(torch, _lib, B, n_branch, dev)
             roof = (tf, gemm_ms, n_gemm)
 
-    clips_total = B * world * args.steps
-    motion_s = MOTION_S_PER_CLIP if W == 0 else MOTION_S_PER_CLIP * (W + 1) / 2.0   # 50 % overlap between windows
-    value = clips_total * motion_s / (ms_dev * 1e-3)
-    e2e_value = clips_total * motion_s / (ms_e2e * 1e-3)
     if rank == 0:
-        peaks = {}
-        pk = ROOT / "MEASURED_PEAKS.json"
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-        mem_tokens = 234
-        fl = denoiser_flops(B, n_branch)
-        ms_den = parts["loop_ms"] / args.ddim_steps
-        line = {
-            "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": dict(workload_config(args, B), batches_in_flight=F,
-                           in_flight=("every step is one full pass over its own batch of %d clips; %d independent batches "
-                                      "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
-                                      % (B, F)) if F > 1 else "one batch at a time"),
-            "e2e": {"value": e2e_value, "unit": "motion-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "one_batch_in_flight": single,
-            "ms_per_denoiser_step": ms_den, "pass_split_ms": parts,
-            # whole pass (conditioning + decode included) / DDIM steps at the measured throughput: with several batches
-            # in flight this is below the single-batch latency figure above
-            "ms_per_denoiser_step_at_throughput": ms_dev / args.steps / args.ddim_steps,
-            "denoiser_step_tflops": {"executed": fl["executed"] / (ms_den * 1e-3) / 1e12,
-                                     "reference_equivalent": fl["as_written"] / (ms_den * 1e-3) / 1e12,
-                                     "executed_gflop_per_step": fl["executed"] / 1e9},
-        }
-        if roof:
-            tf, gemm_ms, n_gemm = roof
-            traffic = None
-            tfile = ROOT / "profiles" / "r01_traffic.json"
-            if tfile.exists():
-                traffic = json.loads(tfile.read_text())
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)", "achieved": tf, "peak": peak_tf,
-                                "unit": "TFLOP/s", "frac": tf / peak_tf,
-                                "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
-                                "peak_source": peak_src,
-                                "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
-                                "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
-                                "whole_step_frac_at_throughput":
-                                    fl["executed"] * args.ddim_steps / (ms_dev / args.steps * 1e-3) / 1e12 / peak_tf}
-        if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            r = cpu_reference_run(2, args.ddim_steps, 4, args.dyadic, cores)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 clips (7x2 denoiser batch), 4 of {args.ddim_steps} DDIM steps timed and "
-                                              "extrapolated linearly + conditioning + decode; oracle port, torch fp32",
-                                    "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
+        line = assemble_line(args, world=world, B=B, F=F, n_branch=n_branch, ms_dev=ms_dev, ms_e2e=ms_e2e, launches=launches,
+                             clocks=clocks, parts=parts, roof=roof, single=single, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
