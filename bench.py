@@ -379,6 +379,11 @@ def run_ours(args):
 
     F = max(1, args.in_flight)
     single = None
+    if F > 1 and any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_NSIGHT_INJECTION_PORT_BASE")):
+        # Nsight Compute serialises every kernel anyway and its injection library did not survive the lane threads'
+        # concurrent graph captures (profiles/README.md): profile one lane
+        print("bench.py: profiler injection detected, running with one batch in flight", file=sys.stderr)
+        F = 1
     if W > 0:
         F = 1      # windows of one stream are serial (preseq + root hand-off)
     if F > 1:
