@@ -49,8 +49,7 @@ def test_optional_paths_agree_with_default(tmp_path):
                       ("ln_separate", {"CFB_FUSE_LN": "0"}),
                       ("staged_epilogue", {"CFB_TC_TMA_EPI": "0"}), ("occ3", {"CFB_TC_OCC3": "1"}),
                       ("softmax_strided", {"CFB_SOFTMAX_STRIDED": "1"}), ("mha_simt", {"CFB_MHA_SIMT": "1"}),
-                      ("serial", {"CFB_CHAINS": "1", "CFB_PDL": "0", "CFB_OVERLAP": "0"}),
-                      ("cta_pair", {"CFB_TC_2CTA": "1", "CFB_CHAINS": "1", "CFB_OVERLAP": "0"})):
+                      ("serial", {"CFB_CHAINS": "1", "CFB_PDL": "0", "CFB_OVERLAP": "0"})):
         got = run(tmp_path, name, env)
         err = float((got[0] - base[0]).abs().max()) / scale
         l2 = float((got[0] - base[0]).norm() / base[0].norm())
@@ -61,9 +60,6 @@ def test_optional_paths_agree_with_default(tmp_path):
         # adds the conditional streams' contribution to the residual BEFORE the shared one (different fp32 order)
         if name in ("cluster42", "cluster21", "serial", "ln_separate", "staged_epilogue", "occ3", "softmax_strided"):
             assert torch.equal(got, base), name
-        elif name == "cta_pair":
-            # cta_group::2 M=256 MMAs: same bf16 products, fp32 accumulation inside the tensor core in its own order
-            assert l2 < 1e-2, name
         elif name == "mha_simt":
             # CUDA-core attention keeps the probabilities in fp32, the tensor-core kernel rounds them to bf16 before
             # P.V: one more bf16 rounding site per attention, amplified like every other one
@@ -71,13 +67,3 @@ def test_optional_paths_agree_with_default(tmp_path):
         else:
             assert l2 < 6e-2, name   # same scale as the bf16-vs-fp32 first-step error (test_gpu_parity)
 
-
-def test_cta_pair_gemm_kernel():
-    """tcgen05.mma.cta_group::2 GEMM (256x256 tile per CTA pair, opt-in CFB_TC_2CTA=1) against float64 on shapes with
-    partial row tiles, an odd number of 128-row tiles, K = 64..1024 and all three epilogues (tools/pair_check.py)."""
-    e = dict(os.environ)
-    e["CFB_TC_2CTA"] = "1"
-    r = subprocess.run([sys.executable, str(ROOT / "tools" / "pair_check.py"), "check"], env=e, capture_output=True,
-                       text=True, timeout=300)
-    print(r.stdout)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
