@@ -127,6 +127,7 @@ def cpu_reference_run(n_clips, ddim_steps, timed_denoiser_steps, dyadic, threads
         den = lambda x, t: O.denoiser_forward(sd, x, t, enc, masks, prefix="denoiser.")
         den(torch.cat([lat] * 7), sch.timesteps[0])          # warm-up
         t0 = time.perf_counter()
+        timed_denoiser_steps = min(timed_denoiser_steps, ddim_steps)
         for t in sch.timesteps[:timed_denoiser_steps]:
             eps, _ = den(torch.cat([lat] * 7), t)
             lat = sch.step(O.guidance_combine(eps, 7.5), t, lat, eta=0.0).prev_sample
@@ -144,7 +145,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_clips, timed = 4, 6
+    n_clips, timed = 8, 8          # bounded sample: ~5-10 s of host work per step
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_reference_run(n_clips, args.ddim_steps, timed, args.dyadic, cores)
@@ -231,9 +232,9 @@ def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, cloc
                                 fl["executed"] * args.ddim_steps * max(1, W) / (ms_dev / args.steps * 1e-3) / 1e12 / peak_tf}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        r = cpu_reference_run(2, args.ddim_steps, 4, args.dyadic, cores)
+        r = cpu_reference_run(8, args.ddim_steps, 8, args.dyadic, cores)
         line["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
-                                "sample": f"2 clips (7x2 denoiser batch), 4 of {args.ddim_steps} DDIM steps timed and "
+                                "sample": f"8 of the {B} clips (7x8 denoiser batch), 8 of {args.ddim_steps} DDIM steps timed and "
                                           "extrapolated linearly + conditioning + decode; oracle port, torch fp32",
                                 "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
     return line
