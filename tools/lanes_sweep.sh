@@ -11,6 +11,11 @@ run() {  # name chains [bench args...]
 for b in 8 16 32 64 128 256; do run b${b}_c6_f1 6 --batch $b --in-flight 1; done
 for c in 1 2 3 4 6; do for f in 2 3; do run b64_c${c}_f${f} $c --in-flight $f; done; done
 run b8_c1_f2 1 --batch 8 --in-flight 2
+# GEMM execution options that were only ever measured with one batch in flight (latency-bound), now with two lanes
+CFB_TC_OCC3=1 run b64_c3_f2_occ3 3 --in-flight 2
+CFB_TC_CLUSTER=21 run b64_c3_f2_mc21 3 --in-flight 2
+CFB_TC_CLUSTER=42 run b64_c3_f2_mc42 3 --in-flight 2
+CFB_TC_2CTA=1 CFB_TC_2CTA_MIN_ROWS=4096 run b64_c1_f1_pair4096 1 --in-flight 1
 python - <<'PY'
 import glob, json
 print(f"{'run':<16} {'motion-s/s':>10} {'e2e':>8} {'ms/pass':>8} {'ms/den.step (1 lane)':>21} {'launches':>9}")
