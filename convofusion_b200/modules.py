@@ -266,6 +266,9 @@ class Denoiser(_CudaModule):
         packed = pack_denoiser(self.state_dict(), "", self.num_layers, self.num_heads, self.n_tokens,
                                _precision_id(self.precision), dev)
         with torch.cuda.device(dev):
+            # the casts / copies above ran on the caller's current stream; other streams (SamplerPool lanes) read the
+            # packed weights too, so they are made globally visible before the handle is published (one-time cost)
+            torch.cuda.current_stream(dev).synchronize()
             h = self._create(packed)
         self._handle, self._packed = h, packed
         return self
@@ -453,6 +456,9 @@ class ConvoFusionVae(_CudaModule):
         packed = pack_vae(self.state_dict(), "", self.num_layers, self.num_heads, self.ff_size,
                           _precision_id(self.precision), dev)
         with torch.cuda.device(dev):
+            # the casts / copies above ran on the caller's current stream; other streams (SamplerPool lanes) read the
+            # packed weights too, so they are made globally visible before the handle is published (one-time cost)
+            torch.cuda.current_stream(dev).synchronize()
             h = self._create(packed)
         self._handle, self._packed = h, packed
         return self
