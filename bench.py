@@ -321,6 +321,7 @@ def run_ours(args):
     lengths = [128] * B
     gathered = [torch.empty(B, 128, 189, device=dev) for _ in range(world)] if world > 1 else None
     stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()      # the inputs above were copied on the default stream; every pass runs on other streams
 
     W = args.windows
     inits = [dinit] * W
