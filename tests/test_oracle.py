@@ -230,3 +230,38 @@ def test_window_driver_matches_reference_process_samples():
         feats = O.stitch_root(O.vae_decode(state_dict(), O.latents_to_vae_input(z), [128] * B, prefix="vae."), prev)
         prev = feats[:, 64:, :]
         assert max_rel(feats, u["feats"][k]) < 1e-3, k
+
+
+def test_scheduler_identities_of_the_published_algorithms():
+    """diffusers 0.14.0 is absent (parity unpinned), so the restated schedulers are anchored on identities of the
+    published algorithms instead.  DDIM (Song et al. 2021, eq. 12, sigma = 0): stepping x_t = sqrt(abar_t) x0 +
+    sqrt(1 - abar_t) eps with the true eps lands exactly on the same (x0, eps) trajectory at the previous timestep.
+    DDPM (Ho et al. 2020, eq. 6-7): the step mean is the posterior mean q(x_{t-1} | x_t, x0), written here through
+    per-interval alphas, and the added noise has the posterior variance beta~_t."""
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.rand(2, 16, 128, generator=g, dtype=torch.float64) * 1.6 - 0.8
+    eps = torch.randn(2, 16, 128, generator=g, dtype=torch.float64)
+    for kw in (dict(clip_sample=True), dict(clip_sample=False, set_alpha_to_one=False, steps_offset=1)):
+        d = O.DDIMSchedulerOracle(**SCHED_KW, **kw)
+        d.set_timesteps(50)
+        ab = d.alphas_cumprod.double()
+        for t in (int(d.timesteps[0]), int(d.timesteps[25]), int(d.timesteps[-1])):
+            prev = t - 20
+            a_p = ab[prev] if prev >= 0 else d.final_alpha_cumprod.double()
+            xt = ab[t].sqrt() * x0 + (1 - ab[t]).sqrt() * eps
+            out = d.step(eps.float(), t, xt.float(), eta=0.0).prev_sample
+            assert torch.allclose(out.double(), a_p.sqrt() * x0 + (1 - a_p).sqrt() * eps, atol=5e-6), (kw, t)
+    p = O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW)
+    p.set_timesteps(50)
+    ab = p.alphas_cumprod.double()
+    for t in (980, 500, 20):
+        prev = t - 20
+        xt = ab[t].sqrt() * x0 + (1 - ab[t]).sqrt() * eps
+        alpha_int = ab[t] / ab[prev]                               # product of the alphas over the skipped interval
+        mean = (ab[prev].sqrt() * (1 - alpha_int) / (1 - ab[t])) * x0 + (alpha_int.sqrt() * (1 - ab[prev]) / (1 - ab[t])) * xt
+        var = (1 - ab[prev]) / (1 - ab[t]) * (1 - alpha_int)
+        z = torch.randn(2, 16, 128, generator=g)
+        out0 = p.step(eps.float(), t, xt.float(), variance_noise=torch.zeros_like(z)).prev_sample
+        out1 = p.step(eps.float(), t, xt.float(), variance_noise=z).prev_sample
+        assert torch.allclose(out0.double(), mean, atol=5e-6), t
+        assert torch.allclose((out1 - out0).double(), var.sqrt() * z.double(), atol=5e-6), t
