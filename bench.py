@@ -61,7 +61,7 @@ def denoiser_flops(n_clips, n_branch, mem_len=(32, 161, 32, 8, 1), d=512, ff=102
     k_tot = sum((m + 63) // 64 * 64 for m in mem_len)
     M = sum(mem_len)
     full = 2.0 * R * (3 * d * d + d * d + d * d + n_tot * d + d * k_tot + d * d + ff * d + d * ff)
-    n_cond_rows = min(n_branch - 1, len(mem_len)) * n_clips * ntok          # branches 1..5: one conditional stream each
+    n_cond_rows = (n_branch - 1) * n_clips * ntok                           # every branch but the first: one conditional stream
     cond = 2.0 * n_cond_rows * 2 * d * d
     self_att = 2.0 * 2 * n_clips * n_branch * ntok * ntok * d
     pair_att = 2.0 * 2 * n_clips * ntok * M * d                             # each clip's own memory, once per stream
@@ -166,7 +166,9 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "motion-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, batch, branches=6):
+def workload_config(args, batch, branches=None):
+    if branches is None:
+        branches = 6 if args.dyadic else 5
     return {"workload": ("dyadic DnD-shaped" if args.dyadic else "monadic BEAT-shaped") +
             f" config_cf_beatdnd random-init, batch {batch} clips/GPU, {args.ddim_steps} DDIM steps, 7-branch guidance 7.5, "
             "VAE decode to 128x189 joints (BASELINE.json configs[%d])" % (2 if args.dyadic else 1),
@@ -303,7 +305,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, n_branch = args.batch, 6
+    # guidance branches evaluated: the weight-0 full-cond branch never; the speaker-only branch only for dyadic clips
+    # (monadic: it repeats the unconditional branch exactly, convofusion_b200.conditioning.guidance_branches)
+    B, n_branch = args.batch, (6 if args.dyadic else 5)
 
     sampler = randomize_(cf.ConvoFusionSampler(precision=args.precision, num_inference_timesteps=args.ddim_steps), 1234)
     sampler = sampler.to(dev).eval()
@@ -337,7 +341,7 @@ def run_ours(args):
 
     def pass_e2e():
         c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        c["lsn_id"] = clip["lsn_id"]
+        c["lsn_id"], c["spk_is_uncond"] = clip["lsn_id"], clip["spk_is_uncond"]
         x = host_init.to(dev, non_blocking=True)
         if W > 0:
             out = sampler.synthesize_unbounded([c] * W, Ud, Uad, [x] * W, use_graph=not args.no_graph)[-1]
@@ -404,7 +408,7 @@ def run_ours(args):
 
         def lane_e2e(_i, k):
             c = {kk: v.to(dev, non_blocking=True) for kk, v in host.items()}
-            c["lsn_id"] = clip["lsn_id"]
+            c["lsn_id"], c["spk_is_uncond"] = clip["lsn_id"], clip["spk_is_uncond"]
             x = host_init.to(dev, non_blocking=True)
             out = sampler.generate(c, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
             j = turn[k] & 1

@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+ABI_VERSION = 2
 N_STREAMS = 5
 N_BRANCH = 7
 F32, BF16 = 0, 1
@@ -38,7 +39,7 @@ class DenoiserWeights(C.Structure):
 
 class Memory(C.Structure):
     _fields_ = [("cond", C.c_void_p * N_STREAMS), ("mask", C.c_void_p * N_STREAMS), ("slot", C.c_void_p * N_STREAMS),
-                ("n_slots", C.c_int32 * N_STREAMS), ("len", C.c_int32 * N_STREAMS)]
+                ("slot_host", C.c_void_p * N_STREAMS), ("n_slots", C.c_int32 * N_STREAMS), ("len", C.c_int32 * N_STREAMS)]
 
 
 class Schedule(C.Structure):
@@ -81,12 +82,13 @@ PROTOTYPES = {
     "cfb_abi_version": (C.c_int, []),
     "cfb_last_error": (C.c_char_p, []),
     "cfb_set_gemm_backend": (C.c_int, [_I]),
+    "cfb_set_shared_plan": (C.c_int, [_I]),
     "cfb_launch_count": (C.c_ulonglong, []),
     "cfb_denoiser_create": (C.c_int, [C.POINTER(DenoiserWeights), C.POINTER(_P)]),
     "cfb_denoiser_destroy": (None, [_P]),
     "cfb_denoiser_set_chains": (C.c_int, [_P, C.c_int]),
     "cfb_denoiser_forward": (C.c_int, [_P, _P, _I, _LL, C.POINTER(Memory), _P, C.POINTER(_P), _P]),
-    "cfb_sample": (C.c_int, [_P, C.POINTER(Schedule), C.POINTER(Memory), _I, _I, _P, _P, _P, _I, _P, C.POINTER(_P),
+    "cfb_sample": (C.c_int, [_P, C.POINTER(Schedule), C.POINTER(Memory), _I, _I, _I, _P, _P, _P, _I, _P, C.POINTER(_P),
                              _I, _P]),
     "cfb_guidance_sched_step": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "cfb_vae_create": (C.c_int, [C.POINTER(VaeWeights), C.POINTER(_P)]),
@@ -118,7 +120,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.cfb_abi_version() != 1:
+        if handle.cfb_abi_version() != ABI_VERSION:
             raise CfbError("libconvofusion_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -14,6 +14,7 @@ conditioning or the batch-wide unconditional constant -- so memory holds 1 + B s
 """
 from __future__ import annotations
 
+import functools
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -128,17 +129,46 @@ def uncond_mel(n_frames: int, n_mel: int, device) -> Tensor:
     return m
 
 
-def guidance_slots(n_clips: int, n_branch: int, device) -> List[Tensor]:
-    """slot[x][g*B + b]: 0 = unconditional constant, 1 + b = clip b's own conditioning."""
-    b = torch.arange(n_clips, device=device, dtype=torch.int32)
+def guidance_branches(return_attention: bool = False, spk_is_uncond: bool = False) -> List[int]:
+    """Branches of convofusion.py:910 that have to be evaluated.  Branch 6 (full-cond) has guidance weight 0
+    (convofusion.py:539) and only matters for its attention maps; branch 3 (speaker-only) equals branch 0 when the
+    speaker stream of every clip IS the unconditional prompt (monadic BEAT clips, dataset.py:185-199), so its term
+    guidance_scale * (e_3 - e_0) is an exact zero."""
+    br = [0, 1, 2] + ([] if spk_is_uncond else [3]) + [4, 5]
+    return br + [6] if return_attention else br
+
+
+@functools.lru_cache(maxsize=64)
+def _slots_host(n_clips: int, branches: Tuple[int, ...]) -> Tuple[Tensor, ...]:
+    b = torch.arange(n_clips, dtype=torch.int32)
     out = []
     for x in range(5):
-        rows = []
-        for g in range(n_branch):
-            cond = g == 6 or BRANCH_STREAM.get(g) == x
-            rows.append(b + 1 if cond else torch.zeros_like(b))
+        rows = [b + 1 if (g == 6 or BRANCH_STREAM.get(g) == x) else torch.zeros_like(b) for g in branches]
         out.append(torch.cat(rows))
-    return out
+    return tuple(out)
+
+
+@functools.lru_cache(maxsize=64)
+def _slots_device(n_clips: int, branches: Tuple[int, ...], device: str) -> Tuple[Tensor, ...]:
+    return tuple(t.to(device) for t in _slots_host(n_clips, branches))
+
+
+def guidance_slots(n_clips: int, branches, device) -> List[Tensor]:
+    """slot[x][i*B + b] for the i-th evaluated branch g = branches[i]: 0 = unconditional constant, 1 + b = clip b's
+    own conditioning.  `branches` is a list of branch ids or an int n (= branches 0..n-1).  The
+    tables are a pure function of (B, branches): built once and cached per device (read-only: do not modify)."""
+    br = tuple(range(branches)) if isinstance(branches, int) else tuple(int(g) for g in branches)
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        return list(_slots_host(n_clips, br))
+    return list(_slots_device(n_clips, br, str(dev)))
+
+
+def guidance_slots_host(n_clips: int, branches) -> List[Tensor]:
+    """Host copy of `guidance_slots` (int32, CPU): lets the library derive its execution plan without reading the
+    device tables back (cfb_memory.slot_host)."""
+    br = tuple(range(branches)) if isinstance(branches, int) else tuple(int(g) for g in branches)
+    return list(_slots_host(n_clips, br))
 
 
 def guidance_memory(controller: TextAudioController, fuser: TextAudioMotionFuser, clip: Dict[str, Tensor],

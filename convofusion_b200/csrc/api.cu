@@ -40,17 +40,6 @@ extern "C" {
 // Debug only (not part of include/convofusion_b200.h): phase timestamps of the last traced tcgen05 GEMM CTA.
 int cfb_debug_tc_trace(unsigned long long* out16) { return cfb::tc_trace_read(out16); }
 
-// Debug only: out[M,512] (float) += A[M,K] W[512,K]^T + bias, then ln_out = LN(out) * g + b through the GEMM's
-// LayerNorm tail (counters: 2 ints per 128-row block, zeroed by the caller once).
-int cfb_debug_linear_ln_tail(const void* A, const void* W, const float* bias, float* out, void* ln_out, const float* g,
-                             const float* b, int* counters, int M, int K, cfb_stream stream) {
-  CFB_TRY(ensure_device());
-  Epilogue ep{};
-  ep.bias = bias; ep.bias_period = 1; ep.accumulate = 1; ep.out = out; ep.ldo = 512; ep.replicate = 1;
-  ep.ln_out = (bf16*)ln_out; ep.ln_g = g; ep.ln_b = b; ep.ln_counters = counters; ep.ln_tail = 1;
-  return gemm_tc((const bf16*)A, K, (const bf16*)W, K, M, 512, K, ep, (cudaStream_t)stream);
-}
-
 int cfb_abi_version(void) { return CFB_ABI_VERSION; }
 const char* cfb_last_error(void) { return g_err; }
 unsigned long long cfb_launch_count(void) { return g_launches.load(); }
@@ -124,7 +113,7 @@ int cfb_guidance_sched_step(const float* eps, float* x, const float* noise, cons
   CFB_CHECK(eps && x && coef_dev, "cfb_guidance_sched_step: null argument");
   StepArgs a{};
   a.eps = eps; a.x = x; a.noise = noise; a.coef = coef_dev; a.n_branch = n_branch; a.n_clips = n_clips;
-  a.n_per_clip = n_per_clip; a.n_steps = 1; a.kind = kind; a.clip_sample = clip_sample; a.guidance_scale = guidance_scale;
+  a.full_last = n_branch == CFB_N_BRANCH; a.n_per_clip = n_per_clip; a.n_steps = 1; a.kind = kind; a.clip_sample = clip_sample; a.guidance_scale = guidance_scale;
   return guidance_sched_step(a, (cudaStream_t)stream);
 }
 

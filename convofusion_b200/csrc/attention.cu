@@ -661,7 +661,8 @@ __global__ void __launch_bounds__(32) self_attn16_kernel(const T* __restrict__ q
 constexpr int SA_SMEM = 3 * SA_L * SA_PITCH * (int)sizeof(float);   // 25,344 B per one-warp block: fits beside two GEMM CTAs
 
 // One warp per query row; see SharedAttnArgs.
-__global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+template <typename TP>
+__global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __restrict__ S, TP* __restrict__ P,
                                                              SharedAttnArgs a, int rows, int n_tokens) {
   pdl_sync();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -669,10 +670,10 @@ __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __rest
   const int bs = r / n_tokens + a.bs_offset;
 #pragma unroll
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
-    bf16* prow = P + (size_t)r * a.ld_p + a.p_off[x];
+    TP* prow = P + (size_t)r * a.ld_p + a.p_off[x];
     const int M = a.len[x], kp = a.kp[x];
     if (a.slot[x][bs] != 0) {
-      for (int j = lane; j < kp; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+      for (int j = lane; j < kp; j += 32) prow[j] = from_f32<TP>(0.f);
       continue;
     }
     const float* srow = S + (size_t)r * a.ld_s + a.s_off[x];
@@ -696,7 +697,7 @@ __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __rest
         const float s = (msk && msk[j]) ? -INFINITY : srow[j];
         p = expf(s - mx) * inv;
       }
-      prow[j] = __float2bfloat16_rn(p);
+      prow[j] = from_f32<TP>(p);
     }
   }
 }
@@ -708,7 +709,8 @@ __global__ void __launch_bounds__(256) softmax_shared_kernel(const float* __rest
 // kernel above walks each segment three times with dependent loads (max, sum, write): ~15 L2 round trips per row,
 // 12-15 us per launch for about a microsecond of work.
 constexpr int SMX_MAXJ = 8;
-__global__ void __launch_bounds__(256) softmax_shared_reg_kernel(const float* __restrict__ S, bf16* __restrict__ P,
+template <typename TP>
+__global__ void __launch_bounds__(256) softmax_shared_reg_kernel(const float* __restrict__ S, TP* __restrict__ P,
                                                                  SharedAttnArgs a, int rows, int n_tokens) {
   pdl_sync();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -717,7 +719,7 @@ __global__ void __launch_bounds__(256) softmax_shared_reg_kernel(const float* __
   const int bs = r / n_tokens + a.bs_offset;
   const int M = a.len[x], kp = a.kp[x];
   const float* srow = S + (size_t)r * a.ld_s + a.s_off[x];
-  bf16* prow = P + (size_t)r * a.ld_p + a.p_off[x];
+  TP* prow = P + (size_t)r * a.ld_p + a.p_off[x];
   const uint8_t* msk = a.mask[x];
   const int slot = a.slot[x][bs];
   float s[SMX_MAXJ];
@@ -745,9 +747,9 @@ __global__ void __launch_bounds__(256) softmax_shared_reg_kernel(const float* __
 #pragma unroll
   for (int i = 0; i < SMX_MAXJ; ++i) {
     const int j = lane + 32 * i;
-    if (j < kp) prow[j] = __float2bfloat16_rn(j < M ? s[i] * inv : 0.f);
+    if (j < kp) prow[j] = from_f32<TP>(j < M ? s[i] * inv : 0.f);
   }
-  for (int j = 32 * SMX_MAXJ + lane; j < kp; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+  for (int j = 32 * SMX_MAXJ + lane; j < kp; j += 32) prow[j] = from_f32<TP>(0.f);
 }
 
 // z0[l][s_off[x] + j] = a_{x,l} . xhat_{x,slot 0, j}: the key-dependent bias of the shared-slot scores.
@@ -756,7 +758,8 @@ struct Z0Args {
   int row_base[CFB_N_STREAMS], len[CFB_N_STREAMS], s_off[CFB_N_STREAMS];
   int tok_base[CFB_N_STREAMS + 1];    // prefix sum of len
 };
-__global__ void __launch_bounds__(256) z0_kernel(const bf16* __restrict__ mem_hat, float* __restrict__ z0, Z0Args a,
+template <typename T>
+__global__ void __launch_bounds__(256) z0_kernel(const T* __restrict__ mem_hat, float* __restrict__ z0, Z0Args a,
                                                  int n_layers, int n_tot) {
   pdl_sync();
   const int t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(256) z0_kernel(const bf16* __restrict__ mem_ha
   for (int i = 1; i < CFB_N_STREAMS; ++i) x += (t >= a.tok_base[i]);
   const int j = t - a.tok_base[x];
   float kv[16];
-  load_row16<bf16>(mem_hat + ((size_t)a.row_base[x] + j) * CROSS_D, lane, kv);
+  load_row16<T>(mem_hat + ((size_t)a.row_base[x] + j) * CROSS_D, lane, kv);
   for (int l = 0; l < n_layers; ++l) {
     const float* av = a.a_zx[x] + (size_t)l * CROSS_D;
     float s = 0.f;
@@ -783,7 +786,8 @@ __global__ void __launch_bounds__(256) z0_kernel(const bf16* __restrict__ mem_ha
 
 }  // namespace
 
-int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
+template <typename T>
+int shared_key_bias(const T* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
                     const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
                     int n_layers, int n_tot, cudaStream_t st) {
   Z0Args a;
@@ -793,32 +797,39 @@ int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_
     a.tok_base[x] = tok; tok += len[x];
   }
   a.tok_base[CFB_N_STREAMS] = tok;
-  launch_k(z0_kernel, ceil_div(tok, 8), 256, 0, st, mem_hat, z0, a, n_layers, n_tot);
+  launch_k(z0_kernel<T>, ceil_div(tok, 8), 256, 0, st, mem_hat, z0, a, n_layers, n_tot);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
+template int shared_key_bias<bf16>(const bf16*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t);
+template int shared_key_bias<float>(const float*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t);
 
-int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
+template <typename TP>
+int softmax_shared(const float* S, TP* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
   const int rows = n_batch * n_tokens;
   if (rows <= 0 || debug_skip(4)) return CFB_OK;
   static const bool strided = getenv("CFB_SOFTMAX_STRIDED") && atoi(getenv("CFB_SOFTMAX_STRIDED"));
   bool fits = true;
   for (int x = 0; x < CFB_N_STREAMS; ++x) fits = fits && a.len[x] <= 32 * SMX_MAXJ;
-  if (fits && !strided) launch_k(softmax_shared_reg_kernel, ceil_div(rows * CFB_N_STREAMS, 8), 256, 0, st, S, P, a, rows, n_tokens);
-  else launch_k(softmax_shared_kernel, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
+  if (fits && !strided) launch_k(softmax_shared_reg_kernel<TP>, ceil_div(rows * CFB_N_STREAMS, 8), 256, 0, st, S, P, a, rows, n_tokens);
+  else launch_k(softmax_shared_kernel<TP>, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
+template int softmax_shared<bf16>(const float*, bf16*, const SharedAttnArgs&, int, int, cudaStream_t);
+template int softmax_shared<float>(const float*, float*, const SharedAttnArgs&, int, int, cudaStream_t);
 
 namespace {
 }  // namespace
 
-// Opt in to large dynamic shared memory once, outside any stream capture.
+// Opt in to large dynamic shared memory once PER DEVICE (the attribute is per device), outside any stream capture.
 int init_attention_kernels() {
-  static bool done = false;
+  static unsigned long long done_mask = 0;
   static std::mutex mu;     // handles may be created from several host threads (SamplerPool lanes)
   std::lock_guard<std::mutex> lock(mu);
-  if (done) return CFB_OK;
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && ((done_mask >> dev) & 1ull)) return CFB_OK;
   if (const char* e = getenv("CFB_MHA_SIMT")) g_mha_simt = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
@@ -827,7 +838,7 @@ int init_attention_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
-  done = true;
+  if (dev < 64) done_mask |= 1ull << dev;
   return CFB_OK;
 }
 

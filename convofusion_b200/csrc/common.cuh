@@ -147,16 +147,6 @@ struct Epilogue {
   int ldo;
   int replicate;       // write `replicate` copies, copy c at out + c * rep_stride elements
   long long rep_stride;
-  // Fused LayerNorm of the UPDATED rows (tcgen05 path, float out with ldo == N == 512): the CTA that finishes a
-  // 128-row block last (per-block counter) normalises those rows of `out` and writes the next GEMM's bf16 operand:
-  // ln_out = LN(out) * ln_g + ln_b, optionally followed by TimeBlock modulation * (1 + scale) + shift and SiLU.
-  bf16* ln_out;              // nullptr = no fused LayerNorm
-  const float* ln_g; const float* ln_b;
-  const float* ln_mod;       // [scale(512) | shift(512)] or nullptr
-  const int* ln_step;        // device step counter selecting the modulation row, or nullptr
-  long long ln_mod_stride;
-  int* ln_counters;          // per 128-row block, zero before the launch; reset by the kernel (2 ints per block with ln_tail)
-  int ln_tail;               // 1: every CTA of a block normalises its share of the rows after the block completes
   int tma_out;               // set by gemm_tc: output tile leaves through TMA store / reduce-add (internal)
 };
 

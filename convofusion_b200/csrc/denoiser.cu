@@ -42,6 +42,10 @@ struct DeviceBuf {
 
 }  // namespace cfb
 
+namespace cfb {
+int g_shared_plan = getenv("CFB_PLAN") ? atoi(getenv("CFB_PLAN")) : 1;   // cfb_set_shared_plan / env CFB_PLAN=0
+}
+
 using namespace cfb;
 
 struct cfb_denoiser {
@@ -50,11 +54,11 @@ struct cfb_denoiser {
   int d, lat, ntok, L, H, ff, prec;
   unsigned epoch = 0;
   DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
-      preseq, slots, masks, uc, sS, sP, zall, z0all, ytall, lncnt;
+      preseq, slots, masks, uc, sS, sP, zall, z0all, ytall;
   // cached CUDA graph of one sampling step
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey {
-    unsigned epoch; int n_clips, n_branch, n_steps, kind, clip, preseq_len; float scale;
+    unsigned epoch; int n_clips, n_branch, full_last, n_steps, kind, clip, preseq_len; float scale;
     int n_slots[CFB_N_STREAMS], len[CFB_N_STREAMS]; bool has_mask[CFB_N_STREAMS];
     const void *noise, *record, *att[CFB_N_STREAMS];
     int plan[2 + 3 * TC_MAX_GROUPS];
@@ -69,6 +73,10 @@ struct cfb_denoiser {
   cudaStream_t chain_st[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
   int n_chains = 1;
+  // device-resident schedule tables of the last cfb_sample call (see cfb_sample)
+  std::vector<float> sched_ts, sched_coef;
+  unsigned sched_epoch = ~0u;
+  cudaEvent_t ev_sched = nullptr;
   int chains_override = 0;   // cfb_denoiser_set_chains (0 = CFB_CHAINS or 6)
   // per chain: side stream for the conditional-pair sub-chain of every layer; per step: two streams that run the
   // memory-side pre-projection (keys / values) while the chains are still in their self-attention blocks
@@ -139,24 +147,29 @@ int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaSt
 }
 
 // Per-step memory-side precompute of the shared-slot plan for all layers: keys Z + key bias z0 (which = 0) or values
-// Y^T (which = 1).  The two halves are independent and run on separate streams.
+// Y^T (which = 1).  The two halves are independent and run on separate streams.  T = bf16: tcgen05 GEMMs; T = float
+// (parity mode): the same algebra on the CUDA-core GEMM, so the plan itself is checked against the oracle at 1e-4.
+template <typename T>
 int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml, const int len[CFB_N_STREAMS],
                       int which, cudaStream_t st) {
   const int d = h->d, Ld = h->L * h->d;
-  const bf16* mh = h->mem_hat.as<bf16>();
+  constexpr int tb = sizeof(T) == 2;
+  const T* mh = h->mem_hat.as<T>();
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
-    const bf16* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
+    const T* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
     if (which == 0) {
-      Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = 1; ez.out = h->zall.as<bf16>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
-      CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
+      Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = tb; ez.out = h->zall.as<T>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
+      if constexpr (tb) CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
+      else CFB_TRY(gemm_simt(m0, 0, d, h->w.w_zx[x], 0, d, len[x], Ld, d, 0, ez, st));
     } else {
       const int rows_avail = ml.total_rows - ml.row_base[x];
-      Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = 1; ey.out = h->ytall.as<bf16>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
+      Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = tb; ey.out = h->ytall.as<T>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
       const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
-      CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+      if constexpr (tb) CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+      else CFB_TRY(gemm_simt(h->w.w_yx[x], 0, d, m0, 0, d, Ld, w_rows, d, 0, ey, st));   // columns past w_rows stay zero
     }
   }
-  if (which == 0) return shared_key_bias(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
+  if (which == 0) return shared_key_bias<T>(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
   return CFB_OK;
 }
 
@@ -197,25 +210,14 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
   };
-  // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  On the
-  // tcgen05 path the LayerNorm runs inside the GEMM (last-arriving CTA of each 128-row block); otherwise it is a
-  // separate row kernel.  `a` may be the GEMM's own A operand: a block is normalised only after all its tiles are done.
-  // measured slower than the separate row kernel (one SM normalising 128 rows is bound by its own L2 port): opt-in
-  // CFB_FUSE_LN: 0 = separate row kernel, 1 = last-arriving CTA normalises the block (slower), 2 = cluster / DSMEM,
-  // 3 = LayerNorm tail: every CTA of a completed block normalises its share of the rows (TMA-epilogue kernel)
-  static const int fuse_mode = getenv("CFB_FUSE_LN") ? atoi(getenv("CFB_FUSE_LN")) : 0;
-  const bool fuse_ln = fuse_mode != 0 && tb && g_gemm_backend != CFB_GEMM_SIMT && row0 % 128 == 0;
+  // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
+  // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
+  //  and are gone; the row-block kernel (rowblock.cu) is what fuses them now.
   auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
                         const float* mod) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
-    const bool fuse = fuse_ln && gemm_tc_supported(R, d, K, K, K);
-    if (fuse) {
-      ep.ln_out = reinterpret_cast<bf16*>(a); ep.ln_g = ln_g; ep.ln_b = ln_b; ep.ln_mod = mod; ep.ln_step = mod ? step_ptr : nullptr;
-      ep.ln_mod_stride = mod_stride; ep.ln_tail = fuse_mode == 3;
-      ep.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : fuse_mode == 3 ? h->lncnt.as<int>() + 2 * (row0 / 128) : nullptr;
-    }
     CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
-    if (!fuse) CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
+    CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
     return (int)CFB_OK;
   };
   CFB_TRY(ln_rows<T>(hres, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr, nullptr, 0, a, R, d, st));
@@ -232,80 +234,90 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     for (int x = 0; x < CFB_N_STREAMS; ++x)
       ca.att[x] = att_base && att_base[x] ? att_base[x] + (size_t)l * h->ntok * ca.len[x] : nullptr;
     bool shared_done = false;
-    if constexpr (sizeof(T) == 2) {
-      if (sp && sp->on) {
-        const int Ld = h->L * d;
-        if (l == 0)
-          for (int i = 0; i < 2; ++i)
-            if (aux->ev_pre[i]) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_pre[i], 0));
-        // conditional pairs: own-stream projection + per-pair attention (on the side stream when there is one: they
-        // only read `a` / mem_hat and write qx / uc), then -- after the shared path -- the own-stream fuser blocks
-        TcGroup gq[TC_MAX_GROUPS], gg[TC_MAX_GROUPS];
-        int ground[TC_MAX_GROUPS], ng = 0;
-        bf16* uc = h->uc.as<bf16>();
-        float* h_abs = h->h.as<float>();
-        for (int z = 0; z < sp->n_groups; ++z) {   // groups carry ABSOLUTE rows; a chain takes the part inside its range
-          const int lo = sp->g_row_start[z] > row0 ? sp->g_row_start[z] : row0;
-          const int hi_g = sp->g_row_start[z] + sp->g_rows[z], hi = hi_g < row0 + R ? hi_g : row0 + R;
-          if (hi <= lo) continue;
-          const int x = sp->g_stream[z];
-          gq[ng] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)x * d * d, w.b_qx + x * d, qx_abs + x * d, lo, hi - lo};
-          gg[ng] = TcGroup{uc + x * d, (const bf16*)w.w_fu + x * d, nullptr, h_abs, lo, hi - lo};
-          ground[ng++] = sp->g_round[z];
+    if (sp && sp->on) {
+      const int Ld = h->L * d;
+      if (l == 0)
+        for (int i = 0; i < 2; ++i)
+          if (aux->ev_pre[i]) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_pre[i], 0));
+      // conditional pairs: own-stream projection + per-pair attention (on the side stream when there is one: they
+      // only read `a` / mem_hat and write qx / uc), then -- after the shared path -- the own-stream fuser blocks
+      struct Grp { int x, lo, rows, round; };
+      Grp grp[TC_MAX_GROUPS];
+      int ng = 0;
+      T* uc = h->uc.as<T>();
+      float* h_abs = h->h.as<float>();
+      for (int z = 0; z < sp->n_groups; ++z) {   // groups carry ABSOLUTE rows; a chain takes the part inside its range
+        const int lo = sp->g_row_start[z] > row0 ? sp->g_row_start[z] : row0;
+        const int hi_g = sp->g_row_start[z] + sp->g_rows[z], hi = hi_g < row0 + R ? hi_g : row0 + R;
+        if (hi <= lo) continue;
+        grp[ng++] = Grp{sp->g_stream[z], lo, hi - lo, sp->g_round[z]};
+      }
+      const bool side = ng > 0 && aux->st2 != nullptr;
+      cudaStream_t sc = side ? aux->st2 : st;
+      if (ng > 0) {
+        if (side) {
+          CFB_CUDA(cudaEventRecord(aux->ev_a, st));
+          CFB_CUDA(cudaStreamWaitEvent(sc, aux->ev_a, 0));
         }
-        const bool side = ng > 0 && aux->st2 != nullptr;
-        cudaStream_t sc = side ? aux->st2 : st;
-        if (ng > 0) {
-          if (side) {
-            CFB_CUDA(cudaEventRecord(aux->ev_a, st));
-            CFB_CUDA(cudaStreamWaitEvent(sc, aux->ev_a, 0));
-          }
-          Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = 1; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+        Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = tb; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+        if constexpr (sizeof(T) == 2) {
+          TcGroup gq[TC_MAX_GROUPS];
+          for (int z = 0; z < ng; ++z)
+            gq[z] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
+                            grp[z].lo, grp[z].rows};
           CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, sc));
-          ca.skip_slot0 = 1;
-          CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, sc));
-          if (side) CFB_CUDA(cudaEventRecord(aux->ev_b, sc));
+        } else {
+          for (int z = 0; z < ng; ++z) {
+            Epilogue e1 = eq; e1.bias = w.b_qx + grp[z].x * d;
+            e1.out = qx_abs + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d;
+            CFB_TRY(gemm_simt(a_abs + (size_t)grp[z].lo * d, 0, d, (const float*)w.w_qx + (size_t)grp[z].x * d * d, 0, d,
+                              grp[z].rows, d, d, 0, e1, sc));
+          }
         }
-        auto cond_fuser = [&]() -> int {
-          if (ng == 0) return CFB_OK;
-          if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
-          Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+        ca.skip_slot0 = 1;
+        CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), uc, ca, n_batch, h->ntok, d, sc));
+        if (side) CFB_CUDA(cudaEventRecord(aux->ev_b, sc));
+      }
+      auto cond_fuser = [&]() -> int {
+        if (ng == 0) return CFB_OK;
+        if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
+        Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+        if constexpr (sizeof(T) == 2) {
           for (int r = 0; r < sp->n_rounds; ++r) {
             TcGroup round[TC_MAX_GROUPS];
             int n = 0;
             for (int z = 0; z < ng; ++z)
-              if (ground[z] == r) round[n++] = gg[z];
+              if (grp[z].round == r)
+                round[n++] = TcGroup{uc + grp[z].x * d, (const bf16*)w.w_fu + grp[z].x * d, nullptr, h_abs, grp[z].lo, grp[z].rows};
             if (n > 0) CFB_TRY(gemm_tc_grouped(round, n, R_total, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
           }
-          return CFB_OK;
-        };
-        // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h
-        float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
-        bf16* sP = h->sP.as<bf16>() + (size_t)row0 * sp->k_tot;
-        Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
-        es.ldo = sp->n_tot; es.replicate = 1;
-        CFB_TRY(gemm_tc(a, d, h->zall.as<bf16>() + (size_t)l * d, Ld, R, sp->n_tot, d, es, st));
-        SharedAttnArgs sa{};
-        for (int x = 0; x < CFB_N_STREAMS; ++x) {
-          sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
-          sa.slot[x] = ca.slot[x]; sa.mask[x] = ca.mask[x];
+        } else {
+          for (int z = 0; z < ng; ++z) {   // one stream: sequential accumulation, overlapping row blocks are fine
+            Epilogue e1 = eg; e1.out = h_abs + (size_t)grp[z].lo * d;
+            CFB_TRY(gemm_simt(uc + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d, 0, CFB_N_STREAMS * d,
+                              (const float*)w.w_fu + grp[z].x * d, 0, CFB_N_STREAMS * d, grp[z].rows, d, d, 0, e1, st));
+          }
         }
-        sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
-        CFB_TRY(softmax_shared(sS, sP, sa, n_batch, h->ntok, st));
-        Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-        if (fuse_ln) {   // the LayerNorm rides on the values GEMM, so every other update of h must precede it
-          CFB_TRY(cond_fuser());
-          ey.ln_out = reinterpret_cast<bf16*>(a); ey.ln_g = w.tb2_g; ey.ln_b = w.tb2_b; ey.ln_mod = mod2; ey.ln_step = step_ptr;
-          ey.ln_mod_stride = mod_stride; ey.ln_tail = fuse_mode == 3;
-          ey.ln_counters = fuse_mode == 1 ? h->lncnt.as<int>() + row0 / 128 : fuse_mode == 3 ? h->lncnt.as<int>() + 2 * (row0 / 128) : nullptr;
-        }
-        CFB_TRY(gemm_tc(sP, sp->k_tot, h->ytall.as<bf16>() + (size_t)l * d * sp->k_tot, sp->k_tot, R, d, sp->k_tot, ey, st));
-        if (!fuse_ln) {
-          CFB_TRY(cond_fuser());
-          CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
-        }
-        shared_done = true;
+        return CFB_OK;
+      };
+      // pairs on slot 0: scores against the pre-projected keys, softmax, pre-projected values straight into h
+      float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
+      T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
+      Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
+      es.ldo = sp->n_tot; es.replicate = 1;
+      CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
+      SharedAttnArgs sa{};
+      for (int x = 0; x < CFB_N_STREAMS; ++x) {
+        sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
+        sa.slot[x] = ca.slot[x]; sa.mask[x] = ca.mask[x];
       }
+      sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
+      CFB_TRY(softmax_shared<T>(sS, sP, sa, n_batch, h->ntok, st));
+      Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
+      CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
+      CFB_TRY(cond_fuser());
+      CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+      shared_done = true;
     }
     if (!shared_done) {
       CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
@@ -350,10 +362,6 @@ int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
   CFB_TRY(h->xin.reserve((size_t)n_in * h->ntok * h->lat * es, &h->epoch));
   CFB_TRY(h->eps.reserve(R * h->lat * 4, &h->epoch));
-  if (h->lncnt.cap < (R / 128 + 2) * 8) {   // fused-LayerNorm block counters: zero once, the kernels re-arm them
-    CFB_TRY(h->lncnt.reserve((R / 128 + 2) * 8, &h->epoch));
-    CFB_CUDA(cudaMemset(h->lncnt.p, 0, h->lncnt.cap));
-  }
   return CFB_OK;
 }
 
@@ -407,14 +415,14 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
     CFB_CUDA(cudaEventRecord(h->ev_mh, h->pre_st[0]));
     CFB_CUDA(cudaStreamWaitEvent(h->pre_st[1], h->ev_mh, 0));
     for (int i = 0; i < 2; ++i) {
-      CFB_TRY(shared_precompute(h, sp, ml, ca.len, i, h->pre_st[i]));
+      CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, i, h->pre_st[i]));
       CFB_CUDA(cudaEventRecord(h->ev_pre[i], h->pre_st[i]));
     }
   } else {
     CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
     if (sp.on) {
-      CFB_TRY(shared_precompute(h, sp, ml, ca.len, 0, st));
-      CFB_TRY(shared_precompute(h, sp, ml, ca.len, 1, st));
+      CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, 0, st));
+      CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, 1, st));
     }
   }
   CFB_TRY(embed_cast<T>(h, h->x.as<float>(), n_clips, st));       // torch.cat([latents] * 7), convofusion.py:499
@@ -451,23 +459,30 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
   return guidance_sched_step(sa, st);
 }
 
-// Decide whether the shared-slot plan applies and derive the conditional row groups from the slot tables.
+// Decide whether the shared-slot plan applies and derive the conditional row groups from the slot tables.  The plan
+// runs in both precisions (fp32: the same algebra on the CUDA-core GEMM, which is how the plan is checked against the
+// oracle at 1e-4); env CFB_PLAN=0 keeps the general per-pair path.  The tables are read from mem->slot_host when the
+// caller supplies a host copy (no device read-back, no stream synchronisation).
 int make_shared_plan(cfb_denoiser* h, const cfb_memory* mem, int n_batch, SharedPlan* sp, cudaStream_t st) {
   sp->on = false;
-  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT) return CFB_OK;
+  if (!g_shared_plan || (h->prec == CFB_BF16 && g_gemm_backend == CFB_GEMM_SIMT)) return CFB_OK;
   for (int x = 0; x < CFB_N_STREAMS; ++x)
     if (mem->slot[x] == nullptr) return CFB_OK;
   std::vector<int> hs((size_t)n_batch);
   int ng = 0, s_off = 0, p_off = 0;
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
-    CFB_CUDA(cudaMemcpyAsync(hs.data(), mem->slot[x], (size_t)n_batch * 4, cudaMemcpyDeviceToHost, st));
-    CFB_CUDA(cudaStreamSynchronize(st));
+    const int* tab = mem->slot_host[x];
+    if (tab == nullptr) {
+      CFB_CUDA(cudaMemcpyAsync(hs.data(), mem->slot[x], (size_t)n_batch * 4, cudaMemcpyDeviceToHost, st));
+      CFB_CUDA(cudaStreamSynchronize(st));
+      tab = hs.data();
+    }
     for (int b = 0; b < n_batch;) {
-      CFB_CHECK(hs[b] >= 0 && hs[b] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, hs[b]);
-      if (hs[b] == 0) { ++b; continue; }
+      CFB_CHECK(tab[b] >= 0 && tab[b] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, tab[b]);
+      if (tab[b] == 0) { ++b; continue; }
       int e = b;
-      while (e < n_batch && hs[e] != 0) {
-        CFB_CHECK(hs[e] >= 0 && hs[e] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, hs[e]);
+      while (e < n_batch && tab[e] != 0) {
+        CFB_CHECK(tab[e] >= 0 && tab[e] < mem->n_slots[x], "memory stream %d: slot index %d out of range", x, tab[e]);
         ++e;
       }
       if (ng == TC_MAX_GROUPS) return CFB_OK;   // too fragmented: keep the general path
@@ -493,14 +508,14 @@ int make_shared_plan(cfb_denoiser* h, const cfb_memory* mem, int n_batch, Shared
     sp->g_round[z] = r;
     if (r + 1 > sp->n_rounds) sp->n_rounds = r + 1;
   }
-  const size_t R = (size_t)n_batch * h->ntok, Ld = (size_t)h->L * h->d;
+  const size_t R = (size_t)n_batch * h->ntok, Ld = (size_t)h->L * h->d, es = h->prec == CFB_BF16 ? 2 : 4;
   const unsigned before = h->epoch;
-  CFB_TRY(h->uc.reserve(R * CFB_N_STREAMS * h->d * 2, &h->epoch));
+  CFB_TRY(h->uc.reserve(R * CFB_N_STREAMS * h->d * es, &h->epoch));
   CFB_TRY(h->sS.reserve(R * sp->n_tot * 4, &h->epoch));
-  CFB_TRY(h->sP.reserve(R * sp->k_tot * 2, &h->epoch));
-  CFB_TRY(h->zall.reserve((size_t)sp->n_tot * Ld * 2, &h->epoch));
+  CFB_TRY(h->sP.reserve(R * sp->k_tot * es, &h->epoch));
+  CFB_TRY(h->zall.reserve((size_t)sp->n_tot * Ld * es, &h->epoch));
   CFB_TRY(h->z0all.reserve((size_t)h->L * sp->n_tot * 4, &h->epoch));
-  CFB_TRY(h->ytall.reserve(Ld * sp->k_tot * 2, &h->epoch));
+  CFB_TRY(h->ytall.reserve(Ld * sp->k_tot * es, &h->epoch));
   if (h->epoch != before) {   // fresh allocations: padding rows/columns must hold finite values
     CFB_CUDA(cudaMemsetAsync(h->zall.p, 0, h->zall.cap, st));
     CFB_CUDA(cudaMemsetAsync(h->z0all.p, 0, h->z0all.cap, st));
@@ -559,11 +574,17 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
     if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
   }
   if (h->ev_mh) cudaEventDestroy(h->ev_mh);
+  if (h->ev_sched) cudaEventDestroy(h->ev_sched);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->lncnt};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall};
   for (DeviceBuf* b : bufs) b->release();
   delete h;
+}
+
+int cfb_set_shared_plan(int enabled) {
+  g_shared_plan = enabled != 0;
+  return CFB_OK;
 }
 
 int cfb_denoiser_set_chains(cfb_denoiser* h, int n_chains) {
@@ -578,6 +599,7 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
   CFB_CHECK(h && sample && mem && eps_out && n_batch > 0, "cfb_denoiser_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CFB_TRY(reserve_rows(h, n_batch, n_batch));
+  h->sched_epoch = ~0u;   // the single-step tables below replace those of the last cfb_sample call
   CFB_TRY(h->tsteps.reserve(4, &h->epoch));
   const float tf = (float)timestep;
   CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, &tf, 4, cudaMemcpyHostToDevice, st));
@@ -600,16 +622,17 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
 }
 
 int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem, int n_clips, int n_branch,
-               float* latents, const float* step_noise, const float* preseq, int preseq_len, float* record,
+               int full_last, float* latents, const float* step_noise, const float* preseq, int preseq_len, float* record,
                float* const att_out[CFB_N_STREAMS], int use_graph, cfb_stream stream) {
   CFB_CHECK(h && sched && mem && latents && n_clips > 0, "cfb_sample: bad argument");
-  CFB_CHECK(n_branch == 6 || n_branch == CFB_N_BRANCH, "cfb_sample: n_branch must be 6 or 7");
+  CFB_CHECK(n_branch >= 1 && n_branch <= CFB_N_BRANCH, "cfb_sample: n_branch must be 1..7");
+  CFB_CHECK(!full_last || n_branch >= 2, "cfb_sample: full_last needs at least the unconditional and the full-cond branch");
   CFB_CHECK(sched->n_steps > 0 && sched->timesteps && sched->coef, "cfb_sample: empty schedule");
   CFB_CHECK(sched->kind == CFB_SCHED_DDIM || sched->kind == CFB_SCHED_DDPM, "cfb_sample: unknown scheduler kind");
   CFB_CHECK(preseq == nullptr || (preseq_len > 0 && preseq_len <= h->ntok), "cfb_sample: bad preseq_len %d", preseq_len);
   bool want_att = false;
   if (att_out) for (int x = 0; x < CFB_N_STREAMS; ++x) want_att |= att_out[x] != nullptr;
-  CFB_CHECK(!want_att || n_branch == CFB_N_BRANCH, "cfb_sample: attention maps come from the full-cond branch; use n_branch=7");
+  CFB_CHECK(!want_att || full_last, "cfb_sample: attention maps come from the full-cond branch; evaluate it (full_last=1)");
   cudaStream_t user_st = (cudaStream_t)stream;
   cudaStream_t st = user_st;
   const bool fenced = use_graph && (user_st == nullptr || user_st == cudaStreamLegacy || user_st == cudaStreamPerThread);
@@ -630,14 +653,28 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_TRY(h->coef.reserve((size_t)(S + 1) * 8 * 4, &h->epoch));
   CFB_TRY(h->step.reserve(4, &h->epoch));
   CFB_TRY(h->x.reserve((size_t)n_clips * n_per_clip * 4, &h->epoch));
+  // Schedule tables (timesteps -> time embedding / TimeBlock modulation tables, scheduler coefficients) are a pure
+  // function of the schedule: they stay on the device across calls and are rebuilt only when the schedule changes
+  // (a pageable-memory upload synchronises the stream, and prep_time is four launches).
   std::vector<float> tf(S);
   for (int i = 0; i < S; ++i) tf[i] = (float)sched->timesteps[i];
-  CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, tf.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
-  CFB_CUDA(cudaMemcpyAsync(h->coef.p, sched->coef, (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st));
-  CFB_CUDA(cudaMemsetAsync(h->coef.as<float>() + (size_t)S * 8, 0, 8 * 4, st));
+  const bool same_sched = h->sched_epoch == h->epoch && h->sched_ts == tf && (int)h->sched_coef.size() == S * 8 &&
+                          memcmp(h->sched_coef.data(), sched->coef, (size_t)S * 8 * 4) == 0;
+  if (!same_sched) {
+    CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, tf.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+    CFB_CUDA(cudaMemcpyAsync(h->coef.p, sched->coef, (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st));
+    CFB_CUDA(cudaMemsetAsync(h->coef.as<float>() + (size_t)S * 8, 0, 8 * 4, st));
+    CFB_CUDA(cudaStreamSynchronize(st));   // tf is a host temporary
+    CFB_TRY(prep_time(h, S, st));
+    h->sched_ts = tf;
+    h->sched_coef.assign(sched->coef, sched->coef + (size_t)S * 8);
+    h->sched_epoch = h->epoch;             // prep_time may have grown buffers: remember the epoch AFTER it
+    if (!h->ev_sched) CFB_CUDA(cudaEventCreateWithFlags(&h->ev_sched, cudaEventDisableTiming));
+    CFB_CUDA(cudaEventRecord(h->ev_sched, st));
+  } else {
+    CFB_CUDA(cudaStreamWaitEvent(st, h->ev_sched, 0));   // a later call may arrive on another stream
+  }
   CFB_CUDA(cudaMemsetAsync(h->step.p, 0, 4, st));
-  CFB_CUDA(cudaStreamSynchronize(st));   // tf is a host temporary
-  CFB_TRY(prep_time(h, S, st));
   MemLayout ml; CrossArgs ca;
   CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
   SharedPlan sp;
@@ -695,7 +732,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   sa.eps = h->eps.as<float>(); sa.x = h->x.as<float>(); sa.noise = step_noise; sa.coef = h->coef.as<float>();
   sa.step_ptr = h->step.as<int>(); sa.step_inc = h->step.as<int>(); sa.record = record;
   sa.preseq = preseq ? h->preseq.as<float>() : nullptr; sa.inp_noise = h->inp_noise.as<float>();
-  sa.n_branch = n_branch; sa.n_clips = n_clips; sa.n_per_clip = n_per_clip; sa.n_inpaint = n_inpaint;
+  sa.n_branch = n_branch; sa.full_last = full_last; sa.n_clips = n_clips; sa.n_per_clip = n_per_clip; sa.n_inpaint = n_inpaint;
   sa.n_steps = S; sa.kind = sched->kind; sa.clip_sample = sched->clip_sample; sa.guidance_scale = sched->guidance_scale;
 
   auto body = [&]() {
@@ -706,7 +743,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   if (use_graph) {
     cfb_denoiser::GraphKey key;
     memset(&key, 0, sizeof(key));
-    key.epoch = h->epoch; key.n_clips = n_clips; key.n_branch = n_branch; key.n_steps = S; key.kind = sched->kind;
+    key.epoch = h->epoch; key.n_clips = n_clips; key.n_branch = n_branch; key.full_last = full_last; key.n_steps = S; key.kind = sched->kind;
     key.clip = sched->clip_sample; key.preseq_len = preseq ? preseq_len : 0; key.scale = sched->guidance_scale;
     for (int x = 0; x < CFB_N_STREAMS; ++x) {
       key.n_slots[x] = mem->n_slots[x]; key.len[x] = mem->len[x]; key.has_mask[x] = mem->mask[x] != nullptr;

@@ -12,7 +12,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Two CTAs fit per SM (<=113 KB smem,
 // BN<=256 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
 #include "common.cuh"
-#include "rowvec.cuh"
+#include "tc_ptx.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -23,164 +23,12 @@ namespace cfb {
 
 namespace {
 
+using namespace tc;
+
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;
 constexpr int NTHREADS = 192;
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-// Multicast variants: the data (and the complete_tx on the barrier at the same offset) land in every CTA of `mask`.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%2, %3}], [%4], %5;"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-// Bulk tensor store / reduce-add of one shared-memory box (async proxy); completion tracked by bulk groups.
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
-               ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// ---- cta_group::2 (CTA pair) variants.  The pair shares one MMA: the leader (cluster rank 0) issues it, the operands
-// are read from BOTH CTAs' shared memory at the same offsets, each CTA's tensor memory receives its own 128 rows.
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
-  return r;
-}
-// TMA load whose completion is signalled on a barrier that may live in the peer CTA (cluster-space address).
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout):
-// [0,14) addr>>4 | [16,30) LBO>>4 (=1, unused when swizzled) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
-// | [46,48) version=1 | [61,64) layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, dense.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 #ifndef CFB_TC_TRACE
 #define CFB_TC_TRACE 0
@@ -203,43 +51,21 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STATS_OFF = BAR_OFF + 128;                             // 128 rows x (sum, sumsq) floats
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024 + 1024;                   // barriers, row stats, alignment slack
+  static constexpr int STATS_OFF = BAR_OFF + 128;                             // BN bias floats
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024 + 1024;                   // barriers, bias, alignment slack
 };
 
 // One 128 x BN output tile: rows [m0, min(m0+128, m_end)), columns [n0, n0+BN).
-//
-// Cluster multicast (CN x CM CTAs = CN consecutive n-tiles x CM consecutive m-tiles).  With 128x128 tiles a CTA pulls
-// 32 KB from L2 per 64-deep K block for 1 M MACs (32 MAC/B), and the L2->SM path, not the tensor pipe, bounds the
-// kernel.  The CN CTAs of a cluster row need the SAME A tile and the CM CTAs of a cluster column the SAME B tile, so
-// each CTA loads only a 1/CN slice of A and a 1/CM slice of B and TMA-multicasts it into every sharer's shared
-// memory (same offset, each sharer's own `full` barrier).  A stage may be overwritten only when every CTA that
-// receives data from this producer has consumed it, so consumers release a stage with a multicast tcgen05.commit to
-// the `empty` barrier of all CN + CM - 1 CTAs that feed them.
-//
-// LNC (LayerNorm over a cluster): the four n-tile CTAs of one 128-row block of a [M,512] residual update form a
-// cluster.  Each CTA keeps its updated 128x128 sub-block in shared memory, publishes per-row (sum, sum of squares) of
-// its 128 columns, and after one cluster barrier reads the other three CTAs' partials through distributed shared
-// memory (mapa + ld.shared::cluster).  Every CTA then normalises its own sub-block and writes the next GEMM's bf16
-// operand: the LayerNorm costs no global read and no kernel launch on the critical path.
-template <int BN, int STAGES, int CN = 1, int CM = 1, bool LNC = false, bool TMA_ONLY = false>
+// TMA_ONLY selects the TMA store / L2 reduce-add epilogue at compile time (fewer registers: the staged ld/st epilogue
+// is not even in the binary); otherwise ep.tma_out picks at run time.
+// Variants that were measured slower on this workload and removed in round 2 (DESIGN.md 5.1 keeps the numbers): cluster
+// TMA multicast of the operands, a 2-stage ring with three CTAs per SM, and three ways of running the following
+// LayerNorm inside this kernel (last-arriving CTA, 4-CTA cluster over DSMEM, a spin-waiting tail).
+template <int BN, int STAGES, bool TMA_ONLY = false>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const CUtensorMap* tmO_p, const int m0,
                                           const int M /* first row NOT to store */, const int n0, const int N,
                                           const int K, const Epilogue& ep) {
   using S = Smem<BN, STAGES>;
-  constexpr int CL = CN * CM;
-  constexpr bool CLUSTERED = CL > 1 || LNC;
-  static_assert(!LNC || (CL == 1 && BN == 128), "cluster LayerNorm: 4 x (128x128) tiles, no multicast");
-  uint32_t crank = 0;
-  if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  const uint32_t rn = crank % CN, rm = crank / CN;
-  // CTAs sharing my A tile (same rm) and my B tile (same rn); their union feeds / is fed by me
-  uint32_t mask_a = 0, mask_b = 0;
-#pragma unroll
-  for (int i = 0; i < CN; ++i) mask_a |= 1u << (rm * CN + i);
-#pragma unroll
-  for (int j = 0; j < CM; ++j) mask_b |= 1u << (rn + j * CN);
-  const uint16_t mask_u = (uint16_t)(mask_a | mask_b);
   const CUtensorMap& tmA = *tmA_p;
   const CUtensorMap& tmB = *tmB_p;
   extern __shared__ uint8_t smem_raw[];
@@ -260,19 +86,14 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + s * 8, 1);
-      mbar_init(bar_empty + s * 8, CN + CM - 1);   // one release per CTA that consumes data I produce
+      mbar_init(bar_empty + s * 8, 1);
     }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
-  if constexpr (CL > 1) {   // barriers of every CTA must be initialised before a peer multicasts into them
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
   pdl_sync();   // everything above touched only shared/tensor memory; operands of the previous kernel are read below
@@ -280,29 +101,17 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
 
   if (warp == 0) {
     if (lane == 0) {
-      constexpr int A_SLICE = BM / CN, B_SLICE = BN / CM;   // rows this CTA loads for its sharers
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + s * 8, ph ^ 1);
         const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
         mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
-        if constexpr (CN > 1)
-          tma_load_2d_mc(sa + rn * (A_SLICE * BK * 2), &tmA, kb * BK, m0 + (int)rn * A_SLICE, bar_full + s * 8, (uint16_t)mask_a);
-        else
-          tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
-        if constexpr (CM > 1)
-          tma_load_2d_mc(sb + rm * (B_SLICE * BK * 2), &tmB, kb * BK, n0 + (int)rm * B_SLICE, bar_full + s * 8, (uint16_t)mask_b);
-        else
-          tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
+        tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
+        tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
         if (kb == 0) trace(2);
       }
       trace(3);
-    }
-    if constexpr (LNC) {   // see warp 1
-      __syncwarp();
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -320,17 +129,10 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
           // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (addr >> 4) field
           umma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
-        // frees the smem slot once these MMAs retire -- in my own CTA and in every CTA that feeds me
-        if constexpr (CL > 1) umma_commit_mc(bar_empty + s * 8, mask_u);
-        else umma_commit(bar_empty + s * 8);
+        umma_commit(bar_empty + s * 8);   // frees the smem slot once these MMAs retire
       }
       umma_commit(bar_acc);
       trace(5);
-    }
-    if constexpr (LNC) {   // matches the epilogue warps' barrier between publishing and reading the row statistics
-      __syncwarp();
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   } else {
     // ---- epilogue.  tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
@@ -338,7 +140,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     // fired, so each warp transposes its 32 x BN slab through that shared memory and then walks its rows with the
     // lanes spread across the columns: every global access of the bias / residual / output is row-contiguous.
     const int q = warp & 3;
-    if (TMA_ONLY || (!LNC && ep.tma_out)) {
+    if (TMA_ONLY || ep.tma_out) {
       // ---- TMA epilogue.  Each warp owns a 32-row slab of the tile.  Per 32 accumulator columns it adds bias /
       // activation in registers, writes the values into a 128B-swizzled [32 rows x 128 B] box in the (now idle)
       // pipeline shared memory and lets one lane hand that box to the TMA unit: a plain tensor store, or an f32
@@ -419,15 +221,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
             }
           }
         }
-        if (lane == 0) {
-          if (ep.ln_out) {                 // a LayerNorm tail reads these rows back: the updates must have landed
-            tma_wait_all0();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __threadfence();
-          } else {
-            tma_wait_read0();              // the boxes must stay intact until the TMA unit has read them
-          }
-        }
+        if (lane == 0) tma_wait_read0();   // the boxes must stay intact until the TMA unit has read them
       }
       if (warp == 2 && lane == 0) trace(7);
     } else if constexpr (!TMA_ONLY) {
@@ -522,19 +316,6 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
 #pragma unroll
           for (int c = 0; c < CPL; ++c) v[i][c] += res[i][c];
       }
-      if constexpr (LNC) {   // keep the updated values on chip and publish this CTA's share of the row statistics
-        float* stats = reinterpret_cast<float*>(gen_base + S::STATS_OFF);
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) { s1 += v[i][c]; s2 = fmaf(v[i][c], v[i][c], s2); }
-          s1 = warp_sum(s1);
-          s2 = warp_sum(s2);
-          if (lane == 0) { stats[(q * 32 + rb + i) * 2] = s1; stats[(q * 32 + rb + i) * 2 + 1] = s2; }
-          *reinterpret_cast<float4*>(stg + (rb + i) * PITCH + lane * 4) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-        }
-      }
       for (int rep = 0; rep < ep.replicate; ++rep) {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
@@ -563,211 +344,35 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         }
       }
     }
-    if constexpr (LNC) {
-      // ---- LayerNorm over the cluster: statistics of the other three column blocks through DSMEM
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-      const uint32_t my_stats = base + S::STATS_OFF + (uint32_t)(q * 32 + lane) * 8;
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (uint32_t peer = 0; peer < 4; ++peer) {
-        uint32_t ra;
-        float a1, a2;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(my_stats), "r"(peer));
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a1) : "r"(ra) : "memory");
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(a2) : "r"(ra + 4) : "memory");
-        t1 += a1; t2 += a2;
-      }
-      const float mean_l = t1 * (1.0f / 512.0f);
-      const float rstd_l = rsqrtf(fmaxf(t2 * (1.0f / 512.0f) - mean_l * mean_l, 0.f) + 1e-5f);   // row q*32+lane
-      const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
-      const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_g + n);
-      const float4 b4 = *reinterpret_cast<const float4*>(ep.ln_b + n);
-      float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
-      if (mod) { sc4 = *reinterpret_cast<const float4*>(mod + n); sh4 = *reinterpret_cast<const float4*>(mod + 512 + n); }
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) {
-        const float mu = __shfl_sync(0xffffffffu, mean_l, rr), rs = __shfl_sync(0xffffffffu, rstd_l, rr);
-        const float4 x = *reinterpret_cast<const float4*>(stg + rr * PITCH + lane * 4);
-        float y0 = (x.x - mu) * rs * g4.x + b4.x, y1 = (x.y - mu) * rs * g4.y + b4.y;
-        float y2 = (x.z - mu) * rs * g4.z + b4.z, y3 = (x.w - mu) * rs * g4.w + b4.w;
-        if (mod) {
-          y0 = act_apply(y0 * (1.0f + sc4.x) + sh4.x, CFB_ACT_SILU); y1 = act_apply(y1 * (1.0f + sc4.y) + sh4.y, CFB_ACT_SILU);
-          y2 = act_apply(y2 * (1.0f + sc4.z) + sh4.z, CFB_ACT_SILU); y3 = act_apply(y3 * (1.0f + sc4.w) + sh4.w, CFB_ACT_SILU);
-        }
-        const int r = r0 + rr;
-        if (r < M) {
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(ep.ln_out + (size_t)r * 512 + n) = pk;
-        }
-      }
-    } else
-    // ---- fused LayerNorm of this 128-row block by the CTA that completes it (see Epilogue::ln_out)
-    if (ep.ln_out != nullptr) {
-      __shared__ int s_last;
-      __threadfence();                                            // my residual stores before my counter increment
-      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps only
-      if (warp == 2 && lane == 0) {
-        const int done = atomicAdd(ep.ln_counters + blockIdx.y, 1);
-        s_last = (done == (int)gridDim.x - 1);
-        if (s_last) ep.ln_counters[blockIdx.y] = 0;               // every n-tile of this block has arrived: re-arm
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (s_last) {
-        __threadfence();                                          // order the counter observation before the reads
-        const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
-        constexpr int LD = 512, NR = 4;                           // rows in flight per warp
-        float gam[16], bet[16];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_g + i * 128 + lane * 4);
-          const float4 b4 = *reinterpret_cast<const float4*>(ep.ln_b + i * 128 + lane * 4);
-          gam[4 * i] = g4.x; gam[4 * i + 1] = g4.y; gam[4 * i + 2] = g4.z; gam[4 * i + 3] = g4.w;
-          bet[4 * i] = b4.x; bet[4 * i + 1] = b4.y; bet[4 * i + 2] = b4.z; bet[4 * i + 3] = b4.w;
-        }
-        const float* hbase = reinterpret_cast<const float*>(ep.out);
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += NR) {
-          float x[NR][16];
-#pragma unroll
-          for (int j = 0; j < NR; ++j) {
-            const int r = min(m0 + q * 32 + rb + j, M - 1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(hbase + (size_t)r * LD + i * 128 + lane * 4));
-              x[j][4 * i] = t.x; x[j][4 * i + 1] = t.y; x[j][4 * i + 2] = t.z; x[j][4 * i + 3] = t.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < NR; ++j) {
-            const int r = m0 + q * 32 + rb + j;
-            float sum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sum += x[j][i];
-            const float mu = warp_sum(sum) * (1.0f / LD);
-            float sq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { x[j][i] -= mu; sq += x[j][i] * x[j][i]; }
-            const float rstd = rsqrtf(warp_sum(sq) * (1.0f / LD) + 1e-5f);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x[j][i] = x[j][i] * rstd * gam[i] + bet[i];
-            if (mod) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 sc = *reinterpret_cast<const float4*>(mod + i * 128 + lane * 4);
-                const float4 sh = *reinterpret_cast<const float4*>(mod + LD + i * 128 + lane * 4);
-                x[j][4 * i] = act_apply(x[j][4 * i] * (1.0f + sc.x) + sh.x, CFB_ACT_SILU);
-                x[j][4 * i + 1] = act_apply(x[j][4 * i + 1] * (1.0f + sc.y) + sh.y, CFB_ACT_SILU);
-                x[j][4 * i + 2] = act_apply(x[j][4 * i + 2] * (1.0f + sc.z) + sh.z, CFB_ACT_SILU);
-                x[j][4 * i + 3] = act_apply(x[j][4 * i + 3] * (1.0f + sc.w) + sh.w, CFB_ACT_SILU);
-              }
-            }
-            if (r < M) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 t0 = __floats2bfloat162_rn(x[j][4 * i], x[j][4 * i + 1]);
-                const __nv_bfloat162 t1 = __floats2bfloat162_rn(x[j][4 * i + 2], x[j][4 * i + 3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
-                *reinterpret_cast<uint2*>(ep.ln_out + (size_t)r * LD + i * 128 + lane * 4) = pk;
-              }
-            }
-          }
-        }
-      }
-    }
     }   // staged (non-TMA) epilogue
   }
   if (warp == 2 && lane == 0) trace(8);
   tc_fence_before();
-  if constexpr (CLUSTERED) {   // no CTA may exit while a peer can still multicast into it, arrive on its barriers or read its statistics
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   if (threadIdx.x == 0) trace(9);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, BN);
     if (lane == 0) trace(10);
   }
-  if constexpr (TMA_ONLY) {
-    // ---- LayerNorm tail (Epilogue::ln_out, float [M,512] residual output).  The gridDim.x CTAs of a 128-row block
-    // signal a per-block counter once their updates are globally visible; each then waits for the whole block and
-    // normalises its own share of the rows with all six warps, writing the next GEMM's bf16 operand.  CTAs are
-    // dispatched in block-id order, so the CTAs a spinning CTA waits for are already resident or ahead of every
-    // undispatched CTA: no deadlock.  The second counter re-arms both once every CTA of the block has passed.
-    if (ep.ln_out != nullptr) {
-      int* cnt = ep.ln_counters + 2 * blockIdx.y;
-      const int n_cta = (int)gridDim.x;
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(cnt, 1);
-        trace(11);
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        while (ld_acquire_gpu(cnt) < n_cta) {
-          __nanosleep(40);
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 2000000ull) break;   // 2 ms: never hang the device on a protocol error
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) trace(12);
-      const float* mod = ep.ln_mod ? ep.ln_mod + (ep.ln_step ? (size_t)(*ep.ln_step) * ep.ln_mod_stride : 0) : nullptr;
-      const int per = (BM + n_cta - 1) / n_cta;
-      const int r_lo = m0 + (int)blockIdx.x * per;
-      const int r_hi = min(min(r_lo + per, m0 + BM), M);
-      const float* hbase = reinterpret_cast<const float*>(ep.out);
-      constexpr int NR = 3;                                   // rows in flight per warp
-#pragma unroll 1
-      for (int r = r_lo + warp * NR; r < r_hi; r += (NTHREADS / 32) * NR) {
-        RowVec<512> rv[NR];
-#pragma unroll
-        for (int j = 0; j < NR; ++j) rv[j].load_cg(hbase + (size_t)min(r + j, r_hi - 1) * 512, lane);
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          ln_row_finish<512, true>(rv[j], ep.ln_g, ep.ln_b, mod, lane);
-          if (r + j < r_hi) rv[j].store(ep.ln_out + (size_t)(r + j) * 512, lane);
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        trace(13);
-        const int old = atomicAdd(cnt + 1, 1);
-        if (old == n_cta - 1) { cnt[1] = 0; __threadfence(); cnt[0] = 0; }
-      }
-    }
-  }
 }
 
-template <int BN, int STAGES, int CN, int CM>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmO, int M, int N,
                                                            int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, CN, CM>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
-// TMA-epilogue-only instantiation: no staged ld/st epilogue in the binary, so it fits 3 CTAs per SM (<=112 registers,
-// 2-stage ring = 68 KB of shared memory): the phases of co-resident CTAs (prologue, operand latency, main loop,
-// epilogue) overlap on one SM.
-template <int BN, int STAGES, int OCC>
-__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB,
-                                                                  const __grid_constant__ CUtensorMap tmO, int M, int N,
-                                                                  int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, 1, 1, false, true>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
-}
-
+// TMA-epilogue-only instantiation: no staged ld/st epilogue in the binary (116 registers, 2 CTAs per SM): the phases
+// of co-resident CTAs (prologue, operand latency, main loop, epilogue) overlap on one SM.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_ln_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmB, int M, int N,
-                                                                  int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, 1, 1, true>(&tmA, &tmB, nullptr, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO, int M, int N,
+                                                               int K, Epilogue ep) {
+  gemm_tile<BN, STAGES, true>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 // ---------------------------------------------------------------- cta_group::2: 256 x 256 tile per CTA pair
@@ -970,8 +575,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_kernel(const __gr
   gemm_tile<BN, STAGES>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
 }
 
-template <int BN, int STAGES, int OCC>
-__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tc_grouped_tma_kernel(const __grid_constant__ GroupedArgs g, int N,
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_tma_kernel(const __grid_constant__ GroupedArgs g, int N,
                                                                           int K, Epilogue ep) {
   const int z = blockIdx.z;
   const int m0 = g.row_start[z] + blockIdx.y * BM;
@@ -979,7 +584,7 @@ __global__ void __launch_bounds__(NTHREADS, OCC) gemm_tc_grouped_tma_kernel(cons
   if (m0 >= m_end) return;
   ep.bias = g.bias[z];
   ep.out = g.out[z];
-  gemm_tile<BN, STAGES, 1, 1, false, true>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, true>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
 }
 
 // ---------------------------------------------------------------- host side
@@ -1016,7 +621,8 @@ struct MapKeyHash {
   }
 };
 
-// Descriptors are pure functions of (pointer, shape), so they are cached for the process lifetime.
+// Descriptors are pure functions of (pointer, shape), so they are cached; the cache is bounded (callers hand in fresh
+// torch allocations on the eager paths): when it fills up it is simply dropped and rebuilt on demand.
 // MAP_OPERAND: bf16 [rows, cols] K-major operand, box 64 x box_rows.  MAP_OUT_*: output tile boxes of one warp's
 // 32 rows x 128 bytes (32 floats / 64 bf16), same 128-byte swizzle.
 int get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int kind = MAP_OPERAND) {
@@ -1043,49 +649,33 @@ int get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap
               rows, cols, ld, box_rows, kind);
     return CFB_ERR_CUDA;
   }
+  if (cache.size() >= 4096) cache.clear();
   cache.emplace(key, tm);
   *out = tm;
   return CFB_OK;
 }
 
 int g_tc_tma_epi = 1;   // env CFB_TC_TMA_EPI=0 keeps the shared-memory-staged ld/st epilogue
-int g_tc_occ3 = 0;      // env CFB_TC_OCC3=0: 3-stage ring, 2 CTAs per SM instead of 2-stage ring, 3 CTAs per SM
 
 // The TMA epilogue takes one output copy and (for bf16) tiles at least one 64-column box wide.
 bool tma_epilogue_ok(const Epilogue& ep, int BN_) {
-  const bool tail = ep.ln_out != nullptr && ep.ln_counters != nullptr && ep.ln_tail;
-  return g_tc_tma_epi && ep.replicate == 1 && (ep.ln_out == nullptr || tail) &&
-         (BN_ >= 64 || !ep.out_bf16);
+  return g_tc_tma_epi && ep.replicate == 1 && (BN_ >= 64 || !ep.out_bf16);
 }
 
-template <int BN, int STAGES, int CN, int CM>
+template <int BN, int STAGES>
 int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep_in,
            cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   CUtensorMap ta, tb, to;
   Epilogue ep = ep_in;
-  CFB_TRY(get_map(A, M, K, lda, BM / CN, &ta));          // each CTA loads (and multicasts) a 1/CN slice of the A tile
-  CFB_TRY(get_map(W, w_rows, K, ldw, BN / CM, &tb));     // rows past w_rows read as zeros (TMA out-of-bounds fill)
+  CFB_TRY(get_map(A, M, K, lda, BM, &ta));
+  CFB_TRY(get_map(W, w_rows, K, ldw, BN, &tb));     // rows past w_rows read as zeros (TMA out-of-bounds fill)
   ep.tma_out = tma_epilogue_ok(ep, BN);
   if (ep.tma_out) CFB_TRY(get_map(ep.out, M, N, ep.ldo, 32, &to, ep.out_bf16 ? MAP_OUT_BF16 : MAP_OUT_F32));
   else to = ta;
-  dim3 grid(ceil_div(N, BN), ceil_div(ceil_div(M, BM), CM) * CM);   // whole clusters; surplus m-tiles store nothing
-  if constexpr (CN * CM == 1) {
-    if (ep.tma_out && g_tc_occ3)
-      launch_k(gemm_tc_tma_kernel<BN, 2, 3>, grid, NTHREADS, Smem<BN, 2>::TOTAL, st, ta, tb, to, M, N, K, ep);
-    else if (ep.tma_out)
-      launch_k(gemm_tc_tma_kernel<BN, STAGES, 2>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
-    else
-      launch_k(gemm_tc_kernel<BN, STAGES, 1, 1>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CN; attr[0].val.clusterDim.y = CM; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, CN, CM>, ta, tb, to, M, N, K, ep));
-  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  if (ep.tma_out) launch_k(gemm_tc_tma_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
+  else launch_k(gemm_tc_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -1115,25 +705,6 @@ int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int 
   return CFB_OK;
 }
 
-// [M,512] residual update + cluster LayerNorm: one 4-CTA cluster per 128-row block, PDL allowed.
-int launch_ln(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
-  using S = Smem<128, 3>;
-  CUtensorMap ta, tb;
-  CFB_TRY(get_map(A, M, K, lda, BM, &ta));
-  CFB_TRY(get_map(W, N, K, ldw, 128, &tb));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(4, ceil_div(M, BM)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
-  cfg.attrs = attr; cfg.numAttrs = 2;
-  CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_ln_kernel<128, 3>, ta, tb, M, N, K, ep));
-  CFB_LAUNCH_CHECK();
-  return CFB_OK;
-}
-
 template <int BN, int STAGES>
 int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
                    const Epilogue& ep_in, cudaStream_t st) {
@@ -1155,10 +726,8 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
   }
   if (max_rows <= 0) return CFB_OK;
   dim3 grid(ceil_div(N, BN), ceil_div(max_rows, BM), n_groups);
-  if (ep.tma_out && g_tc_occ3)
-    launch_k(gemm_tc_grouped_tma_kernel<BN, 2, 3>, grid, NTHREADS, Smem<BN, 2>::TOTAL, st, g, N, K, ep);
-  else if (ep.tma_out)
-    launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES, 2>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  if (ep.tma_out)
+    launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
   else
     launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
   CFB_LAUNCH_CHECK();
@@ -1167,42 +736,33 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
 
 }  // namespace
 
-int g_tc_cluster = 11;   // 10*CN_max + CM_max; 11 = no clusters
-
 int tc_trace_read(unsigned long long out[16]) {
   CFB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 16));
   return CFB_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per device (a process may hold
+// handles on several GPUs), outside any stream capture.
 int init_gemm_tc_kernels() {
-  static bool done = false;
   static std::mutex mu;     // handles may be created from several host threads (SamplerPool lanes)
+  static unsigned long long done_mask = 0;
   std::lock_guard<std::mutex> lock(mu);
-  if (done) return CFB_OK;
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
-  if (const char* e = getenv("CFB_TC_CLUSTER")) g_tc_cluster = atoi(e);
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && ((done_mask >> dev) & 1ull)) return CFB_OK;
   if (const char* e = getenv("CFB_TC_TMA_EPI")) g_tc_tma_epi = atoi(e);
-  if (const char* e = getenv("CFB_TC_OCC3")) g_tc_occ3 = atoi(e);
   if (const char* e = getenv("CFB_TC_2CTA")) g_tc_pair = atoi(e);
   if (const char* e = getenv("CFB_TC_2CTA_MIN_ROWS")) g_tc_pair_min_rows = atoi(e);
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 2>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 2>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_ln_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
-  done = true;
+  if (dev < 64) done_mask |= 1ull << dev;
   return CFB_OK;
 }
 
@@ -1227,30 +787,12 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   CFB_TRY(check_epilogue(ep));
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
-  if (ep.ln_out) {
-    CFB_CHECK(N == 512 && ep.ldo == 512 && !ep.out_bf16 && ep.replicate == 1 && ep.ln_g && ep.ln_b,
-              "gemm_tc: fused LayerNorm needs a float [M,512] output");
-    if (ep.ln_counters == nullptr) return launch_ln(A, lda, W, ldw, M, N, K, ep, st);   // cluster / DSMEM variant
-  }
   if (w_rows <= 0 || w_rows > N) w_rows = N;
-  if (ep.ln_out && ep.ln_tail) return launch<128, 3, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);   // tail needs plain CTAs
-  if (g_tc_pair && N % 256 == 0 && M >= g_tc_pair_min_rows && ep.ln_out == nullptr && tma_epilogue_ok(ep, 256))
+  if (g_tc_pair && N % 256 == 0 && M >= g_tc_pair_min_rows && tma_epilogue_ok(ep, 256))
     return launch_pair(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-  if (N % 128 == 0) {
-    // cluster shape: g_tc_cluster = 10*CN_max + CM_max (env CFB_TC_CLUSTER); CN must divide the number of n-tiles.
-    // Multicast pays when several tiles share an operand; a single m-tile (tiny M) gains nothing from CM.
-    const int n_tiles = N / 128, m_tiles = ceil_div(M, BM);
-    const int cn_max = g_tc_cluster / 10, cm_max = g_tc_cluster % 10;
-    const int cn = (cn_max >= 4 && n_tiles % 4 == 0) ? 4 : ((cn_max >= 2 && n_tiles % 2 == 0) ? 2 : 1);
-    const int cm = (cm_max >= 2 && m_tiles >= 2 && w_rows == N) ? 2 : 1;
-    if (cn == 4 && cm == 2) return launch<128, 3, 4, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-    if (cn == 2 && cm == 2) return launch<128, 3, 2, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-    if (cn == 4) return launch<128, 3, 4, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-    if (cn == 2) return launch<128, 3, 2, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-    return launch<128, 3, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-  }
-  if (N % 64 == 0) return launch<64, 4, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
-  return launch<32, 4, 1, 1>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  if (N % 64 == 0) return launch<64, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  return launch<32, 4>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
 }
 
 int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,

@@ -55,8 +55,10 @@ struct SharedAttnArgs {
   int ld_s, ld_p;
   int bs_offset;                        // batch entry of row 0 of S / P as passed to the launch
 };
-int softmax_shared(const float* S, bf16* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st);
-int shared_key_bias(const bf16* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
+template <typename TP>
+int softmax_shared(const float* S, TP* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st);
+template <typename T>
+int shared_key_bias(const T* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
                     const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
                     int n_layers, int n_tot, cudaStream_t st);
 template <typename T>
@@ -75,6 +77,7 @@ struct StepArgs {
   const float* preseq;     // [B, pl*lat] inpainting source or nullptr
   const float* inp_noise;  // [B, pl*lat]
   int n_branch, n_clips, n_per_clip, n_inpaint, n_steps, kind, clip_sample;
+  int full_last;           // the last evaluated branch is the weight-0 full-cond branch (convofusion.py:539)
   float guidance_scale;
 };
 int guidance_sched_step(const StepArgs& a, cudaStream_t st);

@@ -22,11 +22,15 @@ __global__ void __launch_bounds__(256) guidance_sched_kernel(StepArgs a) {
   const float e0 = a.eps[i];
   float eps = e0;
   if (a.n_branch > 1) {
-    // noise_pred_X = guidance_scale * 1 * (e_X - e_uncond); summed left to right
-    float acc = __fmul_rn(s, __fsub_rn(a.eps[(size_t)1 * total + i], e0));
-    for (int g = 2; g < 6; ++g) acc = __fadd_rn(acc, __fmul_rn(s, __fsub_rn(a.eps[(size_t)g * total + i], e0)));
-    if (a.n_branch == CFB_N_BRANCH)   // guidance_scale * 0 * (e_full - e_uncond)
-      acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(s, 0.0f), __fsub_rn(a.eps[(size_t)6 * total + i], e0)));
+    // noise_pred_X = guidance_scale * 1 * (e_X - e_uncond); summed left to right over the branches that were
+    // evaluated.  A single-modality branch whose conditioning equals the unconditional constant (monadic clips:
+    // the speaker stream, dataset.py:185-199) has e_X == e_uncond, its term is an exact zero and the caller drops it.
+    const int n_cond = a.n_branch - 1 - (a.full_last ? 1 : 0);
+    float acc = 0.0f;
+    if (n_cond > 0) acc = __fmul_rn(s, __fsub_rn(a.eps[(size_t)1 * total + i], e0));
+    for (int g = 2; g <= n_cond; ++g) acc = __fadd_rn(acc, __fmul_rn(s, __fsub_rn(a.eps[(size_t)g * total + i], e0)));
+    if (a.full_last)   // guidance_scale * 0 * (e_full - e_uncond)
+      acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(s, 0.0f), __fsub_rn(a.eps[(size_t)(a.n_branch - 1) * total + i], e0)));
     eps = __fadd_rn(e0, acc);
   }
   const float x = a.x[i];
@@ -69,7 +73,7 @@ __global__ void step_inc_kernel(int* p) {
 int guidance_sched_step(const StepArgs& a, cudaStream_t st) {
   const int total = a.n_clips * a.n_per_clip;
   if (total <= 0) return CFB_OK;
-  CFB_CHECK(a.n_branch == 1 || a.n_branch == 6 || a.n_branch == CFB_N_BRANCH, "guidance: n_branch must be 1, 6 or 7");
+  CFB_CHECK(a.n_branch >= 1 && a.n_branch <= CFB_N_BRANCH, "guidance: n_branch must be 1..7");
   launch_k(guidance_sched_kernel, ceil_div(total, 256), 256, 0, st, a);
   CFB_LAUNCH_CHECK();
   if (a.step_inc) {

@@ -276,7 +276,7 @@ class Denoiser(_CudaModule):
     # ---- memory description
     @staticmethod
     def _memory(enc: Sequence[Tensor], masks: Dict[str, Optional[Tensor]], slots: Optional[Sequence[Optional[Tensor]]],
-                keep: list) -> "_lib.Memory":
+                keep: list, slots_host: Optional[Sequence[Tensor]] = None) -> "_lib.Memory":
         mem = _lib.Memory()
         for x, (name, e) in enumerate(zip(STREAMS, enc)):
             if e.dim() != 3:
@@ -297,6 +297,12 @@ class Denoiser(_CudaModule):
                 s32 = s.to(device=e.device, dtype=torch.int32).contiguous()
                 keep.append(s32)
                 mem.slot[x] = s32.data_ptr()
+                if slots_host is not None:
+                    sh = slots_host[x].to(device="cpu", dtype=torch.int32).contiguous()
+                    if sh.numel() != s32.numel():
+                        raise ValueError("slots_host does not match slots")
+                    keep.append(sh)
+                    mem.slot_host[x] = sh.data_ptr()
         return mem
 
     # ---- reference surface
@@ -328,13 +334,16 @@ class Denoiser(_CudaModule):
 
     def sample(self, scheduler, enc: Sequence[Tensor], masks: Dict[str, Optional[Tensor]],
                slots: Sequence[Optional[Tensor]], latents: Tensor, num_steps: int, guidance_scale: float = 7.5,
-               eta: float = 0.0, n_branch: int = 7, step_noise: Optional[Tensor] = None,
+               eta: float = 0.0, n_branch: int = 7, full_last: Optional[bool] = None,
+               slots_host: Optional[Sequence[Tensor]] = None, step_noise: Optional[Tensor] = None,
                preseq: Optional[Tensor] = None, noise_scheduler=None, record: bool = False,
                return_attention: bool = False, use_graph: bool = True):
         """Whole guided reverse loop on the device (convofusion.py:391-549 / unbounded_synthesis.py:28-187).
 
         enc/masks/slots describe de-duplicated conditioning memory: enc[x] is [n_slots_x, M_x, 512] and
-        slots[x] [n_branch*B] picks the slot every (branch, clip) attends to.  `latents` [B,16,128] is the
+        slots[x] [n_branch*B] picks the slot every (branch, clip) attends to (`slots_host`: the same tables on the
+        host, so the library need not read them back); `full_last`: the last evaluated branch is the weight-0
+        full-cond one (default: n_branch == 7).  `latents` [B,16,128] is the
         initial noise already scaled by init_noise_sigma.  Returns (latents [B,16,128], record or None,
         attention maps or None)."""
         dev = self._device()
@@ -342,7 +351,9 @@ class Denoiser(_CudaModule):
         B = latents.shape[0]
         table = scheduler.step_table(num_steps, eta=eta, noise_scheduler=noise_scheduler)
         keep: list = []
-        mem = self._memory(enc, masks, slots, keep)
+        mem = self._memory(enc, masks, slots, keep, slots_host)
+        if full_last is None:
+            full_last = n_branch == 7
         x = latents.detach().to(device=dev, dtype=torch.float32).contiguous().clone()
         sched = _lib.Schedule()
         ts = np.ascontiguousarray(table["timesteps"], dtype=np.int64)
@@ -368,7 +379,7 @@ class Denoiser(_CudaModule):
             att_ptrs = (C.c_void_p * 5)(*[a.data_ptr() for a in att])
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().cfb_denoiser_set_chains(h, int(self.step_chains)))
-            _lib.check(_lib.lib().cfb_sample(h, C.byref(sched), C.byref(mem), B, n_branch, x.data_ptr(),
+            _lib.check(_lib.lib().cfb_sample(h, C.byref(sched), C.byref(mem), B, n_branch, int(bool(full_last)), x.data_ptr(),
                                              _lib.ptr(step_noise), _lib.ptr(preseq), pl, _lib.ptr(rec), att_ptrs,
                                              int(use_graph), _lib.stream_ptr()))
         return x, rec, att

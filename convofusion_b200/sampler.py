@@ -14,8 +14,8 @@ from typing import Dict, List, Optional, Sequence
 import torch
 from torch import Tensor, nn
 
-from .conditioning import (TextAudioController, TextAudioMotionFuser, expand_guidance_batch, guidance_memory,
-                           guidance_slots)
+from .conditioning import (TextAudioController, TextAudioMotionFuser, expand_guidance_batch, guidance_branches,
+                           guidance_memory, guidance_slots, guidance_slots_host)
 from .modules import ConvoFusionVae, Denoiser
 from .schedulers import DDIMScheduler, DDPMScheduler
 
@@ -130,17 +130,39 @@ class ConvoFusionSampler(nn.Module):
                                                           float(self.guidance_scale), _lib.stream_ptr()))
         return out
 
+    @staticmethod
+    def speaker_is_unconditional(clip: Dict[str, Tensor], uncond_text: Tensor, uncond_text_attn: Tensor) -> bool:
+        """True when the speaker text of EVERY clip is the unconditional prompt (monadic BEAT clips: dataset.py:185-199
+        feeds '-'*10 for the absent speaker), i.e. guidance branch 3 (speaker-only) repeats branch 0.  Callers that
+        know (the data loader does) pass clip["spk_is_uncond"]; otherwise the features are compared on the device,
+        which costs one read-back per call."""
+        hint = clip.get("spk_is_uncond")
+        if hint is not None:
+            return bool(hint)
+        t, a = clip["text_spk"], clip["text_spk_attn"]
+        same = (t == uncond_text.to(t.device).unsqueeze(0)).all() & (a == uncond_text_attn.to(a.device).unsqueeze(0)).all()
+        return bool(same)
+
     @torch.no_grad()
     def sample(self, enc: Sequence[Tensor], masks: Dict[str, Optional[Tensor]], n_clips: int,
                init_latents: Tensor, preseq: Optional[Tensor] = None, step_noise: Optional[Tensor] = None,
-               record: bool = False, return_attention: bool = False, use_graph: bool = True):
+               record: bool = False, return_attention: bool = False, use_graph: bool = True,
+               spk_is_uncond: bool = False):
         """Fused path: the whole reverse loop in one C call.  enc/masks are the de-duplicated slots from
-        `encode_conditions`.  Returns (z [16,B,128] like _diffusion_reverse, record, attention)."""
-        n_branch = 7 if return_attention else 6      # the full-cond branch has guidance weight 0 (convofusion.py:539)
-        slots = guidance_slots(n_clips, n_branch, init_latents.device)
+        `encode_conditions`.  Returns (z [16,B,128] like _diffusion_reverse, record, attention).
+
+        Branches evaluated (`guidance_branches`): the weight-0 full-cond branch only when its attention maps are asked
+        for (convofusion.py:539); the speaker-only branch only when the speaker stream is conditional
+        (`spk_is_uncond=False`).  Both omissions are exact: the dropped terms are zeros in convofusion.py:527-541."""
+        if not self.do_classifier_free_guidance:
+            # convofusion.py:398-401,527: guidance_scale <= 1 runs ONE conditional branch and no combine
+            raise NotImplementedError("guidance_scale <= 1 (no classifier-free guidance) is not on the B200 hot path")
+        branches = guidance_branches(return_attention, spk_is_uncond)
+        slots = guidance_slots(n_clips, branches, init_latents.device)
         x = init_latents * self.scheduler.init_noise_sigma
         lat, rec, att = self.denoiser.sample(self.scheduler, enc, masks, slots, x, self.num_inference_timesteps,
-                                             guidance_scale=self.guidance_scale, eta=self.eta, n_branch=n_branch,
+                                             guidance_scale=self.guidance_scale, eta=self.eta, n_branch=len(branches),
+                                             full_last=return_attention, slots_host=guidance_slots_host(n_clips, branches),
                                              step_noise=step_noise, preseq=preseq, noise_scheduler=self.noise_scheduler,
                                              record=record, return_attention=return_attention, use_graph=use_graph)
         return lat.permute(1, 0, 2), rec, att
@@ -157,6 +179,7 @@ class ConvoFusionSampler(nn.Module):
     def generate(self, clip: Dict[str, Tensor], uncond_text: Tensor, uncond_text_attn: Tensor, lengths: List[int],
                  init_latents: Tensor, **kw):
         """test_diffusion_forward (convofusion.py:817-1036) for one batch of featurised clips."""
+        kw.setdefault("spk_is_uncond", self.speaker_is_unconditional(clip, uncond_text, uncond_text_attn))
         enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
         z, rec, att = self.sample(enc, masks, init_latents.shape[0], init_latents, **kw)
         return {"m_rst": self.decode(z, lengths), "lat_t": z, "record": rec, "test_attention_maps": att}
@@ -173,7 +196,8 @@ class ConvoFusionSampler(nn.Module):
         for k, clip in enumerate(windows):
             B = clip["mel_lsn"].shape[0]
             enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
-            z, _, _ = self.sample(enc, masks, B, init_noise[k], preseq=preseq, use_graph=use_graph)
+            z, _, _ = self.sample(enc, masks, B, init_noise[k], preseq=preseq, use_graph=use_graph,
+                                  spk_is_uncond=self.speaker_is_unconditional(clip, uncond_text, uncond_text_attn))
             preseq = z[z.shape[0] // 2:].permute(1, 0, 2).contiguous()
             feats = self.decode(z, [WINDOW_FRAMES] * B)
             if prev is not None:

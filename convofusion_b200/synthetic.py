@@ -53,9 +53,11 @@ def synthetic_clip(n_clips: int, seed: int = 1234, dyadic: bool = False, text_le
         clip["text_spk"] = torch.randn(B, Lt, 768, generator=g)
         spk_valid = torch.randint(8, Lt + 1, (B,), generator=g)
         clip["text_spk_attn"] = (torch.arange(Lt)[None, :] < spk_valid[:, None]).long()
+        clip["spk_is_uncond"] = False
     else:        # monadic BEAT: speaker stream is the unconditional prompt (dataset.py:185-199)
         clip["text_spk"] = uncond_text.unsqueeze(0).repeat(B, 1, 1)
         clip["text_spk_attn"] = uncond_attn.unsqueeze(0).repeat(B, 1)
+        clip["spk_is_uncond"] = True      # the data loader knows (dataset.py:185-199); see ConvoFusionSampler.sample
     return {"clip": clip, "uncond_text": uncond_text, "uncond_text_attn": uncond_attn}
 
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CFB_ABI_VERSION 1
+#define CFB_ABI_VERSION 2
 #define CFB_N_STREAMS 5      /* spkemb, alsn, tlsn, apb, lsnemb: cross_attention.py:579 */
 #define CFB_N_BRANCH 7       /* clf_guidance_drops + 1: convofusion.py:60,399-401 */
 
@@ -48,6 +48,10 @@ int cfb_abi_version(void);
 const char* cfb_last_error(void);
 /* Which GEMM engine bf16 contractions use (AUTO = tcgen05 whenever the shape allows). */
 int cfb_set_gemm_backend(int backend);
+/* Execution strategy of cfb_sample when slot tables are given: 1 (default) = shared-slot plan (memory-side
+ * pre-projection of the unconditional slot), 0 = general per-pair path.  Same results up to
+ * floating-point summation order; exposed so the tests can compare the two. */
+int cfb_set_shared_plan(int enabled);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);
 
@@ -98,11 +102,14 @@ typedef struct {
 /* Conditioning memory of one call.  cond[x]: [n_slots[x], len[x], d] float, batch-first as
  * returned by TextAudioMotionFuser.forward (condfuser.py:32-51); mask[x]: [n_slots[x], len[x]]
  * bytes, 1 = ignore (key_padding_mask, cross_attention.py:587-591) or NULL; slot[x]: [n_rows/
- * n_tokens] int32 mapping each denoiser batch entry to a slot, or NULL for identity. */
+ * n_tokens] int32 mapping each denoiser batch entry to a slot, or NULL for identity; slot_host[x]:
+ * optional HOST copy of slot[x] (cfb_sample derives its execution plan from the tables: with a host
+ * copy it does not have to read them back from the device). */
 typedef struct {
   const float   *cond[CFB_N_STREAMS];
   const uint8_t *mask[CFB_N_STREAMS];
   const int32_t *slot[CFB_N_STREAMS];
+  const int32_t *slot_host[CFB_N_STREAMS];
   int32_t n_slots[CFB_N_STREAMS];
   int32_t len[CFB_N_STREAMS];
 } cfb_memory;
@@ -146,7 +153,12 @@ typedef struct {
  * n_steps loop (7-branch guidance + scheduler step [+ latent inpainting]) on the device.
  *   n_clips      B; the denoiser batch is n_branch*B rows of n_tokens, branch-major like
  *                torch.cat([latents]*7) (convofusion.py:499)
- *   n_branch     7 = evaluate every branch; 6 = skip the weight-0 full-cond branch
+ *   n_branch     guidance branches evaluated (1..7), in the reference's order (convofusion.py:910) with any subset of
+ *                the single-modality branches left out: a branch whose conditioning equals the unconditional
+ *                constant contributes guidance_scale * (e_uncond - e_uncond) = 0 exactly (monadic BEAT clips: the
+ *                speaker branch, dataset.py:185-199).  Branch 0 is always the all-unconditional one.
+ *   full_last    1 = the last evaluated branch is the weight-0 full-cond branch (convofusion.py:539; needed only for
+ *                attention maps), 0 = it is skipped
  *   mem          slot[x] has n_branch*B entries
  *   latents      in: initial noise * init_noise_sigma [B, n_tokens, latent]; out: final latents
  *   step_noise   [n_steps, B, n_tokens, latent] or NULL (DDPM / eta>0 noise)
@@ -156,12 +168,14 @@ typedef struct {
  *   use_graph    replay one captured CUDA graph per step instead of launching kernels
  */
 int cfb_sample(cfb_denoiser *h, const cfb_schedule *sched, const cfb_memory *mem, int n_clips,
-               int n_branch, float *latents, const float *step_noise, const float *preseq,
+               int n_branch, int full_last, float *latents, const float *step_noise, const float *preseq,
                int preseq_len, float *record, float *const att_out[CFB_N_STREAMS], int use_graph,
                cfb_stream stream);
 
 /* Fused 7-way guidance combine + scheduler step (convofusion.py:527-545 + diffusers step()).
- * eps [n_branch, B, n] ; x [B, n] in/out; coef = one device row of 8 floats as above. */
+ * eps [n_branch, B, n] ; x [B, n] in/out; coef = one device row of 8 floats as above.
+ * n_branch 1..7: branch 0 unconditional, the others single-modality branches; 7 = the last one is the weight-0
+ * full-cond branch. */
 int cfb_guidance_sched_step(const float *eps, float *x, const float *noise, const float *coef_dev,
                             int n_branch, int n_clips, int n_per_clip, int kind, int clip_sample,
                             float guidance_scale, cfb_stream stream);

@@ -112,6 +112,16 @@ def test_guidance_slots_reproduce_the_seven_branch_batch():
             cond = g == 6 or BRANCH_STREAM.get(g) == x
             assert s[g].tolist() == ([1, 2, 3] if cond else [0, 0, 0])
     assert all(len(s) == 6 * B for s in guidance_slots(B, 6, "cpu"))
+    # monadic clips: the speaker-only branch (3) is left out, the remaining branches keep their order
+    from convofusion_b200.conditioning import guidance_branches, guidance_slots_host
+    assert guidance_branches() == [0, 1, 2, 3, 4, 5] and guidance_branches(True) == [0, 1, 2, 3, 4, 5, 6]
+    br = guidance_branches(True, spk_is_uncond=True)
+    assert br == [0, 1, 2, 4, 5, 6]
+    mono = guidance_slots(B, br, "cpu")
+    for x in range(5):
+        assert mono[x].view(6, B).tolist() == [slots[x].view(7, B)[g].tolist() for g in br]
+        assert torch.equal(mono[x], guidance_slots_host(B, br)[x])
+    assert mono[0].view(6, B)[:5].sum() == 0      # no branch but the full one conditions on the speaker
     # gathering slots == torch.cat([...]*7) ordering of convofusion.py:911-929
     enc = [torch.arange(4.0).view(4, 1, 1).expand(4, 2, 3).contiguous() + 10 * x for x in range(5)]
     masks = {"tlsn": torch.tensor([[1, 1], [0, 1], [0, 0], [1, 0]]).bool(), "spkemb": None, "alsn": None}
@@ -135,13 +145,13 @@ def test_abi_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cfb_abi_version() == 1
+    assert lib.cfb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.DenoiserLayer) == 26 * 8
     assert ctypes.sizeof(_lib.DenoiserWeights) == 8 * 4 + 30 * 8
-    assert ctypes.sizeof(_lib.Memory) == 15 * 8 + 10 * 4
+    assert ctypes.sizeof(_lib.Memory) == 20 * 8 + 10 * 4
     assert ctypes.sizeof(_lib.Schedule) == 16 + 16
     assert ctypes.sizeof(_lib.VaeLayer) == 20 * 8
     assert ctypes.sizeof(_lib.VaeDecoder) == 8 + 32 + 32 + 32 + 8
