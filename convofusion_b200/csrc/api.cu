@@ -1,6 +1,7 @@
 // Library-level C ABI: error reporting, switches, and the unit-op entry points the tests use.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rowblock.cuh"
 #include <cstdlib>
 
 namespace cfb {
@@ -39,6 +40,14 @@ extern "C" {
 
 // Debug only (not part of include/convofusion_b200.h): phase timestamps of the last traced tcgen05 GEMM CTA.
 int cfb_debug_tc_trace(unsigned long long* out16) { return cfb::tc_trace_read(out16); }
+
+// Debug only: fault record of the row-block kernel's guarded barrier waits {code, block, warp, stage, barrier, parity};
+// host-mapped memory, readable after the context has been lost to the trap.
+int cfb_debug_rb_fault(unsigned* out8) {
+  const unsigned* f = cfb::rowblock_fault_record();
+  for (int i = 0; i < 8; ++i) out8[i] = f ? f[i] : 0u;
+  return CFB_OK;
+}
 
 int cfb_abi_version(void) { return CFB_ABI_VERSION; }
 const char* cfb_last_error(void) { return g_err; }

@@ -14,6 +14,7 @@
 // T = float (fp32 parity mode) or bf16 (tensor-core mode).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rowblock.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdlib>
@@ -44,6 +45,10 @@ struct DeviceBuf {
 
 namespace cfb {
 int g_shared_plan = getenv("CFB_PLAN") ? atoi(getenv("CFB_PLAN")) : 1;   // cfb_set_shared_plan / env CFB_PLAN=0
+// Row-block kernel (rowblock.cu) for the residual chains of a layer; bit 0: out_proj -> TimeBlock 1 -> norm2,
+// bit 1: shared values (+ conditional fuser block) -> TimeBlock 2 -> norm3, bit 2: linear2 -> next norm1.
+// cfb_set_rowblock / env CFB_ROWBLOCK (0 = the one-kernel-per-operator path everywhere).
+int g_rowblock = getenv("CFB_ROWBLOCK") ? atoi(getenv("CFB_ROWBLOCK")) : 7;
 }
 
 using namespace cfb;
@@ -73,6 +78,13 @@ struct cfb_denoiser {
   cudaStream_t chain_st[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
   int n_chains = 1;
+  // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
+  DeviceBuf rb_prog, rb_blk;
+  std::vector<RbStage> rb_host;
+  std::vector<int> rb_blk_host;
+  int rb_off[3] = {0, 0, 0}, rb_len[3] = {0, 0, 0};   // first stage / stage count of program kind k of layer 0
+  int rb_per_layer = 0, rb_mask = 0;
+  struct RbKey { unsigned epoch; int rows, k_tot, mask; } rb_key = {~0u, 0, 0, 0};
   // device-resident schedule tables of the last cfb_sample call (see cfb_sample)
   std::vector<float> sched_ts, sched_coef;
   unsigned sched_epoch = ~0u;
@@ -173,6 +185,117 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
   return CFB_OK;
 }
 
+// ---- row-block programs -------------------------------------------------------------------------------------------
+// Per layer three programs over the same 128-row blocks (stage kinds in rowblock.cuh):
+//   kind 0  [load h] out_proj (A = self-attention output) -> LN/modulate/SiLU -> TimeBlock 1 -> norm2      -> h, a
+//   kind 1  [load h] conditional fuser block (A = per-pair attention output; blocks with a conditional stream only)
+//           -> shared values (A = P, K = k_tot) -> LN/modulate/SiLU -> TimeBlock 2 -> norm3                -> h, a
+//   kind 2  [load h] linear2 in K halves (A = GELU(linear1)) -> next layer's norm1 / decoder.norm          -> h, a
+// The tensor maps cover whole workspace buffers (absolute rows), so one set serves every chain of the step.
+int build_rowblock_programs(cfb_denoiser* h, int n_batch, int n_clips, const SharedPlan& sp, bool want_att, cudaStream_t st) {
+  h->rb_mask = 0;
+  const int R = n_batch * h->ntok;
+  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT || g_rowblock == 0 || R % 128 != 0 || h->d != 512 ||
+      h->ff % 512 != 0 || h->ntok != 16)
+    return CFB_OK;
+  int mask = g_rowblock & 5;
+  const int n_blocks = R / 128;
+  std::vector<int> blk(n_blocks, -1);
+  bool r2_ok = sp.on && !want_att && n_clips % 8 == 0 && sp.k_tot <= 512 && sp.k_tot % 64 == 0;
+  if (r2_ok) {
+    for (int z = 0; z < sp.n_groups && r2_ok; ++z) {
+      if (sp.g_row_start[z] % 128 != 0 || sp.g_rows[z] % 128 != 0) { r2_ok = false; break; }
+      for (int b = sp.g_row_start[z] / 128; b < (sp.g_row_start[z] + sp.g_rows[z]) / 128; ++b) {
+        if (blk[b] >= 0) { r2_ok = false; break; }            // two conditional streams on one block
+        blk[b] = sp.g_stream[z];
+      }
+    }
+  }
+  if (r2_ok) mask |= g_rowblock & 2;
+  if (mask == 0) return CFB_OK;
+  CFB_TRY(init_rowblock_kernels());
+  const cfb_denoiser::RbKey key{h->epoch, R, sp.on ? sp.k_tot : 0, mask};
+  if (memcmp(&key, &h->rb_key, sizeof(key)) == 0 && blk == h->rb_blk_host) { h->rb_mask = mask; return CFB_OK; }
+  const int d = h->d, nff = h->ff / 512;
+  std::vector<RbStage>& pr = h->rb_host;
+  pr.clear();
+  auto stage = [&](int kind) { RbStage s; memset(&s, 0, sizeof(s)); s.kind = kind; return s; };
+  auto gemm_stage = [&](const void* W, int w_rows, int w_cols, int ldw, int w_col0, int K, RbStage* out) -> int {
+    RbStage s = stage(RB_GEMM);
+    s.K = K; s.N = d; s.w_col0 = w_col0;
+    CFB_TRY(rowblock_operand_map(W, w_rows, w_cols, ldw, &s.map_w));
+    *out = s;
+    return CFB_OK;
+  };
+  auto a_tma = [&](RbStage& s, const void* A, int cols, int col0) -> int {
+    s.a_src = RB_A_TMA; s.a_col0 = col0;
+    return rowblock_operand_map(A, R, cols, cols, &s.map_a);
+  };
+  auto ln_epi = [&](RbStage& s, const float* bias, const float* g, const float* b, const float* mod, bool last) {
+    s.epi = RB_EPI_LN; s.bias = bias; s.ln_g = g; s.ln_b = b; s.mod = mod; s.ln_silu = mod != nullptr;
+    s.mod_stride = (long long)h->L * 2 * 2 * d;
+    if (last) { s.spill = 1; s.store_a = 1; }
+  };
+  for (int l = 0; l < h->L; ++l) {
+    const cfb_denoiser_layer& w = h->layers[l];
+    const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
+    const float* mod2 = mod1 + 2 * d;
+    const size_t first = pr.size();
+    RbStage s;
+    // kind 0
+    if (l == 0) h->rb_off[0] = (int)pr.size();
+    pr.push_back(stage(RB_HLOAD));
+    CFB_TRY(gemm_stage(w.w_so, d, d, d, 0, d, &s)); CFB_TRY(a_tma(s, h->a.p, d, 0)); ln_epi(s, w.b_so, w.tb1_g, w.tb1_b, mod1, false); pr.push_back(s);
+    CFB_TRY(gemm_stage(w.w_tb1, d, d, d, 0, d, &s)); ln_epi(s, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, true); pr.push_back(s);
+    if (l == 0) h->rb_len[0] = (int)pr.size() - h->rb_off[0];
+    // kind 1
+    if (l == 0) h->rb_off[1] = (int)pr.size();
+    if (mask & 2) {
+      pr.push_back(stage(RB_HLOAD));
+      CFB_TRY(gemm_stage(w.w_fu, d, CFB_N_STREAMS * d, CFB_N_STREAMS * d, 0, d, &s));
+      CFB_TRY(a_tma(s, h->uc.p, CFB_N_STREAMS * d, 0)); s.per_stream = 1; pr.push_back(s);
+      CFB_TRY(gemm_stage(h->ytall.as<bf16>() + (size_t)l * d * sp.k_tot, d, sp.k_tot, sp.k_tot, 0, sp.k_tot, &s));
+      CFB_TRY(a_tma(s, h->sP.p, sp.k_tot, 0)); ln_epi(s, w.b_fu, w.tb2_g, w.tb2_b, mod2, false); pr.push_back(s);
+      CFB_TRY(gemm_stage(w.w_tb2, d, d, d, 0, d, &s)); ln_epi(s, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, true); pr.push_back(s);
+    }
+    if (l == 0) h->rb_len[1] = (int)pr.size() - h->rb_off[1];
+    // kind 2
+    if (l == 0) h->rb_off[2] = (int)pr.size();
+    pr.push_back(stage(RB_HLOAD));
+    const bool last_layer = l + 1 == h->L;
+    for (int c = 0; c < nff; ++c) {
+      CFB_TRY(gemm_stage(w.w_ff2, d, h->ff, h->ff, c * 512, 512, &s));
+      CFB_TRY(a_tma(s, h->f.p, h->ff, c * 512));
+      if (c + 1 == nff)
+        ln_epi(s, w.b_ff2, last_layer ? h->w.lnf_g : h->layers[l + 1].ln1_g, last_layer ? h->w.lnf_b : h->layers[l + 1].ln1_b,
+               nullptr, true);
+      pr.push_back(s);
+    }
+    if (l == 0) { h->rb_len[2] = (int)pr.size() - h->rb_off[2]; h->rb_per_layer = (int)(pr.size() - first); }
+  }
+  CFB_TRY(h->rb_prog.reserve(pr.size() * sizeof(RbStage), &h->epoch));   // captured graphs hold these pointers
+  CFB_TRY(h->rb_blk.reserve((size_t)n_blocks * 4, &h->epoch));
+  h->rb_blk_host = blk;
+  CFB_CUDA(cudaMemcpyAsync(h->rb_prog.p, pr.data(), pr.size() * sizeof(RbStage), cudaMemcpyHostToDevice, st));
+  CFB_CUDA(cudaMemcpyAsync(h->rb_blk.p, h->rb_blk_host.data(), (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
+  CFB_CUDA(cudaStreamSynchronize(st));
+  h->rb_key = key;
+  h->rb_key.epoch = h->epoch;
+  h->rb_mask = mask;
+  return CFB_OK;
+}
+
+int rowblock_run(cfb_denoiser* h, int layer, int kind, int row0, int R, int rows_total, const int* step_ptr, cudaStream_t st) {
+  RbLaunch L{};
+  L.prog = h->rb_prog.as<RbStage>() + (size_t)layer * h->rb_per_layer + h->rb_off[kind];
+  L.n_stages = h->rb_len[kind];
+  L.block0 = row0 / 128; L.n_blocks = R / 128;
+  L.blk_stream = h->rb_blk.as<int>();
+  L.step_ptr = step_ptr;
+  L.h = h->h.as<float>(); L.a = h->a.as<bf16>(); L.rows_total = rows_total;
+  return rowblock_launch(L, st);
+}
+
 // Optional concurrency inside one chain (all null = strictly sequential on `st`).
 struct ChainAux {
   cudaStream_t st2 = nullptr;          // conditional-pair projection + attention run here, next to the shared-slot path
@@ -186,7 +309,7 @@ struct ChainAux {
 template <typename T>
 int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
                float* eps_out_all, cudaStream_t st, const SharedPlan* sp = nullptr, int b0 = 0, int n_batch_total = 0,
-               const ChainAux* aux = nullptr) {
+               const ChainAux* aux = nullptr, bool use_rb = false) {
   if (n_batch_total <= 0) n_batch_total = n_batch;
   const ChainAux no_aux;
   if (!aux) aux = &no_aux;
@@ -202,6 +325,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   float* eps_out = eps_out_all + (size_t)row0 * h->lat;
   ca.bs_offset = b0;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
+  // row-block kernel for the residual chains: whole 128-row blocks of a plan-driven bf16 step only
+  const int rb = (sizeof(T) == 2 && use_rb && row0 % 128 == 0 && R % 128 == 0) ? h->rb_mask : 0;
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
     return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
@@ -228,12 +353,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     // self-attention block (cross_attention.py:568-572); a = norm1(h) on entry
     CFB_TRY(lin_T(a, d, w.w_in, w.b_in, qkv, 3 * d, 0));
     CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
-    CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1));          // + time_block1 prologue (:575)
-    CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr));     // + norm2 (:578)
+    if (rb & 1) {   // out_proj -> time_block1 -> norm2 on resident rows (rowblock.cu)
+      CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
+    } else {
+      CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1));          // + time_block1 prologue (:575)
+      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr));     // + norm2 (:578)
+    }
     // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
     for (int x = 0; x < CFB_N_STREAMS; ++x)
       ca.att[x] = att_base && att_base[x] ? att_base[x] + (size_t)l * h->ntok * ca.len[x] : nullptr;
-    bool shared_done = false;
+    bool shared_done = false, rb2_done = false;
     if (sp && sp->on) {
       const int Ld = h->L * d;
       if (l == 0)
@@ -313,10 +442,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       }
       sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
       CFB_TRY(softmax_shared<T>(sS, sP, sa, n_batch, h->ntok, st));
-      Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-      CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
-      CFB_TRY(cond_fuser());
-      CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+      if (rb & 2) {   // fuser block + shared values -> time_block2 -> norm3 on resident rows (rowblock.cu)
+        if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
+        CFB_TRY(rowblock_run(h, l, 1, row0, R, R_total, step_ptr, st));
+        rb2_done = true;
+      } else {
+        Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
+        CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
+        CFB_TRY(cond_fuser());
+        CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+      }
       shared_done = true;
     }
     if (!shared_done) {
@@ -324,12 +459,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
       CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2));   // + time_block2 prologue (:655)
     }
-    CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr));      // + norm3 (:659)
+    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr));      // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
     CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU));
     const bool last = l + 1 == h->L;
-    CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
-                       last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr));
+    if (rb & 4) {   // linear2 -> next norm1 on resident rows (rowblock.cu)
+      CFB_TRY(rowblock_run(h, l, 2, row0, R, R_total, step_ptr, st));
+    } else {
+      CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
+                         last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr));
+    }
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
@@ -436,7 +575,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
     ChainAux aux;
     if (overlap) { aux.ev_pre[0] = h->ev_pre[0]; aux.ev_pre[1] = h->ev_pre[1]; }
     CFB_TRY(embed_rows<T>(h, 0, n_batch, n_clips, st));
-    CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp, 0, n_batch, &aux));
+    CFB_TRY(run_layers<T>(h, n_batch, ca, att_base, step_ptr, h->eps.as<float>(), st, &sp, 0, n_batch, &aux, true));
   } else {
     CFB_CUDA(cudaEventRecord(h->ev_fork, st));
     for (int c = 0; c < nc; ++c) {
@@ -449,7 +588,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
         aux.st2 = h->chain_st2[c]; aux.ev_a = h->ev_a[c]; aux.ev_b = h->ev_b[c];
       }
       CFB_TRY(embed_rows<T>(h, b0, nb, n_clips, cs));
-      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux));
+      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux, true));
       if (c > 0) {
         CFB_CUDA(cudaEventRecord(h->ev_join[c], cs));
         CFB_CUDA(cudaStreamWaitEvent(st, h->ev_join[c], 0));
@@ -577,9 +716,14 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->ev_sched) cudaEventDestroy(h->ev_sched);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk};
   for (DeviceBuf* b : bufs) b->release();
   delete h;
+}
+
+int cfb_set_rowblock(int mask) {
+  g_rowblock = mask & 7;
+  return CFB_OK;
 }
 
 int cfb_set_shared_plan(int enabled) {
@@ -679,6 +823,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
   SharedPlan sp;
   CFB_TRY(make_shared_plan(h, mem, n_batch, &sp, st));
+  CFB_TRY(build_rowblock_programs(h, n_batch, n_clips, sp, want_att, st));
   {
     const char* e = getenv("CFB_CHAINS");
     int want = h->chains_override > 0 ? h->chains_override : e ? atoi(e) : 6;
@@ -750,7 +895,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask; key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }
@@ -772,6 +917,10 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       if (ce != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return CFB_ERR_CUDA; }
       h->graph_key = key; h->graph_valid = true;
       h->graph_nodes = n_nodes;
+      static const bool verbose = getenv("CFB_VERBOSE") && atoi(getenv("CFB_VERBOSE"));
+      if (verbose)
+        fprintf(stderr, "[cfb] handle %p: captured a step graph (%zu nodes; %d clips x %d branches, %d chains, plan %d)\n",
+                (void*)h, n_nodes, n_clips, n_branch, h->n_chains, (int)sp.on);
     }
     for (int i = 0; i < S; ++i) CFB_CUDA(cudaGraphLaunch(h->graph_exec, st));
     g_launches += (unsigned long long)S * h->graph_nodes;

@@ -736,6 +736,12 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
 
 }  // namespace
 
+// tensor maps for the other tcgen05 kernels (rowblock.cu): kind 0 = bf16 operand box 64 x box_rows, 1 = fp32 box
+// 32 x box_rows, 2 = bf16 output box 64 x box_rows
+int tc_get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int kind) {
+  return get_map(p, rows, cols, ld, box_rows, out, kind);
+}
+
 int tc_trace_read(unsigned long long out[16]) {
   CFB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 16));
   return CFB_OK;

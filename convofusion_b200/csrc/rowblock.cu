@@ -1,0 +1,435 @@
+// Row-block kernel (sm_100a): one persistent, warp-specialised tcgen05 CTA owns 128 rows (= 8 batch entries x 16
+// tokens) of the denoiser's query side and runs a PROGRAM of dependent stages on them without leaving the SM:
+//
+//   residual load     h[128, 512] fp32: global -> (TMA boxes) shared -> tcgen05.st -> tensor memory (all 512 columns)
+//   residual GEMM     h += A . W^T: tcgen05.mma accumulates straight onto the resident residual rows in tensor memory
+//                     (the residual add costs nothing and the SM never re-reads h); A [128, K<=512] bf16 is resident in
+//                     shared memory (8 K-panels of 16 KB, 128B-swizzled K-major = the UMMA / TMA layout), W streams
+//                     through a ring of 128 x 64 tiles (TMA), K-outer / N-inner so every A panel is consumed once
+//   LayerNorm         epilogue warps read the updated rows back (tcgen05.ld, one row per thread: statistics need no
+//                     shuffles), add the bias, normalise (+ TimeBlock modulation + SiLU), and write the NEXT stage's A
+//                     operand directly into the swizzled shared-memory panels; the rows stay parked in tensor memory
+//                     for the next residual GEMM; optionally they are spilled (fp32, TMA store) / the operand is
+//                     stored (bf16, TMA store) for the kernels that follow
+//
+// Replaces, per layer and per 128-row block, chains such as  out_proj GEMM -> LayerNorm/modulate/SiLU -> TimeBlock GEMM
+// -> LayerNorm  (4 launches, 2 L2 round trips of the residual, 2 of the operand) by one launch whose only global
+// traffic is the weights, one load and one store of the rows.  cross_attention.py:568-661.
+//
+// Warp roles (320 threads, one CTA per SM: 193 KB of shared memory + all 512 tensor-memory columns):
+//   warp 0      TMA producer: residual boxes, A panels, W tiles
+//   warp 1      tensor-memory allocation + MMA issue (one elected lane)
+//   warps 2..9  epilogue: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+// All roles walk the same program; every mbarrier has exactly one waiter per completed phase (parities are tracked
+// locally).  Waits are guarded: a protocol error writes a fault record to host-mapped memory and traps instead of
+// hanging the GPU.
+#include "rowblock.cuh"
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+#include <mutex>
+
+namespace cfb {
+
+int tc_get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensorMap* out, int kind);   // gemm_tc.cu
+
+namespace {
+
+using namespace tc;
+
+constexpr int RB_THREADS = 320;
+constexpr int PANEL = 128 * 128;              // 128 rows x 64 bf16
+constexpr int N_PANELS = 8;
+constexpr int A_BYTES = N_PANELS * PANEL;     // 128 KB
+constexpr int W_TILE = 128 * 128;             // 128 weight rows x 64 bf16
+constexpr int W_STAGES = 4;
+constexpr int STG_BOX = 4096;                 // 32 rows x 128 B
+constexpr int OFF_W = A_BYTES;
+constexpr int OFF_STG = OFF_W + W_STAGES * W_TILE;
+constexpr int OFF_BAR = OFF_STG + 8 * STG_BOX;
+constexpr int RB_SMEM = OFF_BAR + 512 + 1024;
+static_assert(RB_SMEM <= 232448, "row-block kernel exceeds the 227 KB shared-memory limit");
+
+// barrier slots (8 bytes each) inside the barrier area
+constexpr int B_W_FULL = 0, B_W_EMPTY = 4, B_A_FULL = 8, B_A_EMPTY = 16, B_ACC_FULL = 24, B_EPI_DONE = 25,
+              B_HL_FULL = 26, B_HL_EMPTY = 34, B_TMEM_SLOT = 42;
+
+struct RbParams {
+  const RbStage* prog;
+  int n_stages;
+  int block0;
+  const int* blk_stream;
+  const int* step_ptr;
+  unsigned* fault;
+};
+
+__device__ __forceinline__ void rb_wait(uint32_t bar, uint32_t parity, const RbParams& p, int stage, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) {       // ~3 s: a protocol error, not a slow kernel
+      if (p.fault) {
+        p.fault[1] = blockIdx.x; p.fault[2] = threadIdx.x >> 5; p.fault[3] = (unsigned)stage; p.fault[4] = bar;
+        p.fault[5] = parity; p.fault[0] = (unsigned)code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool rb_skip(const RbStage& s, int x) { return s.per_stream != 0 && x < 0; }
+__device__ __forceinline__ int rb_next(const RbStage* prog, int n, int i, int x) {
+  for (int j = i + 1; j < n; ++j)
+    if (!rb_skip(prog[j], x)) return j;
+  return -1;
+}
+// the stage after GEMM stage i overwrites the A panels through the TMA producer (A load or residual landing zone)
+__device__ __forceinline__ bool rb_commit_a(const RbStage* prog, int n, int i, int x) {
+  const int j = rb_next(prog, n, i, x);
+  return j >= 0 && (prog[j].kind == RB_HLOAD || prog[j].a_src == RB_A_TMA);
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_constant__ CUtensorMap tm_h,
+                                                                  const __grid_constant__ CUtensorMap tm_a, RbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sW = base + OFF_W, sStg = base + OFF_STG, bars = base + OFF_BAR;
+  auto bar = [&](int slot) { return bars + 8u * (uint32_t)slot; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = p.block0 + (int)blockIdx.x;
+  const int row0 = blk * 128;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_h) : "memory");
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar(B_W_FULL + s), 1); mbar_init(bar(B_W_EMPTY + s), 1); }
+    for (int k = 0; k < N_PANELS; ++k) { mbar_init(bar(B_A_FULL + k), 1); mbar_init(bar(B_A_EMPTY + k), 1); }
+    mbar_init(bar(B_ACC_FULL), 1);
+    mbar_init(bar(B_EPI_DONE), 8);
+    for (int w = 0; w < 8; ++w) { mbar_init(bar(B_HL_FULL + w), 1); mbar_init(bar(B_HL_EMPTY + w), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(bar(B_TMEM_SLOT), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * B_TMEM_SLOT);
+  pdl_sync();   // everything above touched only shared / tensor memory
+  const int x = p.blk_stream ? p.blk_stream[blk] : -1;
+  const int n_stages = p.n_stages;
+  const RbStage* prog = p.prog;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t w_it = 0, a_emp_par = 0, hl_rounds = 0;
+      int prev_nkb = 0;          // k-blocks of the preceding GEMM stage when it releases its A panels (else 0)
+      bool hl_pending = false;   // the A buffer still holds residual boxes of the last residual load
+      for (int i = 0; i < n_stages; ++i) {
+        const RbStage& st = prog[i];
+        if (rb_skip(st, x)) continue;
+        if (st.kind == RB_HLOAD) {
+          for (int kb = 0; kb < prev_nkb; ++kb) {            // the A buffer is the landing zone: its readers must be done
+            rb_wait(bar(B_A_EMPTY + kb), (a_emp_par >> kb) & 1u, p, i, 10);
+            a_emp_par ^= 1u << kb;
+          }
+          prev_nkb = 0;
+          for (int r = 0; r < 2; ++r) {
+            for (int w = 0; w < 8; ++w) {
+              if (hl_rounds > 0) rb_wait(bar(B_HL_EMPTY + w), (hl_rounds - 1) & 1u, p, i, 11);
+              const int q = (w + 2) & 3, half = w >> 2;
+              mbar_expect_tx(bar(B_HL_FULL + w), 4 * STG_BOX);
+              for (int j = 0; j < 4; ++j)
+                tma_load_2d(sA + (uint32_t)((w * 4 + j) * STG_BOX), &tm_h, 256 * half + 32 * (4 * r + j), row0 + 32 * q,
+                            bar(B_HL_FULL + w));
+            }
+            ++hl_rounds;
+          }
+          hl_pending = true;
+          continue;
+        }
+        const int nkb = st.K >> 6, nnt = st.N >> 7;
+        const int xoff = st.per_stream ? x * 512 : 0;
+        const int na = nkb > prev_nkb ? nkb : prev_nkb;
+        int a_issued = 0;
+        auto issue_a_upto = [&](int upto) {
+          for (; a_issued <= upto && a_issued < na; ++a_issued) {
+            const int kb = a_issued;
+            if (kb < prev_nkb) {                             // released by the previous stage's MMAs over this panel
+              rb_wait(bar(B_A_EMPTY + kb), (a_emp_par >> kb) & 1u, p, i, 12);
+              a_emp_par ^= 1u << kb;
+            }
+            if (kb < nkb && st.a_src == RB_A_TMA) {
+              if (hl_pending) {
+                for (int w = 0; w < 8; ++w) rb_wait(bar(B_HL_EMPTY + w), (hl_rounds - 1) & 1u, p, i, 13);
+                hl_pending = false;
+              }
+              mbar_expect_tx(bar(B_A_FULL + kb), PANEL);
+              tma_load_2d(sA + (uint32_t)(kb * PANEL), &st.map_a, st.a_col0 + xoff + kb * 64, row0, bar(B_A_FULL + kb));
+            }
+          }
+        };
+        auto issue_w = [&](int kb) {
+          for (int nt = 0; nt < nnt; ++nt) {
+            const uint32_t s = w_it & (W_STAGES - 1);
+            rb_wait(bar(B_W_EMPTY + s), ((w_it / W_STAGES) & 1u) ^ 1u, p, i, 14);
+            mbar_expect_tx(bar(B_W_FULL + s), W_TILE);
+            tma_load_2d(sW + s * W_TILE, &st.map_w, st.w_col0 + xoff + kb * 64, st.w_row0 + nt * 128, bar(B_W_FULL + s));
+            ++w_it;
+          }
+        };
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb == 0) { issue_w(0); issue_a_upto(1); }
+          else { issue_a_upto(kb + 1); issue_w(kb); }
+        }
+        issue_a_upto(na - 1);
+        if (st.a_src != RB_A_TMA) hl_pending = false;       // (programs never keep residual boxes across such a stage)
+        prev_nkb = rb_commit_a(prog, n_stages, i, x) ? nkb : 0;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t w_it = 0, a_full_par = 0, epi_seen = 0;
+      bool prev_epi = false;
+      constexpr uint32_t idesc = make_idesc(128, 128);
+      for (int i = 0; i < n_stages; ++i) {
+        const RbStage& st = prog[i];
+        if (rb_skip(st, x)) continue;
+        if (st.kind == RB_HLOAD) { prev_epi = true; continue; }
+        const int nkb = st.K >> 6, nnt = st.N >> 7;
+        if (prev_epi) {                                      // residual rows resident / operand written / TMEM reads done
+          rb_wait(bar(B_EPI_DONE), epi_seen & 1u, p, i, 20);
+          ++epi_seen;
+        }
+        tc_fence_after();
+        const bool commit_a = rb_commit_a(prog, n_stages, i, x);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (st.a_src == RB_A_TMA) {
+            rb_wait(bar(B_A_FULL + kb), (a_full_par >> kb) & 1u, p, i, 21);
+            a_full_par ^= 1u << kb;
+            tc_fence_after();
+          }
+          const uint64_t adesc = make_smem_desc(sA + (uint32_t)(kb * PANEL));
+          for (int nt = 0; nt < nnt; ++nt) {
+            const uint32_t s = w_it & (W_STAGES - 1);
+            rb_wait(bar(B_W_FULL + s), (w_it / W_STAGES) & 1u, p, i, 22);
+            tc_fence_after();
+            const uint64_t bdesc = make_smem_desc(sW + s * W_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)     // the accumulator already holds the residual rows: always accumulate
+              umma_bf16(tmem + (uint32_t)(nt * 128), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+            umma_commit(bar(B_W_EMPTY + s));
+            ++w_it;
+          }
+          if (commit_a) umma_commit(bar(B_A_EMPTY + kb));
+        }
+        if (st.epi != RB_EPI_NONE) umma_commit(bar(B_ACC_FULL));
+        prev_epi = st.epi == RB_EPI_LN;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ epilogue
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int cbase = 256 * half;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int step = p.step_ptr ? *p.step_ptr : 0;
+    uint32_t acc_seen = 0, hl_seen = 0;
+    bool stored = false;
+    for (int i = 0; i < n_stages; ++i) {
+      const RbStage& st = prog[i];
+      if (rb_skip(st, x)) continue;
+      if (st.kind == RB_HLOAD) {
+        for (int r = 0; r < 2; ++r) {
+          rb_wait(bar(B_HL_FULL + ew), hl_seen & 1u, p, i, 30);
+          ++hl_seen;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const uint8_t* box = gen + (ew * 4 + j) * STG_BOX + lane * 128;
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 t = *reinterpret_cast<const float4*>(box + ((c ^ (int)sw) << 4));
+              v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+            }
+            tmem_st32(tmem + lane_off + (uint32_t)(cbase + 32 * (4 * r + j)), v);
+          }
+          tmem_st_wait();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_HL_EMPTY + ew));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_EPI_DONE));
+        continue;
+      }
+      if (st.epi == RB_EPI_NONE) continue;
+      rb_wait(bar(B_ACC_FULL), acc_seen & 1u, p, i, 31);
+      ++acc_seen;
+      tc_fence_after();
+      const int nx = rb_next(prog, n_stages, i, x);
+      const bool park = nx >= 0 && prog[nx].kind == RB_GEMM;     // more residual updates follow in this launch
+      const float* bias = st.bias;
+      const float* mod = st.mod ? st.mod + (size_t)step * st.mod_stride : nullptr;
+      // ---- pass 1: row statistics of h + bias over this warp's 256 columns (one row per thread)
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int s = 0; s < 8; ++s) {
+        float v[32];
+        tmem_ld32(tmem + lane_off + (uint32_t)(cbase + 32 * s), v);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cbase + 32 * s + 4 * j));
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+      }
+      // the A panels are dead once the stage's MMAs have completed: their first 2 KB carry the partial statistics
+      float2* stats = reinterpret_cast<float2*>(gen);
+      stats[(q * 32 + lane) * 2 + half] = make_float2(s1, s2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2 o = stats[(q * 32 + lane) * 2 + (half ^ 1)];
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // everyone has read: pass 2 may overwrite the panels
+      const float mean = (s1 + o.x) * (1.0f / 512.0f);
+      const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / 512.0f) - mean * mean, 0.f) + 1e-5f);
+      const float nmr = -mean * rstd;
+      // ---- pass 2: LayerNorm (+ modulation + SiLU) -> next A operand; park / spill the updated rows
+#pragma unroll 1
+      for (int s = 0; s < 8; ++s) {
+        const int col = cbase + 32 * s;
+        float v[32];
+        tmem_ld32(tmem + lane_off + (uint32_t)col, v);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + 4 * j));
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+          if (park) tmem_st32(tmem + lane_off + (uint32_t)col, v);
+        }
+        if (st.spill) {
+          const uint32_t boxa = sStg + (uint32_t)(ew * STG_BOX);
+          if (stored) {                                         // the previous box must have been read by the TMA unit
+            if (lane == 0) tma_wait_read0();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(boxa + (uint32_t)lane * 128u + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]),
+                         __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tm_h, col, row0 + 32 * q, boxa); tma_commit(); }
+          stored = true;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(st.ln_g + col + 4 * j));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(st.ln_b + col + 4 * j));
+          v[4 * j] = fmaf(v[4 * j], rstd, nmr) * g4.x + b4.x;
+          v[4 * j + 1] = fmaf(v[4 * j + 1], rstd, nmr) * g4.y + b4.y;
+          v[4 * j + 2] = fmaf(v[4 * j + 2], rstd, nmr) * g4.z + b4.z;
+          v[4 * j + 3] = fmaf(v[4 * j + 3], rstd, nmr) * g4.w + b4.w;
+        }
+        if (mod) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(mod + col + 4 * j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(mod + 512 + col + 4 * j));
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float y = fmaf(v[4 * j + e], 1.0f + scv[e], shv[e]);
+              v[4 * j + e] = __fdividef(y, 1.0f + __expf(-y));
+            }
+          }
+        }
+        // 32 columns = 4 chunks of 8 bf16 inside K panel col / 64
+        const uint32_t prow = sA + (uint32_t)((col >> 6) * PANEL) + (uint32_t)(q * 32 + lane) * 128u;
+        const uint32_t ch0 = (uint32_t)((col & 63) >> 3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          st_shared_v4(prow + (((ch0 + (uint32_t)j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_async_smem();            // operand panels: generic-proxy writes -> tcgen05.mma / TMA reads
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_EPI_DONE));
+      if (st.store_a) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // all eight warps' panel writes are fenced
+        if (ew == 0 && lane == 0) {
+          for (int kp = 0; kp < N_PANELS; ++kp) tma_store_2d(&tm_a, kp * 64, row0, sA + (uint32_t)(kp * PANEL));
+          tma_commit();
+          tma_wait_read0();
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // nobody rewrites the panels while the TMA unit reads them
+      }
+    }
+    if (lane == 0 && stored) tma_wait_read0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+unsigned* g_fault_host = nullptr;
+unsigned* g_fault_dev = nullptr;
+
+}  // namespace
+
+const unsigned* rowblock_fault_record() { return g_fault_host; }
+
+int init_rowblock_kernels() {
+  static std::mutex mu;
+  static unsigned long long done_mask = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && ((done_mask >> dev) & 1ull)) return CFB_OK;
+  CFB_CUDA(cudaFuncSetAttribute(rowblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+  if (!g_fault_host) {
+    CFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_fault_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(g_fault_host, 0, 64);
+    CFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_fault_dev), g_fault_host, 0));
+  }
+  if (dev < 64) done_mask |= 1ull << dev;
+  return CFB_OK;
+}
+
+int rowblock_operand_map(const void* p, int rows, int cols, int ld, CUtensorMap* out) {
+  return tc_get_map(p, rows, cols, ld, 128, out, 0);
+}
+
+int rowblock_launch(const RbLaunch& L, cudaStream_t st) {
+  if (L.n_blocks <= 0 || L.n_stages <= 0) return CFB_OK;
+  CUtensorMap th, ta;
+  CFB_TRY(tc_get_map(L.h, L.rows_total, 512, 512, 32, &th, 1));    // fp32 boxes of 32 rows x 32 columns
+  CFB_TRY(tc_get_map(L.a, L.rows_total, 512, 512, 128, &ta, 0));   // bf16 panels of 128 rows x 64 columns
+  RbParams p;
+  p.prog = L.prog; p.n_stages = L.n_stages; p.block0 = L.block0; p.blk_stream = L.blk_stream; p.step_ptr = L.step_ptr;
+  p.fault = g_fault_dev;
+  launch_k(rowblock_kernel, dim3(L.n_blocks), dim3(RB_THREADS), RB_SMEM, st, th, ta, p);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
+}  // namespace cfb

@@ -1,0 +1,26 @@
+"""Row-block kernel (csrc/rowblock.cu: one persistent tcgen05 CTA per 128 query rows runs a layer's residual chains on
+rows resident in tensor memory) against the one-kernel-per-operator path and against fp32.  Sorted last: a protocol
+error in the kernel traps (it never hangs) and takes the CUDA context with it."""
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+
+
+@pytest.mark.parametrize("B,dyadic", [(8, True), (16, False)])
+def test_rowblock_programs_match_operator_path(B, dyadic):
+    """Guidance scale 1 keeps bf16 rounding flips unamplified, so the bound is tight: every program kind alone
+    (mask 1, 2, 4) and all of them (7), eager and graph-replayed, stays at the bf16 rounding level of the operator path
+    (whose own distance to fp32 is printed beside it) after one and after three steps."""
+    import rb_check
+    res = rb_check.run(B=B, steps=3, dyadic=dyadic, masks=(1, 2, 4, 7))
+    ref_first, ref_last = res["operator_vs_fp32"]
+    for key, (first, last, vs32, finite) in res.items():
+        if key == "operator_vs_fp32":
+            continue
+        assert finite, key
+        assert first < 2.0 * max(ref_first, 2e-3), (key, first, ref_first)
+        assert vs32 < 2.0 * max(ref_last, 4e-3), (key, vs32, ref_last)
