@@ -5,14 +5,18 @@ A "step" is one pass of the hot path over one batch of synthetic clips: conditio
 the DDIM loop (50 denoiser evaluations under 7-branch modality guidance + scheduler), VAE decode to joints.
 One clip = 128 frames @ 25 fps = 5.12 motion-seconds.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N>1: launched under torchrun)
-  python bench.py --impl reference [...]                         the reference algorithm on the host CPU
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm, BASELINE configs[1] (N>1: under torchrun)
+  python bench.py --impl reference [...]                         the reference algorithm on the host CPU cores
+  python bench.py --dyadic                                       configs[2]: DnD-shaped conditioning
+  python bench.py --windows 115 [--batch 1|64]                   configs[3]: ~5 min of unbounded synthesis per stream
+  python bench.py --sweep 4096 [--gpus N]                        configs[4]: 4096 clips, static shard, seeds 1234+clip_id
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
 """
 import argparse
 import json
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -24,6 +28,7 @@ sys.path.insert(0, str(ROOT))
 
 MOTION_S_PER_CLIP = 128 / 25.0
 SCHED_KW = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=True)
+MEM_LEN = (32, 161, 32, 8, 1)      # spk text, lsn audio, lsn text, active-passive bits, listener id
 
 
 def parse():
@@ -38,24 +43,35 @@ def parse():
     ap.add_argument("--dyadic", action="store_true", help="configs[2]: DnD-shaped conditioning")
     ap.add_argument("--windows", type=int, default=0,
                     help="configs[3]: unbounded synthesis, this many serial 128-frame windows at 50 %% overlap per stream "
-                         "(latent inpainting of the previous window + decode per window); 0 = bounded clips")
+                         "(latent inpainting of the previous window + decode per window; 115 = ~5 min); 0 = bounded clips")
+    ap.add_argument("--sweep", type=int, default=0,
+                    help="configs[4]: this many clips in total, statically sharded over the ranks in batches of --batch, "
+                         "per-clip seeds 1234 + clip_id; a step is one batch of the shard and --steps is ignored")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="independent batches kept in flight on one GPU (one sampler handle + stream each); every step "
                          "is still one full pass over one batch of --batch clips, steps of different handles overlap")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-B200 baseline")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-roofline", action="store_true", help="skip the GEMM micro-measurement (profiling runs)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the kernel micro-measurements (profiling runs)")
     return ap.parse_args()
 
 
+def n_branches(args):
+    """Guidance branches our arm evaluates: never the weight-0 full-cond branch; the speaker-only branch only for dyadic
+    clips (monadic: it repeats the unconditional branch exactly, convofusion_b200.conditioning.guidance_branches)."""
+    return 6 if args.dyadic else 5
+
+
 # ------------------------------------------------------------------------------------------ flops
-def denoiser_flops(n_clips, n_branch, mem_len=(32, 161, 32, 8, 1), d=512, ff=1024, L=9, ntok=16, lat=128):
+def denoiser_flops(n_clips, n_branch, mem_len=MEM_LEN, d=512, ff=1024, L=9, ntok=16, lat=128):
     """FLOPs of one denoiser evaluation (2*m*n*k over every GEMM and attention contraction).
     `executed`: what this implementation issues in the shared-slot plan: per layer the
     full-batch GEMMs in_proj / out_proj / 2 x TimeBlock / shared scores (N = sum of 32-padded memory lengths) /
     shared values (K = sum of 64-padded lengths) / FFN, the conditional row groups (one stream per single-modality
     branch: query projection + fuser block), the per-pair and self attention, plus the per-step memory-side
-    pre-projection.  `as_written`: the reference's own count for 7 branches."""
+    pre-projection.  The padding (scores N = 320 for 234 keys, values K = 448) is ~3 % of `executed`.
+    `as_written`: the reference's own count for 7 branches."""
     R = n_clips * n_branch * ntok
     n_tot = sum((m + 31) // 32 * 32 for m in mem_len)
     k_tot = sum((m + 63) // 64 * 64 for m in mem_len)
@@ -103,41 +119,96 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(n_clips, ddim_steps, timed_denoiser_steps, dyadic, threads):
-    """The reference algorithm on host cores: oracle port of Denoiser.forward / guidance / DDIM / VAE decode
-    (oracle/convofusion_oracle.py, pinned to the reference modules by tests/golden).  Times `timed_denoiser_steps`
-    evaluations of the 7*B batch plus one decode and extrapolates the loop linearly to `ddim_steps`."""
-    import torch
-    import convofusion_b200 as cf
-    from convofusion_b200.synthetic import randomize_, synthetic_clip
-    from oracle import convofusion_oracle as O
-    torch.set_num_threads(threads)
-    sd = {k: v for k, v in randomize_(cf.ConvoFusionSampler(precision="fp32"), 1234).state_dict().items()}
-    syn = synthetic_clip(n_clips, seed=1234, dyadic=dyadic)
-    clip = dict(syn["clip"])
-    clip["text_lsn_mask"], clip["text_spk_mask"] = ~clip["text_lsn_attn"].bool(), ~clip["text_spk_attn"].bool()
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        enc, masks = O.assemble_guidance_batch(sd, clip, syn["uncond_text"], ~syn["uncond_text_attn"].bool())
-        t_cond = time.perf_counter() - t0
-        sch = O.DDIMSchedulerOracle(**SCHED_KW)
-        sch.set_timesteps(ddim_steps)
-        lat = torch.randn(n_clips, 16, 128, generator=torch.Generator().manual_seed(1))
-        den = lambda x, t: O.denoiser_forward(sd, x, t, enc, masks, prefix="denoiser.")
-        den(torch.cat([lat] * 7), sch.timesteps[0])          # warm-up
-        t0 = time.perf_counter()
-        timed_denoiser_steps = min(timed_denoiser_steps, ddim_steps)
-        for t in sch.timesteps[:timed_denoiser_steps]:
-            eps, _ = den(torch.cat([lat] * 7), t)
-            lat = sch.step(O.guidance_combine(eps, 7.5), t, lat, eta=0.0).prev_sample
-        t_step = (time.perf_counter() - t0) / timed_denoiser_steps
-        t0 = time.perf_counter()
-        O.vae_decode(sd, O.latents_to_vae_input(lat.permute(1, 0, 2)), [128] * n_clips, prefix="vae.")
-        t_dec = time.perf_counter() - t0
-    total = t_cond + ddim_steps * t_step + t_dec
-    return {"seconds_per_pass": total, "ms_per_denoiser_step": t_step * 1e3, "decode_ms": t_dec * 1e3,
-            "value": n_clips * MOTION_S_PER_CLIP / total}
+# ------------------------------------------------------------------------------------------ reference algorithm
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class ReferencePass:
+    """The reference algorithm (oracle port of Denoiser.forward / 7-branch guidance / DDIM / VAE decode,
+    oracle/convofusion_oracle.py, pinned to the reference modules by tests/golden) on the FULL batch of the workload:
+    all 7 guidance branches as written (convofusion.py:499-541).  `run(n)` times conditioning + n denoiser evaluations
+    of the 7*B batch + one decode; only the NUMBER of DDIM steps is extrapolated (linearly: every step is the same
+    work).  device 'cpu' = the host-core baseline; a CUDA device = PyTorch eager on the B200 (TF32 off)."""
+
+    def __init__(self, n_clips, ddim_steps, dyadic, device="cpu", threads=None, autocast=False):
+        import torch
+        import convofusion_b200 as cf
+        from convofusion_b200.synthetic import randomize_, synthetic_clip
+        from oracle import convofusion_oracle as O
+        self.torch, self.O, self.n_clips, self.ddim_steps, self.autocast = torch, O, n_clips, ddim_steps, autocast
+        self.dev = torch.device(device)
+        if self.dev.type == "cpu" and threads:
+            torch.set_num_threads(threads)
+        if self.dev.type == "cuda":
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+        sd = randomize_(cf.ConvoFusionSampler(precision="fp32"), 1234).state_dict()
+        self.sd = {k: v.to(self.dev) for k, v in sd.items()}
+        syn = synthetic_clip(n_clips, seed=1234, dyadic=dyadic)
+        clip = {k: (v.to(self.dev) if torch.is_tensor(v) else v) for k, v in syn["clip"].items()}
+        clip["text_lsn_mask"], clip["text_spk_mask"] = ~clip["text_lsn_attn"].bool(), ~clip["text_spk_attn"].bool()
+        self.clip, self.U, self.Um = clip, syn["uncond_text"].to(self.dev), (~syn["uncond_text_attn"].bool()).to(self.dev)
+        self.lat0 = torch.randn(n_clips, 16, 128, generator=torch.Generator().manual_seed(1)).to(self.dev)
+        self.sch = O.DDIMSchedulerOracle(**SCHED_KW)
+        self.sch.set_timesteps(ddim_steps)
+
+    def _sync(self):
+        if self.dev.type == "cuda":
+            self.torch.cuda.synchronize(self.dev)
+
+    def run(self, timed_steps):
+        torch, O = self.torch, self.O
+        timed_steps = max(1, min(timed_steps, self.ddim_steps))
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if (self.autocast and self.dev.type == "cuda") else _Null()
+        with torch.no_grad(), ctx:
+            self._sync()
+            t0 = time.perf_counter()
+            enc, masks = O.assemble_guidance_batch(self.sd, self.clip, self.U, self.Um)
+            self._sync()
+            t_cond = time.perf_counter() - t0
+            lat = self.lat0
+            t0 = time.perf_counter()
+            for t in self.sch.timesteps[:timed_steps]:
+                eps, _ = O.denoiser_forward(self.sd, torch.cat([lat] * 7), t, enc, masks, prefix="denoiser.")
+                lat = self.sch.step(O.guidance_combine(eps.float(), 7.5), t, lat, eta=0.0).prev_sample
+            self._sync()
+            t_step = (time.perf_counter() - t0) / timed_steps
+            t0 = time.perf_counter()
+            O.vae_decode(self.sd, O.latents_to_vae_input(lat.permute(1, 0, 2)), [128] * self.n_clips, prefix="vae.")
+            self._sync()
+            t_dec = time.perf_counter() - t0
+        total = t_cond + self.ddim_steps * t_step + t_dec
+        return {"seconds_per_pass": total, "ms_per_denoiser_step": t_step * 1e3, "decode_ms": t_dec * 1e3,
+                "conditioning_ms": t_cond * 1e3, "value": self.n_clips * MOTION_S_PER_CLIP / total}
+
+
+def cpu_sample_text(B, ddim_steps, timed, cores):
+    return (f"all {B} clips of the batch (7x{B} denoiser batch, 7 branches as written), conditioning + {timed} of {ddim_steps} "
+            f"DDIM steps (each step is identical work: only the step count is extrapolated) + VAE decode of the {B} "
+            f"clips; oracle port of the reference, torch fp32, {cores} threads")
+
+
+def workload_config(args, batch):
+    """Identical in both arms (the driver compares them); how each arm evaluates it is in `execution`."""
+    if args.sweep:
+        tag = f"BASELINE.json configs[4]: {args.sweep} clips data-parallel, static shard, seeds 1234+clip_id"
+    elif args.windows:
+        tag = "BASELINE.json configs[3]: unbounded synthesis"
+    else:
+        tag = "BASELINE.json configs[%d]" % (2 if args.dyadic else 1)
+    return {"workload": ("dyadic DnD-shaped" if args.dyadic else "monadic BEAT-shaped") +
+            f" config_cf_beatdnd random-init, batch {batch} clips/GPU, {args.ddim_steps} DDIM steps, 7-branch guidance 7.5, "
+            f"VAE decode to 128x189 joints ({tag})",
+            "clips_per_gpu": batch, "ddim_steps": args.ddim_steps, "guidance_scale": 7.5,
+            "unbounded_windows": args.windows, "sweep_clips": args.sweep, "memory_tokens": sum(MEM_LEN),
+            "l2": "no flush: one pass streams 186 MB of bf16 weights 50x plus >150 MB of activations, above the 126 MB L2",
+            "reference": "the reference arm (--impl reference) runs the same workload through the oracle port of the "
+                         "reference's algorithm on the host cores, all 7 guidance branches as written"}
 
 
 def run_reference_arm(args):
@@ -145,130 +216,107 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_clips, timed = 8, 8          # bounded sample: ~5-10 s of host work per step
+    ref = ReferencePass(args.batch, args.ddim_steps, args.dyadic, "cpu", cores)
+    # every step = one bounded sample: conditioning + `timed` denoiser evaluations of the full 7x64 batch + decode,
+    # sized from a first probe so that the whole --steps/--warmup run stays within a few minutes
+    probe = ref.run(1)                                   # also pages in the weights / warms the thread pool
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    timed = int(max(1, min(4, budget_s * 1e3 // max(1.0, probe["ms_per_denoiser_step"]))))
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_run(n_clips, args.ddim_steps, timed, args.dyadic, cores)
+        r = ref.run(timed)
         if i >= args.warmup:
             vals.append(r)
     v = sum(r["value"] for r in vals) / len(vals)
     ms = sum(r["seconds_per_pass"] for r in vals) / len(vals) * 1e3
-    sample = (f"{n_clips} of the {args.batch} clips (7x{n_clips} denoiser batch), {timed} of {args.ddim_steps} DDIM steps timed and "
-              f"extrapolated linearly, + conditioning + VAE decode; torch fp32, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "motion_seconds_per_second", "value": v, "unit": "motion-s/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.sweep else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # same workload as our arm (BASELINE configs[1]: batches of 64 clips); each step times a bounded sample of it
-        # (cpu_baseline.sample).  The reference evaluates all 7 guidance branches as written, ours skips the weight-0 one.
-        "config": dict(workload_config(args, args.batch), batches_in_flight=1, reference_branches_evaluated=7),
-        "cpu_baseline": {"value": v, "unit": "motion-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.batch),
+        "execution": {"guidance_branches_evaluated": 7, "batches_in_flight": 1, "device": "host CPU cores"},
+        "ms_per_denoiser_step": sum(r["ms_per_denoiser_step"] for r in vals) / len(vals),
+        "cpu_baseline": {"value": v, "unit": "motion-s/s", "cores": cores, "kind": "port",
+                         "sample": cpu_sample_text(args.batch, args.ddim_steps, timed, cores)},
         "e2e": {"value": v, "unit": "motion-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, batch, branches=None):
-    if branches is None:
-        branches = 6 if args.dyadic else 5
-    return {"workload": ("dyadic DnD-shaped" if args.dyadic else "monadic BEAT-shaped") +
-            f" config_cf_beatdnd random-init, batch {batch} clips/GPU, {args.ddim_steps} DDIM steps, 7-branch guidance 7.5, "
-            "VAE decode to 128x189 joints (BASELINE.json configs[%d])" % (2 if args.dyadic else 1),
-            "clips_per_gpu": batch, "ddim_steps": args.ddim_steps, "guidance_branches_evaluated": branches,
-            "unbounded_windows": args.windows,
-            "memory_tokens": 234 if args.dyadic else 234,
-            "l2": "no flush: one pass streams 186 MB of bf16 weights 50x plus >150 MB of activations, above the 126 MB L2"}
+def load_peaks():
+    pk = ROOT / "MEASURED_PEAKS.json"
+    return json.loads(pk.read_text()) if pk.exists() else {}
 
 
 def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, clocks, parts, roof, single, h2d_bytes,
-                  d2h_bytes):
+                  d2h_bytes, steps=None, clips_total=None, extra=None):
     """The contract's JSON line from the measurements of run_ours (pure host arithmetic: unit-tested on the CPU)."""
     W = args.windows
-    clips_total = B * world * args.steps
+    steps = steps if steps is not None else args.steps
+    if clips_total is None:
+        clips_total = B * world * steps
     motion_s = MOTION_S_PER_CLIP if W == 0 else MOTION_S_PER_CLIP * (W + 1) / 2.0   # 50 % overlap between windows
     value = clips_total * motion_s / (ms_dev * 1e-3)
     e2e_value = clips_total * motion_s / (ms_e2e * 1e-3)
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
-    # B200_PROFILING.md: burst peak for a kernel timed alone (the GEMM mix runs by itself for ~15 ms at full clocks),
+    peaks = load_peaks()
+    # B200_PROFILING.md: burst peak for a kernel timed alone (the kernel mix runs by itself for ~15 ms at full clocks),
     # sustained peak for work timed inside a long step (the whole denoiser step)
     peak_burst = peaks.get("bf16_tflops", 1590.0)
     peak_tf = peaks.get("bf16_tflops_sustained", peak_burst)
-    peak_src = ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone) (of measured)" if peaks
+    peak_src = ("MEASURED_PEAKS.json bf16_tflops (burst; kernels timed alone) (of measured)" if peaks
                 else "fallback 1.59 PFLOP/s (of fallback)")
     fl = denoiser_flops(B, n_branch)
     ms_den = parts["loop_ms"] / args.ddim_steps          # `parts` times one sample() call = one window
     line = {
-        "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "motion_seconds_per_second", "value": value, "unit": "motion-s/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
+        "scaling": "strong" if args.sweep else "weak",
         "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-        "config": dict(workload_config(args, B), batches_in_flight=F,
-                       in_flight=("every step is one full pass over its own batch of %d clips; %d independent batches "
-                                  "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
-                                  % (B, F)) if F > 1 else "one batch at a time"),
+        "config": workload_config(args, B),
+        "execution": {"guidance_branches_evaluated": n_branch, "batches_in_flight": F,
+                      "in_flight": ("every step is one full pass over its own batch of %d clips; %d independent batches "
+                                    "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
+                                    % (B, F)) if F > 1 else "one batch at a time"},
         "e2e": {"value": e2e_value, "unit": "motion-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches), "clocks": clocks,
         "one_batch_in_flight": single,
         "ms_per_denoiser_step": ms_den, "pass_split_ms": parts,
         # whole pass (conditioning + decode included) / DDIM steps at the measured throughput: with several batches
         # in flight this is below the single-batch latency figure above
-        "ms_per_denoiser_step_at_throughput": ms_dev / args.steps / args.ddim_steps / max(1, W),
+        "ms_per_denoiser_step_at_throughput": ms_dev / steps / args.ddim_steps / max(1, W),
         "denoiser_step_tflops": {"executed": fl["executed"] / (ms_den * 1e-3) / 1e12,
                                  "reference_equivalent": fl["as_written"] / (ms_den * 1e-3) / 1e12,
                                  "executed_gflop_per_step": fl["executed"] / 1e9},
     }
+    if W:
+        line["windows_per_second"] = clips_total * W / (ms_dev * 1e-3)
     if roof:
-        tf, gemm_ms, n_gemm = roof
+        tf = roof["tflops"]
         traffic = None
-        tfile = ROOT / "profiles" / "r01_traffic.json"
-        if tfile.exists():
-            traffic = json.loads(tfile.read_text())
-        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_tma_kernel (tcgen05, TMA store / L2 reduce-add epilogue)",
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            if (ROOT / "profiles" / name).exists():
+                traffic = json.loads((ROOT / "profiles" / name).read_text())
+                break
+        line["roofline"] = {"bound": "tensor", "kernel": roof["kernel"],
                             "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
                             "frac_of_sustained_peak": tf / peak_tf, "sustained_peak": peak_tf,
                             "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
-                            "peak_source": peak_src, "launches_timed": n_gemm, "ms_per_72_gemms": gemm_ms,
+                            "peak_source": peak_src, "launches_timed": roof["launches"], "ms_timed": roof["ms"],
+                            "shapes": roof.get("shapes"),
                             "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
                             "whole_step_frac_at_throughput":
-                                fl["executed"] * args.ddim_steps * max(1, W) / (ms_dev / args.steps * 1e-3) / 1e12 / peak_tf}
-    if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        r = cpu_reference_run(8, args.ddim_steps, 8, args.dyadic, cores)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
-                                "sample": f"8 of the {B} clips (7x8 denoiser batch), 8 of {args.ddim_steps} DDIM steps timed and "
-                                          "extrapolated linearly + conditioning + decode; oracle port, torch fp32",
-                                "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
+                                fl["executed"] * args.ddim_steps * max(1, W) / (ms_dev / steps * 1e-3) / 1e12 / peak_tf}
+        if roof.get("mem"):
+            line["roofline_mem"] = roof["mem"]
+    if extra:
+        line.update(extra)
     return line
 
 
-# ------------------------------------------------------------------------------------------ our arm
-def gemm_roofline(torch, lib_mod, batch, n_branch, dev, iters=20):
-    """Device time of the dominant kernel (gemm_tc_kernel) over exactly the GEMM shape mix of one denoiser
-    evaluation, CUDA events on the launching stream; weights of all 9 layers rotate so operands exceed L2."""
-    from convofusion_b200 import _lib
-    R, d = batch * n_branch * 16, 512
-    # (N, K, epilogue) of the eight full-batch GEMMs of one layer in the shared-slot plan: in_proj, self out_proj,
-    # time_block1, shared scores, shared values, time_block2, linear1 (GELU), linear2.  "res" = fp32 residual update.
-    spec = [(3 * d, d, "bf16"), (d, d, "res"), (d, d, "res"), (320, d, "f32"), (d, 448, "res"), (d, d, "res"),
-            (1024, d, "gelu"), (d, 1024, "res")]
-    shapes = [(n, k) for n, k, _ in spec]
-    Ws = [[torch.randn(n, k, device=dev).bfloat16() for (n, k) in shapes] for _ in range(9)]
-    As = {k: torch.randn(R, k, device=dev).bfloat16() for k in (d, 448, 1024)}
-    outs = {"bf16": {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, 1024)},
-            "f32": {n: torch.zeros(R, n, device=dev) for n in (d, 320)}}
-    side = torch.cuda.Stream(device=dev)
-    st = side.cuda_stream
-
-    def one_pass():
-        for layer in Ws:
-            for (n, k, kind), w in zip(spec, layer):
-                obf = kind in ("bf16", "gelu")
-                out = outs["bf16" if obf else "f32"][n]
-                _lib.check(_lib.lib().cfb_linear(As[k].data_ptr(), 1, w.data_ptr(), 0, out.data_ptr(), int(obf), R, n, k,
-                                                 1 if kind == "gelu" else 0, 0, int(kind == "res"), _lib.GEMM_TCGEN05, st))
-    # An eager launch through ctypes costs ~12 us of host time, more than most of these kernels run, so the pass is
-    # captured into a CUDA graph and replayed: the events below bracket device time only.
+# ------------------------------------------------------------------------------------------ kernel micro-measurements
+def _graph_time(torch, side, one_pass, iters):
+    """Device time of `one_pass` (launches on stream `side`) replayed as a CUDA graph: an eager launch through ctypes
+    costs ~12 us of host time, more than most of these kernels run, so the events bracket device time only."""
     with torch.cuda.stream(side):
         for _ in range(3):
             one_pass()
@@ -284,16 +332,115 @@ def gemm_roofline(torch, lib_mod, batch, n_branch, dev, iters=20):
             graph.replay()
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    flops = 9 * sum(2.0 * R * n * k for (n, k) in shapes)
-    return flops / (ms * 1e-3) / 1e12, ms, 9 * len(shapes)
+    return e0.elapsed_time(e1) / iters
 
 
+def gemm_roofline(torch, batch, n_branch, dev, chains, iters=20):
+    """Device time of the tcgen05 GEMM kernel family over the GEMM shape mix of one denoiser evaluation AT THE SHAPES
+    THE STEP LAUNCHES: every chain's row count (n_batch / chains entries x 16 tokens), the eight full-batch operators
+    of a layer, the conditional projections (query projection + fuser block of the chain's conditional stream) and the
+    per-step memory-side pre-projection; weights of all 9 layers rotate so operands exceed L2.  Chains run back to
+    back here (the step overlaps them on forked streams), so this is the kernel's efficiency at production shapes,
+    not the step time."""
+    from convofusion_b200 import _lib
+    d, L = 512, 9
+    n_batch = batch * n_branch
+    per = ((n_batch + chains - 1) // chains + 7) // 8 * 8
+    rows = [min(per, n_batch - c * per) * 16 for c in range((n_batch + per - 1) // per)]
+    n_tot = sum((m + 31) // 32 * 32 for m in MEM_LEN)
+    k_tot = sum((m + 63) // 64 * 64 for m in MEM_LEN)
+    spec = [(3 * d, d, "bf16"), (d, d, "res"), (d, d, "res"), (n_tot, d, "f32"), (d, k_tot, "res"), (d, d, "res"),
+            (1024, d, "gelu"), (d, 1024, "res"),
+            (d, d, "bf16"), (d, d, "res")]             # conditional rows: query projection, fuser block
+    R = max(rows)
+    Ws = [[torch.randn(n, k, device=dev).bfloat16() for (n, k, _) in spec] for _ in range(L)]
+    As = {k: torch.randn(R, k, device=dev).bfloat16() for k in (d, k_tot, 1024)}
+    outs = {"bf16": {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, 1024, d)},
+            "f32": {n: torch.zeros(R, n, device=dev) for n in (d, n_tot)}}
+    Am = torch.randn(max(MEM_LEN), d, device=dev).bfloat16()
+    Wz = torch.randn(L * d, d, device=dev).bfloat16()
+    Oz = torch.empty(max(MEM_LEN), L * d, device=dev, dtype=torch.bfloat16)
+    side = torch.cuda.Stream(device=dev)
+    st = side.cuda_stream
+    lib = _lib.lib()
+    acc = {"flops": 0.0, "n": 0}
+
+    def lin(A, W, out, M, n, k, kind):
+        obf = kind in ("bf16", "gelu")
+        _lib.check(lib.cfb_linear(A.data_ptr(), 1, W.data_ptr(), 0, out.data_ptr(), int(obf), M, n, k,
+                                  1 if kind == "gelu" else 0, 0, int(kind == "res"), _lib.GEMM_TCGEN05, st))
+        acc["flops"] += 2.0 * M * n * k
+        acc["n"] += 1
+
+    def one_pass():
+        acc["flops"], acc["n"] = 0.0, 0
+        for x_len in MEM_LEN:                           # memory side: Z and Y^T of the unconditional slot, all layers
+            lin(Am, Wz, Oz, x_len, L * d, d, "bf16")
+            lin(Am, Wz, Oz, x_len, L * d, d, "bf16")
+        for M in rows:
+            for layer in Ws:
+                for (n, k, kind), w in zip(spec, layer):
+                    lin(As[k], w, outs["bf16" if kind in ("bf16", "gelu") else "f32"][n], M, n, k, kind)
+
+    ms = _graph_time(torch, side, one_pass, iters)
+    return {"tflops": acc["flops"] / (ms * 1e-3) / 1e12, "ms": ms, "launches": acc["n"],
+            "kernel": "gemm_tc_tma_kernel family (tcgen05, TMA store / L2 reduce-add epilogue) at the step's per-chain shapes",
+            "shapes": {"chain_rows": rows, "per_layer_NK": [(n, k) for n, k, _ in spec],
+                       "memory_side": f"{len(MEM_LEN)} streams x 2 x [len, {L * d}, {d}]"}}
+
+
+def memory_bound_roofline(torch, batch, n_branch, dev, chains):
+    """Achieved GB/s of the memory-bound row kernels at the step's shapes, CUDA events over graph replays, against the
+    measured HBM copy peak: LayerNorm rows (fp32 in, bf16 out), the per-step memory normalisation, the fused guidance
+    combine + scheduler step."""
+    from convofusion_b200 import _lib
+    lib = _lib.lib()
+    peaks = load_peaks()
+    peak = peaks.get("hbm_gbs", 6650.0)
+    d = 512
+    n_batch = batch * n_branch
+    per = ((n_batch + chains - 1) // chains + 7) // 8 * 8
+    side = torch.cuda.Stream(device=dev)
+    st = side.cuda_stream
+    out = {}
+    g, b = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+
+    def ln_case(rows, note=None):
+        x = torch.randn(rows, d, device=dev)
+        y = torch.empty(rows, d, device=dev, dtype=torch.bfloat16)
+        ms = _graph_time(torch, side, lambda: _lib.check(lib.cfb_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                                                            y.data_ptr(), 1, rows, d, st)), 50)
+        by = rows * d * 6
+        r = {"rows": rows, "bytes": by, "us": ms * 1e3, "gbs": by / (ms * 1e-3) / 1e9, "frac": by / (ms * 1e-3) / 1e9 / peak}
+        if note:
+            r["note"] = note
+        return r
+
+    out["ln_rows_chain"] = ln_case(per * 16)
+    out["ln_rows_full_batch"] = ln_case(n_batch * 16)
+    out["mem_hat_rows"] = ln_case((1 + batch) * sum(MEM_LEN),
+                                  "timed through cfb_layernorm on the memory rows (same row-kernel body; mem_hat adds one 2 KB time-embedding row)")
+    n = 16 * 128
+    eps = torch.randn(n_branch, batch, n, device=dev)
+    xl = torch.randn(batch, n, device=dev)
+    coef = torch.tensor([0.5, 0.8, 0.9, 0.1, 0.0, 0.0, 0.0, 0.0], device=dev)
+    ms = _graph_time(torch, side, lambda: _lib.check(lib.cfb_guidance_sched_step(
+        eps.data_ptr(), xl.data_ptr(), 0, coef.data_ptr(), n_branch, batch, n, _lib.SCHED_DDIM, 1, 7.5, st)), 50)
+    by = (n_branch + 2) * batch * n * 4
+    out["guidance_sched_step"] = {"bytes": by, "us": ms * 1e3, "gbs": by / (ms * 1e-3) / 1e9, "frac": by / (ms * 1e-3) / 1e9 / peak,
+                                  "note": "launch-latency sized: %d KB per step" % (by // 1024)}
+    return {"bound": "hbm", "peak": peak, "unit": "GB/s",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+            "kernels": out}
+
+
+# ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import convofusion_b200 as cf
     from convofusion_b200 import _lib
+    from convofusion_b200.distributed import batches as shard_batches, clip_seeds, shard_range
     from convofusion_b200.synthetic import randomize_, synthetic_clip
 
     rank = int(os.environ.get("RANK", "0"))
@@ -305,58 +452,152 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # guidance branches evaluated: the weight-0 full-cond branch never; the speaker-only branch only for dyadic clips
-    # (monadic: it repeats the unconditional branch exactly, convofusion_b200.conditioning.guidance_branches)
-    B, n_branch = args.batch, (6 if args.dyadic else 5)
+    B, n_branch = args.batch, n_branches(args)
+    W = args.windows
+    F = max(1, args.in_flight)
+    if F > 1 and any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_NSIGHT_INJECTION_PORT_BASE")):
+        # Nsight Compute serialises every kernel anyway and its injection library did not survive the lane threads'
+        # concurrent graph captures (profiles/README.md): profile one lane
+        print("bench.py: profiler injection detected, running with one batch in flight", file=sys.stderr)
+        F = 1
+    # host cores of this rank: lane threads and the gather thread are pinned inside this set, so that the 2-3 host
+    # threads of each of the N processes of a node do not migrate over each other (8-GPU tail)
+    cores_all = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    per_rank = max(1, len(cores_all) // max(1, world))
+    my_cores = cores_all[local * per_rank:(local + 1) * per_rank] or cores_all
 
     sampler = randomize_(cf.ConvoFusionSampler(precision=args.precision, num_inference_timesteps=args.ddim_steps), 1234)
     sampler = sampler.to(dev).eval()
-    syn = synthetic_clip(B, seed=1234 + rank, dyadic=args.dyadic)     # config 5: seeds 1234 + shard id
-    clip, U, Ua = syn["clip"], syn["uncond_text"], syn["uncond_text_attn"]
-    init = torch.randn(B, 16, 128, generator=torch.Generator().manual_seed(77 + rank))
-    host = {k: v.pin_memory() for k, v in clip.items() if torch.is_tensor(v)}
-    host_init = init.pin_memory()
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values()) + host_init.numel() * 4
-    out_host = torch.empty(B, 128, 189).pin_memory()
-    d2h_bytes = out_host.numel() * 4
-    Ud, Uad = U.to(dev), Ua.to(dev)
-    dclip = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in clip.items()}
-    dinit = init.to(dev)
     lengths = [128] * B
-    gathered = [torch.empty(B, 128, 189, device=dev) for _ in range(world)] if world > 1 else None
+
+    # ---- workload: the host batches (pinned) this rank walks through
+    def make_batch(seeds):
+        if isinstance(seeds, int):
+            syn = synthetic_clip(B, seed=seeds, dyadic=args.dyadic)
+            clip = syn["clip"]
+            init = torch.randn(B, 16, 128, generator=torch.Generator().manual_seed(77 + seeds))
+        else:                                   # per-clip seeds (config 5): any sharding generates the same clips
+            one = [synthetic_clip(1, seed=s, dyadic=args.dyadic)["clip"] for s in seeds]
+            clip = {}
+            for k, v0 in one[0].items():
+                if torch.is_tensor(v0):
+                    clip[k] = torch.cat([c[k] for c in one])
+                elif isinstance(v0, list):
+                    clip[k] = [c[k][0] for c in one]
+                else:
+                    clip[k] = v0
+            init = torch.cat([torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(77 + s)) for s in seeds])
+        host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in clip.items()}
+        return host, init.pin_memory()
+
+    syn0 = synthetic_clip(B, seed=1234 + rank, dyadic=args.dyadic)   # the unconditional prompt (one per run)
+    Ud, Uad = syn0["uncond_text"].to(dev), syn0["uncond_text_attn"].to(dev)
+    if args.sweep:
+        lo, hi = shard_range(args.sweep, rank, world)
+        spans = shard_batches(lo, hi, B)
+        if any(b - a != B for a, b in spans):
+            raise ValueError("--sweep needs the shard of every rank to be a multiple of --batch")
+        work = [make_batch(clip_seeds(a, b)) for a, b in spans]
+        if not args.dyadic:     # monadic clips: the speaker text IS the run's unconditional prompt (dataset.py:185-199)
+            for h, _ in work:
+                h["text_spk"] = syn0["uncond_text"].unsqueeze(0).repeat(B, 1, 1).pin_memory()
+                h["text_spk_attn"] = syn0["uncond_text_attn"].unsqueeze(0).repeat(B, 1).pin_memory()
+        n_steps = len(work)
+    else:
+        work = [make_batch(1234 + rank)]
+        n_steps = args.steps
+    h2d_bytes = sum(v.numel() * v.element_size() for v in work[0][0].values() if torch.is_tensor(v)) + work[0][1].numel() * 4
+    d2h_bytes = B * 128 * 189 * 4
+    dwork = [({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in h.items()}, x.to(dev)) for h, x in work]
     stream = torch.cuda.Stream(device=dev)
+    comm_stream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()      # the inputs above were copied on the default stream; every pass runs on other streams
 
-    W = args.windows
-    inits = [dinit] * W
-
-    def pass_device():
+    def one_pass(clip, x):
         if W > 0:   # serial windows of B independent streams (unbounded_synthesis.py:244-512)
-            out = sampler.synthesize_unbounded([dclip] * W, Ud, Uad, inits, use_graph=not args.no_graph)[-1]
-        else:
-            out = sampler.generate(dclip, Ud, Uad, lengths, dinit, use_graph=not args.no_graph)["m_rst"]
-        if world > 1:
-            dist.all_gather(gathered, out)        # the only collective: output motions at the end
+            return sampler.synthesize_unbounded([clip] * W, Ud, Uad, [x] * W, use_graph=not args.no_graph)[-1]
+        return sampler.generate(clip, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
+
+    def device_pass(i, k=0):
+        clip, x = dwork[i % len(dwork)]
+        return one_pass(clip, x)
+
+    # e2e: two pinned result buffers per lane; a buffer is waited for only when its turn comes again, so a lane
+    # enqueues its next pass while the previous pass's joints are still on their way to the host
+    outs_host = [[torch.empty(B, 128, 189).pin_memory() for _ in range(2)] for _ in range(F)]
+    landed = [[None, None] for _ in range(F)]
+    turn = [0] * F
+
+    def e2e_pass(i, k=0):
+        host, hx = work[i % len(work)]
+        c = {kk: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for kk, v in host.items()}
+        x = hx.to(dev, non_blocking=True)
+        out = one_pass(c, x)
+        j = turn[k] & 1
+        turn[k] += 1
+        if landed[k][j] is not None:
+            landed[k][j].synchronize()                 # the joints written two passes ago are on the host
+        outs_host[k][j].copy_(out, non_blocking=True)
+        landed[k][j] = torch.cuda.Event()
+        landed[k][j].record()
         return out
 
-    def pass_e2e():
-        c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        c["lsn_id"], c["spk_is_uncond"] = clip["lsn_id"], clip["spk_is_uncond"]
-        x = host_init.to(dev, non_blocking=True)
-        if W > 0:
-            out = sampler.synthesize_unbounded([c] * W, Ud, Uad, [x] * W, use_graph=not args.no_graph)[-1]
+    # ---- the only collective: output motions.  Each pass's all_gather is issued on a communication stream as soon as
+    # that pass's joints exist (it overlaps the next pass), in step order on every rank, by one gather thread.
+    gathered = [torch.empty(B, 128, 189, device=dev) for _ in range(world)] if world > 1 else None
+
+    class Gatherer:
+        def __init__(self, n):
+            self.n, self.q, self.pending = n, queue.Queue(), {}
+            self.t = threading.Thread(target=self.run, daemon=True)
+            if world > 1:
+                self.t.start()
+
+        def put(self, i, out):
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record()                    # on the producing lane's stream
+                self.q.put((i, out, ev))
+
+        def run(self):
+            torch.cuda.set_device(dev)
+            if hasattr(os, "sched_setaffinity") and my_cores:
+                try:
+                    os.sched_setaffinity(0, {my_cores[-1]})
+                except OSError:
+                    pass
+            nxt = 0
+            while nxt < self.n:
+                i, out, ev = self.q.get()
+                self.pending[i] = (out, ev)
+                while nxt in self.pending:
+                    o, e = self.pending.pop(nxt)
+                    with torch.cuda.stream(comm_stream):
+                        comm_stream.wait_event(e)
+                        dist.all_gather(gathered, o)
+                        o.record_stream(comm_stream)
+                    nxt += 1
+
+        def join(self):
+            if world > 1:
+                self.t.join()
+                torch.cuda.current_stream().wait_stream(comm_stream)
+
+    pool = cf.SamplerPool(sampler, lanes=F, affinity=my_cores) if F > 1 else None
+    use_pool = [pool is not None]
+
+    def run_steps(fn, n):
+        g = Gatherer(n)
+        if use_pool[0]:
+            pool.map(lambda i, k: fn(i, k), list(range(n)), on_result=g.put)
         else:
-            out = sampler.generate(c, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
-        if world > 1:
-            dist.all_gather(gathered, out)
-        out_host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out_host
+            for i in range(n):
+                g.put(i, fn(i, 0))
+        g.join()
 
     def timed(fn, warmup, steps, sample_clocks):
         with torch.cuda.stream(stream):
-            for _ in range(warmup):
-                fn()
+            run_steps(fn, max(warmup, 1) * (F if use_pool[0] else 1))
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -367,8 +608,7 @@ def run_ours(args):
             l0 = _lib.lib().cfb_launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(steps):
-                fn()
+            run_steps(fn, steps)
             e1.record()
             torch.cuda.synchronize()
             if world > 1:
@@ -377,114 +617,79 @@ def run_ours(args):
             ms = e0.elapsed_time(e1)
             launches = _lib.lib().cfb_launch_count() - l0
             ck = clocks.stop() if clocks else None
+        per_rank_ms = None
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, launches, ck
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank_ms = [float(v) for v in allt]
+            ms = max(per_rank_ms)
+        return ms, launches, ck, per_rank_ms
 
-    F = max(1, args.in_flight)
+    ms_dev, launches, clocks, per_rank_ms = timed(device_pass, args.warmup, n_steps, True)
+    ms_e2e, _, _, _ = timed(e2e_pass, 1, n_steps, False)
     single = None
-    if F > 1 and any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_NSIGHT_INJECTION_PORT_BASE")):
-        # Nsight Compute serialises every kernel anyway and its injection library did not survive the lane threads'
-        # concurrent graph captures (profiles/README.md): profile one lane
-        print("bench.py: profiler injection detected, running with one batch in flight", file=sys.stderr)
-        F = 1
-    if W > 0:
-        F = 1      # windows of one stream are serial (preseq + root hand-off)
-    if F > 1:
-        # Successive steps are independent batches, so F of them are kept in flight (convofusion_b200.SamplerPool:
-        # one handle over the same packed weights + one stream + one host thread per lane).  The timed region is
-        # still exactly K full passes over K batches of B clips.
-        pool = cf.SamplerPool(sampler, lanes=F)
-        # e2e: two pinned result buffers per lane; a buffer is waited for only when its turn comes again, so a lane
-        # enqueues its next pass while the previous pass's joints are still on their way to the host
-        outs_host = [[torch.empty(B, 128, 189).pin_memory() for _ in range(2)] for _ in range(F)]
-        landed = [[None, None] for _ in range(F)]
-        turn = [0] * F
+    if pool is not None and not args.sweep:
+        use_pool[0] = False                              # one batch in flight: the latency view
+        k1 = max(2, n_steps // 2)
+        ms_one, _, _, _ = timed(device_pass, args.warmup, k1, False)
+        use_pool[0] = True
+        motion = MOTION_S_PER_CLIP if W == 0 else MOTION_S_PER_CLIP * (W + 1) / 2.0
+        single = {"value": B * world * k1 * motion / (ms_one * 1e-3), "unit": "motion-s/s", "ms_per_step": ms_one / k1}
 
-        def lane_device(_i, k):
-            return sampler.generate(dclip, Ud, Uad, lengths, dinit, use_graph=not args.no_graph)["m_rst"]
-
-        def lane_e2e(_i, k):
-            c = {kk: v.to(dev, non_blocking=True) for kk, v in host.items()}
-            c["lsn_id"], c["spk_is_uncond"] = clip["lsn_id"], clip["spk_is_uncond"]
-            x = host_init.to(dev, non_blocking=True)
-            out = sampler.generate(c, Ud, Uad, lengths, x, use_graph=not args.no_graph)["m_rst"]
-            j = turn[k] & 1
-            turn[k] += 1
-            if landed[k][j] is not None:
-                landed[k][j].synchronize()                 # the joints written two passes ago are on the host
-            outs_host[k][j].copy_(out, non_blocking=True)
-            landed[k][j] = torch.cuda.Event()
-            landed[k][j].record()
-            return out
-
-        def run_steps(fn, n):
-            outs = pool.map(fn, list(range(n)))
-            if world > 1:      # the only collective: output motions, gathered by the main thread once the lanes are
-                for o in outs:  # done (a fixed order on every rank; NCCL calls are not issued from the lane threads)
-                    dist.all_gather(gathered, o)
-
-        def timed_pool(fn, warmup, steps, sample_clocks):
-            with torch.cuda.stream(stream):
-                run_steps(fn, max(warmup, 1) * F)
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                    torch.cuda.synchronize()
-                clocks = ClockSampler(local) if sample_clocks else None
-                if clocks:
-                    clocks.start()
-                l0 = _lib.lib().cfb_launch_count()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                run_steps(fn, steps)
-                e1.record()
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                    torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
-                launches = _lib.lib().cfb_launch_count() - l0
-                ck = clocks.stop() if clocks else None
-            if world > 1:
-                t = torch.tensor([ms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t)
-            return ms, launches, ck
-
-        ms_dev, launches, clocks = timed_pool(lane_device, args.warmup, args.steps, True)
-        ms_e2e, _, _ = timed_pool(lane_e2e, 1, args.steps, False)
-        ms_one, _, _ = timed(pass_device, args.warmup, max(2, args.steps // 2), False)   # one batch in flight: the latency view
-        single = {"value": B * world * max(2, args.steps // 2) * MOTION_S_PER_CLIP / (ms_one * 1e-3), "unit": "motion-s/s",
-                  "ms_per_step": ms_one / max(2, args.steps // 2)}
-    else:
-        ms_dev, launches, clocks = timed(pass_device, args.warmup, args.steps, True)
-        ms_e2e, _, _ = timed(pass_e2e, 1, args.steps, False)
-
-    # split of one pass: conditioning / loop / decode (device events, rank 0 only, untimed extra pass)
-    parts = {}
+    # split of one pass: conditioning / loop / decode (device events; the first repetition warms this call pattern up)
+    roof, extra = None, {}
     with torch.cuda.stream(stream):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        enc, masks = sampler.encode_conditions(dclip, Ud, Uad)
-        ev[1].record()
-        z, _, _ = sampler.sample(enc, masks, B, dinit, use_graph=not args.no_graph)
-        ev[2].record()
-        sampler.decode(z, lengths)
-        ev[3].record()
-        torch.cuda.synchronize()
+        clip0, x0 = dwork[0]
+        for rep in range(2):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            enc, masks = sampler.encode_conditions(clip0, Ud, Uad)
+            ev[1].record()
+            z, _, _ = sampler.sample(enc, masks, B, x0, use_graph=not args.no_graph, spk_is_uncond=not args.dyadic)
+            ev[2].record()
+            sampler.decode(z, lengths)
+            ev[3].record()
+            torch.cuda.synchronize()
         parts = {"conditioning_ms": ev[0].elapsed_time(ev[1]), "loop_ms": ev[1].elapsed_time(ev[2]),
                  "decode_ms": ev[2].elapsed_time(ev[3])}
-        roof = None
         if rank == 0 and args.precision == "bf16" and not args.no_roofline:
-            tf, gemm_ms, n_gemm = gemm_roofline(torch, _lib, B, n_branch, dev)
-            roof = (tf, gemm_ms, n_gemm)
+            chains = 3 if F > 1 else 6
+            roof = gemm_roofline(torch, B, n_branch, dev, chains)
+            roof["mem"] = memory_bound_roofline(torch, B, n_branch, dev, chains)
+    if per_rank_ms:
+        extra["per_rank_ms"] = per_rank_ms
+    if rank == 0 and world == 1 and not args.no_gpu_eager and not W and not args.sweep:
+        # PyTorch eager on the same B200 (SURVEY 8d / BASELINE.md 4.5): the oracle port with its tensors on the GPU,
+        # TF32 off, and once under bf16 autocast; the full 7 x B batch, 5 of the DDIM steps timed
+        try:
+            eager = {}
+            for tag, ac in (("fp32", False), ("bf16_autocast", True)):
+                ref = ReferencePass(B, args.ddim_steps, args.dyadic, dev, autocast=ac)
+                ref.run(2)
+                r = ref.run(5)
+                eager[tag] = {"value": r["value"], "unit": "motion-s/s", "ms_per_denoiser_step": r["ms_per_denoiser_step"],
+                              "decode_ms": r["decode_ms"]}
+                del ref
+            eager["what"] = ("oracle port of the reference (plain torch ops, all 7 branches as written) with its tensors on "
+                             "this GPU, TF32 off; conditioning + 5 of the DDIM steps timed (step count extrapolated) + decode")
+            extra["gpu_eager_baseline"] = eager
+            torch.cuda.empty_cache()
+        except Exception as exc:      # a baseline leg must never take the benchmark line down
+            extra["gpu_eager_baseline"] = {"unavailable": repr(exc)[:300]}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        ref = ReferencePass(B, args.ddim_steps, args.dyadic, "cpu", cores)
+        ref.run(1)
+        r = ref.run(2)
+        extra["cpu_baseline"] = {"value": r["value"], "unit": "motion-s/s", "cores": cores, "kind": "port",
+                                 "sample": cpu_sample_text(B, args.ddim_steps, 2, cores),
+                                 "ms_per_denoiser_step": r["ms_per_denoiser_step"]}
 
     if rank == 0:
         line = assemble_line(args, world=world, B=B, F=F, n_branch=n_branch, ms_dev=ms_dev, ms_e2e=ms_e2e, launches=launches,
-                             clocks=clocks, parts=parts, roof=roof, single=single, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes)
+                             clocks=clocks, parts=parts, roof=roof, single=single, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes,
+                             steps=n_steps, clips_total=args.sweep if args.sweep else None, extra=extra)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -4,6 +4,7 @@ Public surface (mirrors the reference's operator surface):
   Denoiser, ConvoFusionVae            drop-in modules (identical state_dict keys and call signatures)
   DDIMScheduler, DDPMScheduler        diffusers-0.14-compatible scheduler mirrors
   ConvoFusionSampler                  test_diffusion_forward / unbounded synthesis orchestration
+  MotionWriter                        pred.npy / gt.npy / att_*.npy output layout of base.py:save_npy, asynchronous D2H
   SamplerPool                         several independent batches in flight on one GPU (one handle + stream per lane)
   slice_windows, window_text          host-side window bookkeeping of unbounded synthesis (process_samples / process_text)
 All arithmetic runs in lib/libconvofusion_b200.so (hand-written CUDA, C ABI in include/convofusion_b200.h).
@@ -14,8 +15,9 @@ from .conditioning import AudioConvEncoder, T5TextEncoder, TextAudioController, 
 from .sampler import ConvoFusionSampler, default_denoiser, default_scheduler, default_vae
 from .postprocess import keypoints3d
 from .pool import SamplerPool
+from .writer import MotionWriter
 from .windows import slice_windows, window_spans, window_text
 
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
-           "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool", "slice_windows", "window_spans", "window_text"]
+           "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool", "MotionWriter", "slice_windows", "window_spans", "window_text"]

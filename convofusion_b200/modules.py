@@ -108,22 +108,27 @@ _lane_lock = threading.RLock()   # handle creation (module-level: nn.Modules mus
 
 
 @contextlib.contextmanager
-def lane(index: int):
+def lane(index: int, chains: Optional[int] = None):
     """Selects the device handle the calling thread's Denoiser / ConvoFusionVae calls run on.
 
     A handle owns one workspace and one captured step graph, so it serves one call at a time.  Lane k > 0 is an
     extra handle over the SAME packed weights, created on first use; `SamplerPool` (pool.py) runs one host thread +
     one stream per lane to keep several independent batches in flight on one GPU."""
-    prev = getattr(_lane_state, "index", 0)
-    _lane_state.index = int(index)
+    prev, prev_chains = getattr(_lane_state, "index", 0), getattr(_lane_state, "chains", None)
+    _lane_state.index, _lane_state.chains = int(index), chains
     try:
         yield
     finally:
-        _lane_state.index = prev
+        _lane_state.index, _lane_state.chains = prev, prev_chains
 
 
 def current_lane() -> int:
     return getattr(_lane_state, "index", 0)
+
+
+def current_chains() -> Optional[int]:
+    """Concurrent chains per captured step requested for the calling thread's lane (None = the module's setting)."""
+    return getattr(_lane_state, "chains", None)
 
 
 class _CudaModule(nn.Module):
@@ -378,7 +383,8 @@ class Denoiser(_CudaModule):
             att = [torch.empty(len(ts), B, self.num_layers, self.n_tokens, mem.len[i], device=dev) for i in range(5)]
             att_ptrs = (C.c_void_p * 5)(*[a.data_ptr() for a in att])
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().cfb_denoiser_set_chains(h, int(self.step_chains)))
+            chains = current_chains()
+            _lib.check(_lib.lib().cfb_denoiser_set_chains(h, int(self.step_chains if chains is None else chains)))
             _lib.check(_lib.lib().cfb_sample(h, C.byref(sched), C.byref(mem), B, n_branch, int(bool(full_last)), x.data_ptr(),
                                              _lib.ptr(step_noise), _lib.ptr(preseq), pl, _lib.ptr(rec), att_ptrs,
                                              int(use_graph), _lib.stream_ptr()))

@@ -36,10 +36,11 @@ def _record_stream(obj: Any, stream: torch.cuda.Stream) -> None:
 
 
 class SamplerPool:
-    def __init__(self, sampler, lanes: int = 2, chains: Optional[int] = None):
+    def __init__(self, sampler, lanes: int = 2, chains: Optional[int] = None, affinity: Optional[Sequence[int]] = None):
         """chains: concurrent chains inside each lane's captured step (Denoiser.step_chains) while the pool runs;
         default 3 with two or more lanes (the lanes already supply concurrency: measured 6.18 k vs 6.00 k motion-s/s
-        with 6), the library default otherwise."""
+        with 6), the library default otherwise.  affinity: host cores the lane threads are pinned to (lane k ->
+        affinity[k % len]); several processes per node (one per GPU) then do not migrate over each other."""
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
         if lanes > 1 and os.environ.get("CFB_TC_2CTA", "0") not in ("", "0"):
@@ -48,6 +49,7 @@ class SamplerPool:
         self.sampler = sampler
         self.lanes = int(lanes)
         self.chains = int(chains) if chains is not None else (3 if lanes > 1 else 0)
+        self.affinity = list(affinity) if affinity else None
         self._streams: Optional[List[torch.cuda.Stream]] = None
 
     def _device(self) -> torch.device:
@@ -59,8 +61,10 @@ class SamplerPool:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
         return self._streams
 
-    def map(self, fn: Callable[[Any, int], Any], items: Sequence[Any]) -> List[Any]:
-        """Runs fn(item, lane_index) for every item, `lanes` at a time; results in item order.
+    def map(self, fn: Callable[[Any, int], Any], items: Sequence[Any],
+            on_result: Optional[Callable[[int, Any], None]] = None) -> List[Any]:
+        """Runs fn(item, lane_index) for every item, `lanes` at a time; results in item order.  on_result(i, result)
+        is called on the lane's thread (lane stream current) as soon as item i has been enqueued.
 
         Inside fn the calling thread's current stream is the lane's stream and Denoiser / ConvoFusionVae calls run
         on the lane's handle.  Work already queued on the caller's current stream is visible to every lane, and the
@@ -79,30 +83,32 @@ class SamplerPool:
         def worker(k: int):
             try:
                 torch.cuda.set_device(dev)
-                with lane(k), torch.cuda.stream(streams[k]), torch.no_grad():
+                if self.affinity and hasattr(os, "sched_setaffinity"):
+                    try:
+                        os.sched_setaffinity(0, {self.affinity[k % len(self.affinity)]})   # this thread only
+                    except OSError:
+                        pass
+                with lane(k, chains=self.chains), torch.cuda.stream(streams[k]), torch.no_grad():
                     while not errors:
                         try:
                             i, it = todo.get_nowait()
                         except queue.Empty:
                             return
                         results[i] = fn(it, k)
+                        if on_result is not None:
+                            on_result(i, results[i])
             except BaseException as exc:      # re-raised on the calling thread
                 errors.append(exc)
 
         n = min(self.lanes, max(1, len(items)))
-        den = self.sampler.denoiser
-        prev_chains, den.step_chains = den.step_chains, self.chains
-        try:
-            if n == 1:
-                worker(0)
-            else:
-                threads = [threading.Thread(target=worker, args=(k,), name=f"cfb-lane-{k}") for k in range(n)]
-                for t in threads:
-                    t.start()
-                for t in threads:
-                    t.join()
-        finally:
-            den.step_chains = prev_chains
+        if n == 1 and not self.affinity:
+            worker(0)
+        else:      # (with an affinity list even one lane runs on its own thread: the caller's affinity is left alone)
+            threads = [threading.Thread(target=worker, args=(k,), name=f"cfb-lane-{k}") for k in range(n)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
         for s in streams:
             caller.wait_stream(s)
         if errors:

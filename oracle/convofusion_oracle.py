@@ -2,7 +2,9 @@
 
 This file is a plain torch-CPU, state_dict-driven restatement of the reference's
 sampling path.  It is imported only by tests/, __graft_entry__.smoke() and the
-cpu_baseline / --impl reference legs of bench.py -- never by the product package
+baseline legs of bench.py (cpu_baseline / --impl reference on the host cores;
+gpu_eager_baseline = the same eager torch code with its tensors on the B200, the
+"PyTorch eager on the same box" yardstick of SURVEY 8d) -- never by the product package
 (convofusion_b200/), which must fail loudly when its CUDA library is missing.
 
 Pinning status
@@ -55,7 +57,7 @@ def timestep_embedding(timesteps: Tensor, dim: int, flip_sin_to_cos: bool = True
                        freq_shift: float = 0.0) -> Tensor:
     """embeddings.py:245-285 (scale=1, max_period=10000)."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device)
     exponent = exponent / (half - freq_shift)
     emb = torch.exp(exponent)
     emb = timesteps[:, None].float() * emb[None, :]
@@ -96,7 +98,7 @@ def mha(query: Tensor, key: Tensor, value: Tensor, in_w: Tensor, in_b: Tensor,
     v = v.reshape(S, B * nheads, hd).transpose(0, 1)
     scores = torch.bmm(q * math.sqrt(1.0 / hd), k.transpose(1, 2))  # [B*H, L, S]
     if key_padding_mask is not None:
-        m = torch.zeros(B, 1, 1, S, dtype=scores.dtype)
+        m = torch.zeros(B, 1, 1, S, dtype=scores.dtype, device=scores.device)
         m = m.masked_fill(key_padding_mask.view(B, 1, 1, S), float("-inf"))
         scores = (scores.view(B, nheads, L, S) + m).view(B * nheads, L, S)
     attn = torch.softmax(scores, dim=-1)
@@ -162,7 +164,7 @@ def denoiser_forward(sd: Dict[str, Tensor], sample: Tensor, timestep, enc: Seque
     x = sample.permute(1, 0, 2)
     x = _lin(sd, p + "latent_embd.", x)                                   # :187
     bs = x.shape[1]
-    t = torch.as_tensor(timestep).reshape(-1)[:1].expand(bs)
+    t = torch.as_tensor(timestep).to(x.device).reshape(-1)[:1].expand(bs)
     temb = timestep_embedding(t, d, True, 0.0).to(x.dtype)                # :195-197
     temb = _lin(sd, p + "time_embedding.linear_2.",
                 F.silu(_lin(sd, p + "time_embedding.linear_1.", temb))).unsqueeze(0)  # :199
@@ -228,12 +230,12 @@ def vae_decode(sd: Dict[str, Tensor], z: Tensor, lengths: Sequence[int], prefix:
     """vae.py:268-372 (arch=encoder_decoder, pe_type=convofusion).
     z [2, B, n_chunks, latent]; returns [B, nframes, 189]."""
     p = prefix
-    mask = lengths_to_mask(lengths)
+    mask = lengths_to_mask(lengths).to(z.device)
     bs, nframes = mask.shape
     dlat = z.shape[-1]
     pe_q = sd[p + "query_pos_decoder.pe"][:, 0]
     pe_m = sd[p + "mem_pos_decoder.pe"][:, 0]
-    queries = torch.zeros(nframes, bs, dlat, dtype=z.dtype) + pe_q[:nframes, None]   # :277,321
+    queries = torch.zeros(nframes, bs, dlat, dtype=z.dtype, device=z.device) + pe_q[:nframes, None]   # :277,321
     outs = []
     for part, zz in zip(("body", "hands"), torch.chunk(z, 2, dim=0)):
         m = zz.squeeze(0).permute(1, 0, 2)                                           # :279-285
@@ -328,7 +330,7 @@ def text_projection(sd, t5_hidden: Tensor,
 def condition_fuser(sd, apb: Tensor, lsn_id: Sequence[int], prefix: str = "condition_fuser."):
     """condfuser.py:32-51: two embedding lookups."""
     a = sd[prefix + "active_passive_emb.weight"][apb.long()]
-    l = sd[prefix + "lsn_id_emb.weight"][torch.as_tensor(list(lsn_id)).long()].unsqueeze(1)
+    l = sd[prefix + "lsn_id_emb.weight"][torch.as_tensor(list(lsn_id), device=apb.device).long()].unsqueeze(1)
     return a, l
 
 

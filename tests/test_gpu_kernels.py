@@ -194,3 +194,33 @@ def test_keypoints3d_is_bit_exact():
     assert got.shape == (5, 37, 63, 3) and torch.equal(got.cpu(), want)
     with pytest.raises(_lib.CfbError):
         cf.keypoints3d(x)
+
+
+def test_motion_writer_npy_layout(tmp_path):
+    """pred.npy / gt.npy / att_*.npy as base.py:save_npy lays them out (key points [length, 63, 3], cut to the
+    sample's length; attention map of batch entry 0 per recorded timestep), written behind an asynchronous D2H copy."""
+    import numpy as np
+    g = torch.Generator().manual_seed(21)
+    pred, gt = torch.randn(3, 128, 189, generator=g), torch.randn(3, 128, 189, generator=g)
+    lengths, keys = [128, 100, 37], ["a_1", "b_2", "c_3"]
+    att = {981: [torch.rand(3, 9, 16, m, generator=g) for m in (32, 161, 32, 8, 1)],
+           1: [torch.rand(3, 9, 16, m, generator=g) for m in (32, 161, 32, 8, 1)]}
+    with cf.MotionWriter(tmp_path, ring=2) as w:
+        for rep in range(3):          # more batches than ring slots: slots are recycled
+            w.submit(pred.to(DEV) + rep, lengths, [k + f"_{rep}" for k in keys], m_ref=gt.to(DEV),
+                     att_maps={t: [a.to(DEV) for a in maps] for t, maps in att.items()} if rep == 0 else None)
+        w.flush()
+        assert w.files_written == 3 * 2 * 3 + 3 * 2 * 5
+    for rep in range(3):
+        want = O.feats_to_keypoints3d((pred + rep).reshape(-1, 189)).reshape(3, 128, 63, 3).numpy()
+        want_gt = O.feats_to_keypoints3d(gt.reshape(-1, 189)).reshape(3, 128, 63, 3).numpy()
+        for i, (k, L) in enumerate(zip(keys, lengths)):
+            p = np.load(tmp_path / f"{k}_{rep}" / "pred.npy")
+            assert p.shape == (L, 63, 3) and p.dtype == np.float32 and np.array_equal(p, want[i, :L])
+            assert np.array_equal(np.load(tmp_path / f"{k}_{rep}" / "gt.npy"), want_gt[i, :L])
+    for k in keys:
+        for name, maps_t in (("att_alsn", 1), ("att_lsnemb", 4)):
+            a = np.load(tmp_path / f"{k}_0" / name / "att_981.npy")
+            assert np.array_equal(a, att[981][maps_t][0].numpy())
+    with pytest.raises(_lib.CfbError):
+        cf.MotionWriter(tmp_path).submit(pred, lengths, keys)

@@ -284,11 +284,13 @@ def test_bench_line_assembly_carries_the_contract_keys():
     clocks = {"sm_mhz": 1965, "sm_max_mhz": 1965, "reasons": [], "samples": 4}
     for windows, world, F in ((0, 1, 2), (0, 1, 1), (12, 1, 1), (0, 8, 2)):
         args = types.SimpleNamespace(steps=16, warmup=3, ddim_steps=50, precision="bf16", dyadic=False, windows=windows,
-                                     no_cpu_baseline=True, batch=64)
+                                     no_cpu_baseline=True, batch=64, sweep=0)
         single = {"value": 5000.0, "unit": "motion-s/s", "ms_per_step": 65.5} if F > 1 else None
         per_step = 53.7 * max(1, windows)                               # a step of W serial windows takes W passes
         line = bench.assemble_line(args, world=world, B=64, F=F, n_branch=6, ms_dev=16 * per_step, ms_e2e=16 * per_step * 1.01,
-                                   launches=400000, clocks=clocks, parts=parts, roof=(451.0, 0.74, 72), single=single,
+                                   launches=400000, clocks=clocks, parts=parts,
+                                   roof={"tflops": 451.0, "ms": 0.74, "launches": 72, "kernel": "k", "mem": {"bound": "hbm"}},
+                                   single=single,
                                    h2d_bytes=16441344, d2h_bytes=6193152)
         json_line = __import__("json").dumps(line)                      # serialisable
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -298,7 +300,8 @@ def test_bench_line_assembly_carries_the_contract_keys():
         assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
         motion_s = 5.12 if windows == 0 else 5.12 * (windows + 1) / 2
         assert abs(line["value"] - 64 * world * motion_s / (per_step * 1e-3)) < 1e-6 * line["value"]
-        assert abs(line["ms_per_step"] - per_step) < 1e-9 and line["config"]["batches_in_flight"] == F
+        assert abs(line["ms_per_step"] - per_step) < 1e-9 and line["execution"]["batches_in_flight"] == F
+        assert line["roofline_mem"] == {"bound": "hbm"} and line["execution"]["guidance_branches_evaluated"] == 6
         r = line["roofline"]
         assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
         assert r["peak"] >= r["sustained_peak"] > 0 and (r["traffic"] is None or r["traffic"] > 0)
