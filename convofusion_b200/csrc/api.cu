@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 int init_gemm_tc_kernels();
 int init_attention_kernels();
 int tc_trace_read(unsigned long long out[16]);
+extern int g_rb_trace_kind, g_rb_trace_layer;   // denoiser.cu
 
 static int ensure_device() {
   int ndev = 0;
@@ -48,6 +49,14 @@ int cfb_debug_rb_fault(unsigned* out8) {
   for (int i = 0; i < 8; ++i) out8[i] = f ? f[i] : 0u;
   return CFB_OK;
 }
+
+// Debug only: arm phase tracing of the next launch of program `kind` of `layer` (eager launches only), read it back.
+int cfb_debug_rb_trace_arm(int kind, int layer, int n) {
+  cfb::g_rb_trace_kind = kind; cfb::g_rb_trace_layer = layer;
+  cfb::rowblock_trace_arm(n);
+  return CFB_OK;
+}
+int cfb_debug_rb_trace_read(unsigned long long* out64) { return cfb::rowblock_trace_read(out64); }
 
 int cfb_abi_version(void) { return CFB_ABI_VERSION; }
 const char* cfb_last_error(void) { return g_err; }

@@ -47,8 +47,12 @@ namespace cfb {
 int g_shared_plan = getenv("CFB_PLAN") ? atoi(getenv("CFB_PLAN")) : 1;   // cfb_set_shared_plan / env CFB_PLAN=0
 // Row-block kernel (rowblock.cu) for the residual chains of a layer; bit 0: out_proj -> TimeBlock 1 -> norm2,
 // bit 1: shared values (+ conditional fuser block) -> TimeBlock 2 -> norm3, bit 2: linear2 -> next norm1.
-// cfb_set_rowblock / env CFB_ROWBLOCK (0 = the one-kernel-per-operator path everywhere).
-int g_rowblock = getenv("CFB_ROWBLOCK") ? atoi(getenv("CFB_ROWBLOCK")) : 7;
+// cfb_set_rowblock / env CFB_ROWBLOCK.  Default 0 (one kernel per operator): measured on the B200 the row-block
+// programs are correct but SLOWER at the reference's batch sizes -- a 128-row block is serialised on one SM (MMA phase,
+// then statistics pass, then LayerNorm pass: 63 us per two-GEMM chain, profiles/r02_rowblock_trace.txt) while the
+// operator path spreads the same rows over 4 n-tiles x 2 co-resident CTAs.
+int g_rowblock = getenv("CFB_ROWBLOCK") ? atoi(getenv("CFB_ROWBLOCK")) : 0;
+int g_rb_trace_kind = -1, g_rb_trace_layer = -1;   // debug: which program to trace (cfb_debug_rb_trace_arm)
 }
 
 using namespace cfb;
@@ -293,6 +297,7 @@ int rowblock_run(cfb_denoiser* h, int layer, int kind, int row0, int R, int rows
   L.blk_stream = h->rb_blk.as<int>();
   L.step_ptr = step_ptr;
   L.h = h->h.as<float>(); L.a = h->a.as<bf16>(); L.rows_total = rows_total;
+  L.trace = (g_rb_trace_kind == kind && g_rb_trace_layer == layer);
   return rowblock_launch(L, st);
 }
 

@@ -60,7 +60,18 @@ struct RbParams {
   const int* blk_stream;
   const int* step_ptr;
   unsigned* fault;
+  unsigned long long* trace;   // debug: globaltimer stamps of row block `block0` (null in production)
 };
+
+// trace slots: [0] start, then 8 per stage: 0 A/residual ready for the MMAs, 1 first operands landed, 2 all MMAs
+// issued, 3 accumulators complete (epilogue woke up), 4 statistics pass done, 5 LayerNorm pass done, 6 stores issued
+__device__ __forceinline__ void rb_trace(const RbParams& p, int stage, int what) {
+  if (p.trace != nullptr && blockIdx.x == 0 && stage < 7) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[stage < 0 ? what : 1 + 8 * stage + what] = t;
+  }
+}
 
 __device__ __forceinline__ void rb_wait(uint32_t bar, uint32_t parity, const RbParams& p, int stage, int code) {
   if (mbar_try_wait(bar, parity)) return;
@@ -120,6 +131,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + OFF_BAR + 8 * B_TMEM_SLOT);
   pdl_sync();   // everything above touched only shared / tensor memory
   const int x = p.blk_stream ? p.blk_stream[blk] : -1;
+  if (threadIdx.x == 0) rb_trace(p, -1, 0);
   const int n_stages = p.n_stages;
   const RbStage* prog = p.prog;
 
@@ -207,6 +219,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
           ++epi_seen;
         }
         tc_fence_after();
+        rb_trace(p, i, 0);
         const bool commit_a = rb_commit_a(prog, n_stages, i, x);
         for (int kb = 0; kb < nkb; ++kb) {
           if (st.a_src == RB_A_TMA) {
@@ -219,6 +232,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
             const uint32_t s = w_it & (W_STAGES - 1);
             rb_wait(bar(B_W_FULL + s), (w_it / W_STAGES) & 1u, p, i, 22);
             tc_fence_after();
+            if (kb == 0 && nt == 0) rb_trace(p, i, 1);
             const uint64_t bdesc = make_smem_desc(sW + s * W_TILE);
 #pragma unroll
             for (int k = 0; k < 4; ++k)     // the accumulator already holds the residual rows: always accumulate
@@ -229,6 +243,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
           if (commit_a) umma_commit(bar(B_A_EMPTY + kb));
         }
         if (st.epi != RB_EPI_NONE) umma_commit(bar(B_ACC_FULL));
+        rb_trace(p, i, 2);
         prev_epi = st.epi == RB_EPI_LN;
       }
     }
@@ -266,12 +281,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(B_EPI_DONE));
+        if (ew == 0 && lane == 0) rb_trace(p, i, 5);
         continue;
       }
       if (st.epi == RB_EPI_NONE) continue;
       rb_wait(bar(B_ACC_FULL), acc_seen & 1u, p, i, 31);
       ++acc_seen;
       tc_fence_after();
+      if (ew == 0 && lane == 0) rb_trace(p, i, 3);
       const int nx = rb_next(prog, n_stages, i, x);
       const bool park = nx >= 0 && prog[nx].kind == RB_GEMM;     // more residual updates follow in this launch
       const float* bias = st.bias;
@@ -301,6 +318,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
       const float mean = (s1 + o.x) * (1.0f / 512.0f);
       const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / 512.0f) - mean * mean, 0.f) + 1e-5f);
       const float nmr = -mean * rstd;
+      if (ew == 0 && lane == 0) rb_trace(p, i, 4);
       // ---- pass 2: LayerNorm (+ modulation + SiLU) -> next A operand; park / spill the updated rows
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
@@ -371,6 +389,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_EPI_DONE));
+      if (ew == 0 && lane == 0) rb_trace(p, i, 5);
       if (st.store_a) {
         asm volatile("bar.sync 1, 256;" ::: "memory");          // all eight warps' panel writes are fenced
         if (ew == 0 && lane == 0) {
@@ -379,9 +398,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
           tma_wait_read0();
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");          // nobody rewrites the panels while the TMA unit reads them
+        if (ew == 0 && lane == 0) rb_trace(p, i, 6);
       }
     }
     if (lane == 0 && stored) tma_wait_read0();
+    if (ew == 0 && lane == 0) rb_trace(p, -1, 63);
   }
   tc_fence_before();
   __syncthreads();
@@ -393,10 +414,20 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rowblock_kernel(const __grid_co
 
 unsigned* g_fault_host = nullptr;
 unsigned* g_fault_dev = nullptr;
+unsigned long long* g_trace_dev = nullptr;
+int g_trace_armed = 0;
 
 }  // namespace
 
 const unsigned* rowblock_fault_record() { return g_fault_host; }
+
+// Debug: the NEXT `n` rowblock_launch calls with trace = true record phase timestamps of their first row block.
+void rowblock_trace_arm(int n) { g_trace_armed = n; }
+int rowblock_trace_read(unsigned long long out[64]) {
+  if (!g_trace_dev) { memset(out, 0, 64 * 8); return CFB_OK; }
+  CFB_CUDA(cudaMemcpy(out, g_trace_dev, 64 * 8, cudaMemcpyDeviceToHost));
+  return CFB_OK;
+}
 
 int init_rowblock_kernels() {
   static std::mutex mu;
@@ -410,6 +441,8 @@ int init_rowblock_kernels() {
     CFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_fault_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
     memset(g_fault_host, 0, 64);
     CFB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_fault_dev), g_fault_host, 0));
+    CFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), 64 * 8));
+    CFB_CUDA(cudaMemset(g_trace_dev, 0, 64 * 8));
   }
   if (dev < 64) done_mask |= 1ull << dev;
   return CFB_OK;
@@ -427,6 +460,8 @@ int rowblock_launch(const RbLaunch& L, cudaStream_t st) {
   RbParams p;
   p.prog = L.prog; p.n_stages = L.n_stages; p.block0 = L.block0; p.blk_stream = L.blk_stream; p.step_ptr = L.step_ptr;
   p.fault = g_fault_dev;
+  p.trace = nullptr;
+  if (L.trace && g_trace_armed > 0 && !t_capturing) { p.trace = g_trace_dev; --g_trace_armed; }
   launch_k(rowblock_kernel, dim3(L.n_blocks), dim3(RB_THREADS), RB_SMEM, st, th, ta, p);
   CFB_LAUNCH_CHECK();
   return CFB_OK;

@@ -48,6 +48,7 @@ struct RbLaunch {
   float* h;                 // residual stream [rows_total, 512] fp32
   bf16* a;                  // A operand buffer [rows_total, 512] bf16 (store_a target)
   int rows_total;
+  int trace;                // debug: candidate for phase tracing (rowblock_trace_arm)
 };
 
 int init_rowblock_kernels();
@@ -56,5 +57,7 @@ int rowblock_launch(const RbLaunch& L, cudaStream_t st);
 int rowblock_operand_map(const void* p, int rows, int cols, int ld, CUtensorMap* out);
 // host-mapped fault record of the last protocol timeout: {code, block, warp, stage, barrier}; all zero = none
 const unsigned* rowblock_fault_record();
+void rowblock_trace_arm(int n);
+int rowblock_trace_read(unsigned long long out[64]);
 
 }  // namespace cfb

@@ -55,8 +55,9 @@ int cfb_set_shared_plan(int enabled);
 /* Row-block kernel (one persistent tcgen05 CTA per 128 query rows runs a layer's residual chains -- GEMM, residual
  * add, LayerNorm / TimeBlock modulation / SiLU, next GEMM -- on rows resident in tensor memory) in cfb_sample's bf16
  * step: bit 0 out_proj -> time_block1 -> norm2, bit 1 cross-attention values / fuser -> time_block2 -> norm3,
- * bit 2 linear2 -> next norm1.  Default 7; 0 = one kernel per operator.  Same arithmetic up to summation order and
- * the LayerNorm statistics formula. */
+ * bit 2 linear2 -> next norm1.  Default 0 = one kernel per operator (the row-block programs are verified but slower at
+ * the reference's batch sizes); 7 = all.  Same arithmetic up to summation order and the LayerNorm
+ * statistics formula. */
 int cfb_set_rowblock(int mask);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);

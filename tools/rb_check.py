@@ -61,7 +61,7 @@ def run(B=8, steps=2, dyadic=True, masks=(1, 2, 4, 7), scale=1.0, dev="cuda:0", 
         print("FAILED:", exc, "| row-block fault record {code, block, warp, stage, barrier, parity}:", fault())
         raise
     finally:
-        lib.cfb_set_rowblock(7)
+        lib.cfb_set_rowblock(0)
     if verbose:
         print(f"B={B} steps={steps} dyadic={dyadic} guidance_scale={scale}")
         print(f"  operator path vs fp32: first {res['operator_vs_fp32'][0]:.3e} last {res['operator_vs_fp32'][1]:.3e}")
