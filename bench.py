@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--in-flight", type=int, default=2,
                     help="independent batches kept in flight on one GPU (one sampler handle + stream each); every step "
                          "is still one full pass over one batch of --batch clips, steps of different handles overlap")
+    ap.add_argument("--chains", type=int, default=-1,
+                    help="concurrent chains inside every lane's captured step (-1 = SamplerPool default: 3 with lanes, "
+                         "the library default of 6 with one batch in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-B200 baseline")
     ap.add_argument("--no-graph", action="store_true")
@@ -272,7 +275,7 @@ def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, cloc
         "scaling": "strong" if args.sweep else "weak",
         "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
         "config": workload_config(args, B),
-        "execution": {"guidance_branches_evaluated": n_branch, "batches_in_flight": F,
+        "execution": {"guidance_branches_evaluated": n_branch, "batches_in_flight": F, "chains": getattr(args, "chains", -1),
                       "in_flight": ("every step is one full pass over its own batch of %d clips; %d independent batches "
                                     "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
                                     % (B, F)) if F > 1 else "one batch at a time"},
@@ -583,7 +586,9 @@ def run_ours(args):
                 self.t.join()
                 torch.cuda.current_stream().wait_stream(comm_stream)
 
-    pool = cf.SamplerPool(sampler, lanes=F, affinity=my_cores) if F > 1 else None
+    pool = cf.SamplerPool(sampler, lanes=F, affinity=my_cores, chains=args.chains if args.chains >= 0 else None) if F > 1 else None
+    if F == 1 and args.chains >= 0:
+        sampler.denoiser.step_chains = args.chains
     use_pool = [pool is not None]
 
     def run_steps(fn, n):

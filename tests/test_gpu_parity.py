@@ -18,10 +18,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 # bf16 mode: operands of every GEMM and the attention memory are bf16 (8 mantissa bits, ~4e-3 per rounding);
-# residual stream, LayerNorm statistics, softmax, guidance combine and scheduler stay fp32.  One denoiser
-# evaluation lands at ~1e-2 relative L2; the -36.5/+7.5 guidance weights amplify branch-differential error, so
-# per-step latents are held to 5e-2 of scale for >= 90 % of elements and final joints to 1e-1 max-relative.
-BF16_TOL = {"eps_l2": 3e-2, "latent_frac_tol": 5e-2, "latent_frac": 0.5, "latent_l2": 0.3, "joints": 0.5}
+# residual stream, LayerNorm statistics, softmax, guidance combine and scheduler stay fp32.  Measured on the B200
+# (round 2): one denoiser evaluation 4.2e-3 relative L2; the -36.5/+7.5 guidance weights amplify branch-differential
+# rounding and random-init weights make the trajectory chaotic, so over 50 DDIM steps the latents drift to 0.16-0.20
+# relative L2 (0.05-0.06 after the first step) with >= 58 % of the elements within 5e-2 of the tensor scale at every
+# step and >= 90 % within 0.3 of it, and the decoded joints land within 2.5e-2 max-relative.  Every entry is at most
+# 2x its measured value.
+BF16_TOL = {"eps_l2": 8e-3, "latent_frac_tol": 5e-2, "latent_frac": 0.5, "latent_l2": 0.3, "joints": 5e-2,
+            "latent_frac90_tol": 0.3}
 
 _samplers = {}
 
@@ -385,10 +389,13 @@ def test_bf16_sampling_run_vs_reference_golden():
         rec = rec.cpu()
         l2 = [rel_err(rec[i], g["record"][i]) for i in range(50)]
         fr = [frac_within(rec[i], g["record"][i], BF16_TOL["latent_frac_tol"]) for i in range(50)]
+        fr90 = min(frac_within(rec[i], g["record"][i], BF16_TOL["latent_frac90_tol"]) for i in range(50))
         ej = max_rel(sb.decode(z, [128]).cpu(), g["joints"])
         print(f"bf16 vs reference golden (speaker branch dropped: {mono}): latents L2 first/max/last {l2[0]:.3f}/{max(l2):.3f}/"
               f"{l2[-1]:.3f}; min frac within {BF16_TOL['latent_frac_tol']}: {min(fr):.3f}; joints max-rel {ej:.3e}")
+        print(f"   min fraction within {BF16_TOL['latent_frac90_tol']} of scale: {fr90:.3f}")
         assert max(l2) < BF16_TOL["latent_l2"] and min(fr) >= BF16_TOL["latent_frac"] and ej < BF16_TOL["joints"]
+        assert fr90 >= 0.9
 
 
 def test_shared_slot_plan_equals_general_path():
@@ -410,7 +417,7 @@ def test_shared_slot_plan_equals_general_path():
             _, rec32, _ = sf.sample(enc, masks, 5, init, record=True)
             e_pg, e_p32, e_g32 = rel_err(rec_plan[-1], rec_gen[-1]), rel_err(rec_plan[-1], rec32[-1]), rel_err(rec_gen[-1], rec32[-1])
             print(f"steps={steps} att={want_att}: plan-vs-general {e_pg:.2e}, plan-vs-fp32 {e_p32:.2e}, general-vs-fp32 {e_g32:.2e}")
-            assert e_p32 < 2.5 * max(e_g32, 1e-2) and e_pg < 2.5 * max(e_g32, 1e-2)
+            assert e_p32 < 1.5 * max(e_g32, 1e-2) and e_pg < 2.0 * max(e_g32, 1e-2)      # measured 1.12x / 1.39x
             if want_att and steps == 1:   # later steps start from latents that already differ by bf16 noise
                 assert max_rel(att_plan[1].cpu(), att_gen[1].cpu()) < 5e-2
 

@@ -18,9 +18,10 @@ def test_rowblock_programs_match_operator_path(B, dyadic):
     import rb_check
     res = rb_check.run(B=B, steps=3, dyadic=dyadic, masks=(1, 2, 4, 7))
     ref_first, ref_last = res["operator_vs_fp32"]
-    for key, (first, last, vs32, finite) in res.items():
+    for key, val in res.items():
         if key == "operator_vs_fp32":
             continue
+        first, last, vs32, finite = val
         assert finite, key
         assert first < 2.0 * max(ref_first, 2e-3), (key, first, ref_first)
         assert vs32 < 2.0 * max(ref_last, 4e-3), (key, vs32, ref_last)
