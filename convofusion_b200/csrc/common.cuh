@@ -136,6 +136,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- fp32-accurate tensor-core GEMMs (gemm_split.cu): resources of one call chain
+struct SplitCache;
+struct SplitCtx {
+  void* a_ws; size_t a_ws_bytes;   // stream-ordered scratch for the split of a dynamic A operand
+  void* w_ws; size_t w_ws_bytes;   // ... of a dynamic W operand
+  SplitCache* cache;               // splits of static operands (weights), filled on first use outside stream capture
+};
+SplitCache* split_cache_create();
+void split_cache_destroy(SplitCache* c);
+size_t split_cache_bytes(const SplitCache* c);
+
 // ---- epilogue description shared by the SIMT and tcgen05 GEMMs -------------------
 struct Epilogue {
   const float* bias;   // [bias_period, N] (period 1 = ordinary bias) or nullptr
@@ -148,6 +159,9 @@ struct Epilogue {
   int replicate;       // write `replicate` copies, copy c at out + c * rep_stride elements
   long long rep_stride;
   int tma_out;               // set by gemm_tc: output tile leaves through TMA store / reduce-add (internal)
+  // fp32 operands on the tensor cores (3-way bf16 split, gemm_split.cu): null = CUDA-core GEMM for fp32 operands
+  const SplitCtx* split;
+  int a_static, w_static;    // the operand is a weight (its split is cached) rather than an activation
 };
 
 // GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.
@@ -166,6 +180,9 @@ struct TcGroup {
 int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
                     const Epilogue& ep, cudaStream_t st);
 extern int g_gemm_backend;
+bool gemm_split_supported(int M, int N, int K, long long lda, long long ldw);
+int gemm_split(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K, const Epilogue& ep,
+               cudaStream_t st);
 
 // y = act(A W^T + b) dispatch: bf16 operands use tcgen05 when allowed, everything else SIMT.
 int gemm(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw, int M, int N, int K,

@@ -53,6 +53,9 @@ int g_shared_plan = getenv("CFB_PLAN") ? atoi(getenv("CFB_PLAN")) : 1;   // cfb_
 // operator path spreads the same rows over 4 n-tiles x 2 co-resident CTAs.
 int g_rowblock = getenv("CFB_ROWBLOCK") ? atoi(getenv("CFB_ROWBLOCK")) : 0;
 int g_rb_trace_kind = -1, g_rb_trace_layer = -1;   // debug: which program to trace (cfb_debug_rb_trace_arm)
+// fp32 handles: GEMMs of the denoiser as three-way bf16 splits on the tcgen05 tensor cores (gemm_split.cu) instead of
+// the CUDA-core FFMA kernel.  cfb_set_fp32_tensor_cores / env CFB_FP32_TC=1.
+int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 0;
 }
 
 using namespace cfb;
@@ -82,6 +85,11 @@ struct cfb_denoiser {
   cudaStream_t chain_st[MAX_CHAINS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {};
   int n_chains = 1;
+  // fp32-accurate tensor-core GEMMs (gemm_split.cu): per-chain scratch for split activations + cache of split weights
+  SplitCache* split_cache = nullptr;
+  DeviceBuf split_ws;
+  size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
+  bool fp32_tc = false;
   // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
   DeviceBuf rb_prog, rb_blk;
   std::vector<RbStage> rb_host;
@@ -128,6 +136,53 @@ struct SharedPlan {
   int g_round[TC_MAX_GROUPS], n_rounds = 0;
 };
 
+// ---- fp32 on the tensor cores ---------------------------------------------------------------------------------------
+// Scratch layout of h->split_ws: [main A arena | side A arena | 2 x MAX_CHAINS W slots | 2 x (A, W) slots of the
+// memory-side pre-projection streams].  A arenas are indexed by ABSOLUTE query row (chains own disjoint row ranges).
+SplitCtx split_ctx(const cfb_denoiser* h, int row, int chain, bool side) {
+  SplitCtx c{};
+  if (!h->fp32_tc) return c;
+  uint8_t* base = h->split_ws.as<uint8_t>();
+  c.a_ws = base + (side ? h->split_a_bytes : 0) + (size_t)row * h->split_row_bytes;
+  c.a_ws_bytes = h->split_a_bytes - (size_t)row * h->split_row_bytes;
+  c.w_ws = base + 2 * h->split_a_bytes + (size_t)(2 * chain + (side ? 1 : 0)) * h->split_w_bytes;
+  c.w_ws_bytes = h->split_w_bytes;
+  c.cache = h->split_cache;
+  return c;
+}
+SplitCtx split_ctx_pre(const cfb_denoiser* h, int which) {
+  SplitCtx c{};
+  if (!h->fp32_tc) return c;
+  uint8_t* base = h->split_ws.as<uint8_t>() + 2 * h->split_a_bytes + (size_t)2 * cfb_denoiser::MAX_CHAINS * h->split_w_bytes;
+  c.a_ws = base + (size_t)(2 * which) * h->split_w_bytes; c.a_ws_bytes = h->split_w_bytes;
+  c.w_ws = base + (size_t)(2 * which + 1) * h->split_w_bytes; c.w_ws_bytes = h->split_w_bytes;
+  c.cache = h->split_cache;
+  return c;
+}
+
+int reserve_split(cfb_denoiser* h, int n_batch, const cfb_memory* mem, bool plan) {
+  h->fp32_tc = h->prec == CFB_F32 && g_fp32_tc != 0 && g_gemm_backend != CFB_GEMM_SIMT;
+  if (!h->fp32_tc) return CFB_OK;
+  if (!h->split_cache) h->split_cache = split_cache_create();
+  const size_t R = (size_t)n_batch * h->ntok, d = h->d;
+  size_t kmax = h->ff > (int)d ? h->ff : d, rows_w = d, k_w = d;
+  int n_tot = 0, k_tot = 0, maxlen = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    n_tot += (mem->len[x] + 31) & ~31; k_tot += (mem->len[x] + 63) & ~63;
+    if (mem->len[x] > maxlen) maxlen = mem->len[x];
+  }
+  if (!plan && kmax < CFB_N_STREAMS * d) kmax = CFB_N_STREAMS * d;     // general path: fuser over all five streams
+  if ((size_t)k_tot > kmax) kmax = k_tot;
+  if ((size_t)n_tot > rows_w) rows_w = n_tot;
+  if ((size_t)((maxlen + 63) & ~63) > rows_w) rows_w = (maxlen + 63) & ~63;
+  if ((size_t)k_tot > k_w) k_w = k_tot;
+  h->split_row_bytes = 6 * kmax * 2;
+  h->split_a_bytes = R * h->split_row_bytes;
+  h->split_w_bytes = (rows_w * 6 * k_w * 2 + 255) & ~(size_t)255;
+  return h->split_ws.reserve(2 * h->split_a_bytes + (size_t)(2 * cfb_denoiser::MAX_CHAINS + 4) * h->split_w_bytes, &h->epoch);
+}
+
+
 // Embedding of the batch entries [b0, b0 + nb) of the guidance batch (entry e = branch * n_clips + clip reads the
 // latents of `clip`): every chain embeds its own rows on its own stream instead of one replicated launch up front.
 // h->xin must hold the cast latents (embed_cast).
@@ -171,18 +226,24 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
   const int d = h->d, Ld = h->L * h->d;
   constexpr int tb = sizeof(T) == 2;
   const T* mh = h->mem_hat.as<T>();
+  const SplitCtx sc_pre = split_ctx_pre(h, which);
+  const SplitCtx* scp = h->fp32_tc ? &sc_pre : nullptr;
+  (void)scp;
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     const T* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
     if (which == 0) {
       Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = tb; ez.out = h->zall.as<T>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
       if constexpr (tb) CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
-      else CFB_TRY(gemm_simt(m0, 0, d, h->w.w_zx[x], 0, d, len[x], Ld, d, 0, ez, st));
+      else { ez.split = scp; ez.w_static = 1; CFB_TRY(gemm(m0, 0, d, h->w.w_zx[x], 0, d, len[x], Ld, d, 0, ez, st)); }
     } else {
       const int rows_avail = ml.total_rows - ml.row_base[x];
       Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = tb; ey.out = h->ytall.as<T>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
       const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
       if constexpr (tb) CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
-      else CFB_TRY(gemm_simt(h->w.w_yx[x], 0, d, m0, 0, d, Ld, w_rows, d, 0, ey, st));   // columns past w_rows stay zero
+      else {   // columns past w_rows stay zero
+        ey.split = scp; ey.a_static = 1;
+        CFB_TRY(gemm(h->w.w_yx[x], 0, d, m0, 0, d, Ld, w_rows, d, 0, ey, st));
+      }
     }
   }
   if (which == 0) return shared_key_bias<T>(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
@@ -314,7 +375,7 @@ struct ChainAux {
 template <typename T>
 int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base[CFB_N_STREAMS], const int* step_ptr,
                float* eps_out_all, cudaStream_t st, const SharedPlan* sp = nullptr, int b0 = 0, int n_batch_total = 0,
-               const ChainAux* aux = nullptr, bool use_rb = false) {
+               const ChainAux* aux = nullptr, bool use_rb = false, int chain = 0) {
   if (n_batch_total <= 0) n_batch_total = n_batch;
   const ChainAux no_aux;
   if (!aux) aux = &no_aux;
@@ -332,13 +393,15 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
   // row-block kernel for the residual chains: whole 128-row blocks of a plan-driven bf16 step only
   const int rb = (sizeof(T) == 2 && use_rb && row0 % 128 == 0 && R % 128 == 0) ? h->rb_mask : 0;
+  // fp32 handles with tensor cores enabled: every GEMM below runs as a three-way bf16 split (gemm_split.cu); the
+  // contexts name this chain's scratch (main stream / side stream) and the handle's cache of split weights
+  const SplitCtx sc_main = split_ctx(h, row0, chain, false), sc_side = split_ctx(h, row0, chain, true);
+  const SplitCtx* scm = (!tb && h->fp32_tc) ? &sc_main : nullptr;
+  const SplitCtx* scs = (!tb && h->fp32_tc) ? &sc_side : nullptr;
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    ep.split = scm; ep.w_static = 1;
     return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
-  };
-  auto lin_res = [&](const void* A, int K, const void* W, const float* b) {
-    Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
-    return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
   };
   // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
   // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
@@ -346,6 +409,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
                         const float* mod) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
+    ep.split = scm; ep.w_static = 1;
     CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
     CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
     return (int)CFB_OK;
@@ -404,8 +468,10 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           for (int z = 0; z < ng; ++z) {
             Epilogue e1 = eq; e1.bias = w.b_qx + grp[z].x * d;
             e1.out = qx_abs + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d;
-            CFB_TRY(gemm_simt(a_abs + (size_t)grp[z].lo * d, 0, d, (const float*)w.w_qx + (size_t)grp[z].x * d * d, 0, d,
-                              grp[z].rows, d, d, 0, e1, sc));
+            const SplitCtx sg = split_ctx(h, grp[z].lo, chain, side);   // the group's own rows of the scratch arena
+            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1;
+            CFB_TRY(gemm(a_abs + (size_t)grp[z].lo * d, 0, d, (const float*)w.w_qx + (size_t)grp[z].x * d * d, 0, d,
+                         grp[z].rows, d, d, 0, e1, sc));
           }
         }
         ca.skip_slot0 = 1;
@@ -428,8 +494,10 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         } else {
           for (int z = 0; z < ng; ++z) {   // one stream: sequential accumulation, overlapping row blocks are fine
             Epilogue e1 = eg; e1.out = h_abs + (size_t)grp[z].lo * d;
-            CFB_TRY(gemm_simt(uc + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d, 0, CFB_N_STREAMS * d,
-                              (const float*)w.w_fu + grp[z].x * d, 0, CFB_N_STREAMS * d, grp[z].rows, d, d, 0, e1, st));
+            const SplitCtx sg = split_ctx(h, grp[z].lo, chain, false);
+            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1;
+            CFB_TRY(gemm(uc + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d, 0, CFB_N_STREAMS * d,
+                         (const float*)w.w_fu + grp[z].x * d, 0, CFB_N_STREAMS * d, grp[z].rows, d, d, 0, e1, st));
           }
         }
         return CFB_OK;
@@ -438,7 +506,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
-      es.ldo = sp->n_tot; es.replicate = 1;
+      es.ldo = sp->n_tot; es.replicate = 1; es.split = scm;     // keys Z change every step: split into this chain's W slot
       CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
@@ -453,6 +521,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         rb2_done = true;
       } else {
         Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
+        ey.split = scm;
         CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
         CFB_TRY(cond_fuser());
         CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
@@ -477,6 +546,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
+  ep.split = scm; ep.w_static = 1;
   return gemm(a, tb, d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
 }
 
@@ -593,7 +663,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
         aux.st2 = h->chain_st2[c]; aux.ev_a = h->ev_a[c]; aux.ev_b = h->ev_b[c];
       }
       CFB_TRY(embed_rows<T>(h, b0, nb, n_clips, cs));
-      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux, true));
+      CFB_TRY(run_layers<T>(h, nb, ca, att_base, step_ptr, h->eps.as<float>(), cs, &sp, b0, n_batch, &aux, true, c));
       if (c > 0) {
         CFB_CUDA(cudaEventRecord(h->ev_join[c], cs));
         CFB_CUDA(cudaStreamWaitEvent(st, h->ev_join[c], 0));
@@ -721,13 +791,19 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->ev_sched) cudaEventDestroy(h->ev_sched);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws};
   for (DeviceBuf* b : bufs) b->release();
+  split_cache_destroy(h->split_cache);
   delete h;
 }
 
 int cfb_set_rowblock(int mask) {
   g_rowblock = mask & 7;
+  return CFB_OK;
+}
+
+int cfb_set_fp32_tensor_cores(int enabled) {
+  g_fp32_tc = enabled != 0;
   return CFB_OK;
 }
 
@@ -760,6 +836,7 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
     ca.att_step_stride[x] = 0;
   }
   ca.att_first_batch = 0; ca.step_ptr = nullptr;
+  CFB_TRY(reserve_split(h, n_batch, mem, false));
   if (h->prec == CFB_BF16) {
     CFB_TRY(mem_hat<bf16>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<bf16>(), ml.total_rows, h->d, st));
     CFB_TRY(embed<bf16>(h, sample, n_batch, 1, st));
@@ -829,6 +906,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   SharedPlan sp;
   CFB_TRY(make_shared_plan(h, mem, n_batch, &sp, st));
   CFB_TRY(build_rowblock_programs(h, n_batch, n_clips, sp, want_att, st));
+  CFB_TRY(reserve_split(h, n_batch, mem, sp.on));
   {
     const char* e = getenv("CFB_CHAINS");
     int want = h->chains_override > 0 ? h->chains_override : e ? atoi(e) : 6;
@@ -869,15 +947,22 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   }
   ca.att_first_batch = (n_branch - 1) * n_clips;
   ca.step_ptr = h->step.as<int>();
-  CFB_CUDA(cudaMemcpyAsync(h->x.p, latents, (size_t)n_clips * n_per_clip * 4, cudaMemcpyDeviceToDevice, st));
   const int n_inpaint = preseq ? preseq_len * h->lat : 0;
   if (preseq) {
     CFB_TRY(h->preseq.reserve((size_t)n_clips * n_inpaint * 4, &h->epoch));
     CFB_TRY(h->inp_noise.reserve((size_t)n_clips * n_inpaint * 4, &h->epoch));
-    CFB_CUDA(cudaMemcpyAsync(h->preseq.p, preseq, (size_t)n_clips * n_inpaint * 4, cudaMemcpyDeviceToDevice, st));
-    CFB_TRY(inpaint_first(h->x.as<float>(), h->preseq.as<float>(), h->inp_noise.as<float>(), h->coef.as<float>(),
-                          n_clips, n_per_clip, n_inpaint, st));
   }
+  auto init_state = [&]() -> int {   // step counter, latents (+ the first inpainting) as the first step expects them
+    CFB_CUDA(cudaMemsetAsync(h->step.p, 0, 4, st));
+    CFB_CUDA(cudaMemcpyAsync(h->x.p, latents, (size_t)n_clips * n_per_clip * 4, cudaMemcpyDeviceToDevice, st));
+    if (preseq) {
+      CFB_CUDA(cudaMemcpyAsync(h->preseq.p, preseq, (size_t)n_clips * n_inpaint * 4, cudaMemcpyDeviceToDevice, st));
+      CFB_TRY(inpaint_first(h->x.as<float>(), h->preseq.as<float>(), h->inp_noise.as<float>(), h->coef.as<float>(),
+                            n_clips, n_per_clip, n_inpaint, st));
+    }
+    return CFB_OK;
+  };
+  CFB_TRY(init_state());
   StepArgs sa{};
   sa.eps = h->eps.as<float>(); sa.x = h->x.as<float>(); sa.noise = step_noise; sa.coef = h->coef.as<float>();
   sa.step_ptr = h->step.as<int>(); sa.step_inc = h->step.as<int>(); sa.record = record;
@@ -890,6 +975,22 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
                                : step_body<float>(h, n_clips, n_branch, ml, ca, want_att ? att_out : nullptr, sa, sp, st);
   };
 
+  // fp32 on the tensor cores: the three-way splits of the weights are computed on first use and cached, which must not
+  // happen inside a stream capture (the split would be replayed with every step) nor race between chain streams.  One
+  // eager, single-stream evaluation of the step fills the cache before every (re)capture; the state it advanced is then
+  // set up again.  Eager runs keep to one chain for the same reason.
+  auto warm_splits = [&]() -> int {
+    const int keep = h->n_chains;
+    h->n_chains = 1;
+    const int rc = body();
+    h->n_chains = keep;
+    CFB_TRY(rc);
+    CFB_TRY(init_state());
+    CFB_CUDA(cudaStreamSynchronize(st));
+    return CFB_OK;
+  };
+  if (h->fp32_tc && !use_graph) h->n_chains = 1;
+
   if (use_graph) {
     cfb_denoiser::GraphKey key;
     memset(&key, 0, sizeof(key));
@@ -900,13 +1001,14 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (int)h->fp32_tc; key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }
     if (!h->graph_valid || memcmp(&key, &h->graph_key, sizeof(key)) != 0) {
       if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
       h->graph_valid = false;
+      if (h->fp32_tc) CFB_TRY(warm_splits());
       cudaGraph_t graph = nullptr;
       CFB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       t_capturing = true;   // captured, not launched

@@ -132,7 +132,10 @@ def current_chains() -> Optional[int]:
 
 
 class _CudaModule(nn.Module):
-    """Shared handle management: weights are (re)packed lazily whenever parameters may have changed."""
+    """Shared handle management: weights are (re)packed lazily whenever parameters may have changed -- `.to()` /
+    `load_state_dict` / `set_precision` invalidate eagerly, and every call compares a key built from each parameter's
+    storage pointer and in-place version counter (`p.data.copy_`, `optimizer.step`, `torch.nn.init`, EMA swaps), so
+    stale folded weights / captured graphs are never used silently."""
 
     def __init__(self):
         super().__init__()
@@ -156,14 +159,23 @@ class _CudaModule(nn.Module):
         self._handle, self._packed, self._pack_key = None, None, None
         self._lanes = {}
 
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _ensure(self):
         """Handle of the calling thread's lane (packs the weights / creates the handle on first use)."""
         k = current_lane()
+        if self._handle is not None and self._pack_key != self._param_key():
+            if k != 0:
+                raise _lib.CfbError("parameters were modified in place while lanes are in flight; call pack() from "
+                                    "the main thread before SamplerPool.map")
+            self._invalidate()                       # parameters were edited in place since pack()
         if k == 0 and self._handle is not None:
             return self._handle
         with _lane_lock:
             if self._handle is None:
                 self.pack()
+                self._pack_key = self._param_key()
             if k == 0:
                 return self._handle
             if k not in self._lanes:
@@ -276,6 +288,7 @@ class Denoiser(_CudaModule):
             torch.cuda.current_stream(dev).synchronize()
             h = self._create(packed)
         self._handle, self._packed = h, packed
+        self._pack_key = self._param_key()
         return self
 
     # ---- memory description
@@ -478,6 +491,7 @@ class ConvoFusionVae(_CudaModule):
             torch.cuda.current_stream(dev).synchronize()
             h = self._create(packed)
         self._handle, self._packed = h, packed
+        self._pack_key = self._param_key()
         return self
 
     def decode(self, z: Tensor, lengths: List[int]) -> Tensor:

@@ -91,6 +91,9 @@ class ConvoFusionSampler(nn.Module):
         two host syncs per step; kept for drop-in parity with callers that pass a pre-expanded 7*B batch."""
         if len(focus_indices) > 0:
             raise NotImplementedError("word-excitation guidance needs autograd through the denoiser (SURVEY 8f rank 2)")
+        if not self.do_classifier_free_guidance:
+            # convofusion.py:398-401,527: guidance_scale <= 1 runs ONE conditional branch and no combine
+            raise NotImplementedError("guidance_scale <= 1 (no classifier-free guidance) is not on the B200 hot path")
         dev = encoder_hidden_states[0].device
         mult = self.clf_guidance_drops + 1
         bsz = encoder_hidden_states[0].shape[0] // mult

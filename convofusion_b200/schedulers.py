@@ -18,6 +18,8 @@ import ctypes as C
 from types import SimpleNamespace
 from typing import Optional
 
+import hashlib
+
 import numpy as np
 import torch
 
@@ -77,7 +79,11 @@ class _Base:
         ops), so the table is memoised per (steps, eta, noise schedule): repeated sampling calls pay it once."""
         self.set_timesteps(num_steps)
         ns = noise_scheduler if noise_scheduler is not None else self
-        key = (int(num_steps), float(eta), ns.kind, repr(sorted(vars(ns.config).items())))
+        # the noise schedule itself is part of the key: `trained_betas` is not in `config`, two schedulers with the same
+        # config can carry different alphas_cumprod
+        acp = ns.alphas_cumprod.detach().to("cpu", torch.float64).contiguous().numpy()
+        key = (int(num_steps), float(eta), ns.kind, repr(sorted(vars(ns.config).items())),
+               hashlib.sha1(acp.tobytes()).hexdigest())
         cache = self.__dict__.setdefault("_step_tables", {})
         if key in cache:
             return cache[key]

@@ -59,6 +59,11 @@ int cfb_set_shared_plan(int enabled);
  * the reference's batch sizes); 7 = all.  Same arithmetic up to summation order and the LayerNorm
  * statistics formula. */
 int cfb_set_rowblock(int mask);
+/* fp32 handles (precision = CFB_F32): 1 = the denoiser's GEMMs run on the tcgen05 tensor cores as three-way bf16 splits
+ * of both fp32 operands (hi + mid + lo, six partial products, fp32 accumulation in tensor memory: fp32-level error at
+ * 6x the MMA work of the bf16 mode, csrc/gemm_split.cu) instead of the CUDA-core FFMA GEMM; 0 (default, also env
+ * CFB_FP32_TC) = CUDA cores.  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
+int cfb_set_fp32_tensor_cores(int enabled);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);
 
