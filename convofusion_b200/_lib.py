@@ -90,6 +90,8 @@ PROTOTYPES = {
     "cfb_denoiser_destroy": (None, [_P]),
     "cfb_denoiser_set_chains": (C.c_int, [_P, C.c_int]),
     "cfb_denoiser_forward": (C.c_int, [_P, _P, _I, _LL, C.POINTER(Memory), _P, C.POINTER(_P), _P]),
+    "cfb_denoiser_weg_forward": (C.c_int, [_P, _P, _I, _LL, C.POINTER(Memory), _I, _P, _P]),
+    "cfb_denoiser_weg_backward": (C.c_int, [_P, _P, _P, _P]),
     "cfb_sample": (C.c_int, [_P, C.POINTER(Schedule), C.POINTER(Memory), _I, _I, _I, _P, _P, _P, _I, _P, C.POINTER(_P),
                              _I, _P]),
     "cfb_guidance_sched_step": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),

@@ -54,8 +54,9 @@ int g_shared_plan = getenv("CFB_PLAN") ? atoi(getenv("CFB_PLAN")) : 1;   // cfb_
 int g_rowblock = getenv("CFB_ROWBLOCK") ? atoi(getenv("CFB_ROWBLOCK")) : 0;
 int g_rb_trace_kind = -1, g_rb_trace_layer = -1;   // debug: which program to trace (cfb_debug_rb_trace_arm)
 // fp32 handles: GEMMs of the denoiser as three-way bf16 splits on the tcgen05 tensor cores (gemm_split.cu) instead of
-// the CUDA-core FFMA kernel.  cfb_set_fp32_tensor_cores / env CFB_FP32_TC=1.
-int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 0;
+// the CUDA-core FFMA kernel (default on: 1e-4 parity holds on both, the split is 2.4x faster at batch 16).
+// cfb_set_fp32_tensor_cores / env CFB_FP32_TC=0 selects the CUDA cores.
+int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
 }
 
 using namespace cfb;
@@ -106,6 +107,9 @@ struct cfb_denoiser {
   // memory-side pre-projection (keys / values) while the chains are still in their self-attention blocks
   cudaStream_t chain_st2[MAX_CHAINS] = {}, pre_st[2] = {};
   cudaEvent_t ev_a[MAX_CHAINS] = {}, ev_b[MAX_CHAINS] = {}, ev_mh = nullptr, ev_pre[2] = {};
+  // word-excitation guidance: activations saved by cfb_denoiser_weg_forward for cfb_denoiser_weg_backward
+  DeviceBuf wg_h, wg_qkv, wg_z, wg_p, wg_g, wg_t1, wg_t2;
+  struct WegState { bool valid = false; int n_batch = 0, att_stream = 0; cfb::CrossArgs ca; long long p_off[CFB_N_STREAMS]; } weg;
 };
 
 namespace {
@@ -791,7 +795,8 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   if (h->ev_sched) cudaEventDestroy(h->ev_sched);
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
-                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws};
+                       &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws,
+                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2};
   for (DeviceBuf* b : bufs) b->release();
   split_cache_destroy(h->split_cache);
   delete h;
@@ -845,6 +850,141 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
   CFB_TRY(mem_hat<float>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<float>(), ml.total_rows, h->d, st));
   CFB_TRY(embed<float>(h, sample, n_batch, 1, st));
   return run_layers<float>(h, n_batch, ca, att_out, nullptr, eps_out, st);
+}
+
+
+// ---- word-excitation guidance (convofusion.py:437-496, 298-388) ---------------------------------------------------
+// The reference differentiates a loss on the listener-text attention maps of the text-only branch with respect to the
+// latents (torch.autograd through Denoiser.forward).  Here: one fp32 evaluation that keeps what the backward needs
+// (the five LayerNorm inputs of every layer, qkv, the pre-GELU activations, all cross-attention probabilities), then
+// the reverse walk with the input-gradient kernels of weg.cu.  fp32 handles only; batch = the text-only branch.
+int cfb_denoiser_weg_forward(cfb_denoiser* h, const float* sample, int n_batch, int64_t timestep, const cfb_memory* mem,
+                             int att_stream, float* att_out, cfb_stream stream) {
+  CFB_CHECK(h && sample && mem && att_out && n_batch > 0, "cfb_denoiser_weg_forward: bad argument");
+  CFB_CHECK(h->prec == CFB_F32, "cfb_denoiser_weg_forward: word-excitation guidance runs on an fp32 handle");
+  CFB_CHECK(att_stream >= 0 && att_stream < CFB_N_STREAMS, "cfb_denoiser_weg_forward: bad stream %d", att_stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  h->weg.valid = false;
+  const int d = h->d, L = h->L, R = n_batch * h->ntok, ff = h->ff;
+  CFB_TRY(reserve_rows(h, n_batch, n_batch));
+  h->sched_epoch = ~0u;
+  CFB_TRY(h->tsteps.reserve(4, &h->epoch));
+  const float tf = (float)timestep;
+  CFB_CUDA(cudaMemcpyAsync(h->tsteps.p, &tf, 4, cudaMemcpyHostToDevice, st));
+  CFB_TRY(prep_time(h, 1, st));
+  MemLayout ml; CrossArgs ca;
+  CFB_TRY(prep_memory(h, mem, n_batch, &ml, &ca, st));
+  long long p_total = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    h->weg.p_off[x] = p_total;
+    p_total += (long long)n_batch * L * h->ntok * mem->len[x];
+    ca.att_batch_stride[x] = (long long)L * h->ntok * mem->len[x];
+    ca.att_step_stride[x] = 0;
+  }
+  ca.att_first_batch = 0; ca.step_ptr = nullptr; ca.skip_slot0 = 0; ca.bs_offset = 0;
+  const size_t Rd = (size_t)R * d;
+  int wide = CFB_N_STREAMS * d;
+  if (ff > wide) wide = ff;
+  CFB_TRY(h->wg_h.reserve((size_t)L * 5 * Rd * 4, nullptr));
+  CFB_TRY(h->wg_qkv.reserve((size_t)L * Rd * 3 * 4, nullptr));
+  CFB_TRY(h->wg_z.reserve((size_t)L * R * ff * 4, nullptr));
+  CFB_TRY(h->wg_p.reserve((size_t)p_total * 4, nullptr));
+  CFB_TRY(h->wg_g.reserve(Rd * 4, nullptr));
+  CFB_TRY(h->wg_t1.reserve((size_t)R * wide * 4, nullptr));
+  CFB_TRY(h->wg_t2.reserve((size_t)R * wide * 4, nullptr));
+  CFB_TRY(mem_hat<float>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<float>(), ml.total_rows, d, st));
+  CFB_TRY(embed<float>(h, sample, n_batch, 1, st));
+  float* hres = h->h.as<float>();
+  float* a = h->a.as<float>();
+  float* qx = h->qx.as<float>();
+  float* f = h->f.as<float>();
+  auto snap = [&](int l, int k) {
+    return cudaMemcpyAsync(h->wg_h.as<float>() + ((size_t)l * 5 + k) * Rd, hres, Rd * 4, cudaMemcpyDeviceToDevice, st);
+  };
+  auto lin = [&](const float* A, int K, const void* W, const float* b, float* out, int N, int act, int accumulate) {
+    Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.accumulate = accumulate; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    return gemm(A, 0, K, W, 0, K, R, N, K, 0, ep, st);
+  };
+  for (int l = 0; l < L; ++l) {
+    const cfb_denoiser_layer& w = h->layers[l];
+    const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
+    const float* mod2 = mod1 + 2 * d;
+    float* qkv = h->wg_qkv.as<float>() + (size_t)l * Rd * 3;
+    float* z = h->wg_z.as<float>() + (size_t)l * R * ff;
+    CFB_CUDA(snap(l, 0));
+    CFB_TRY(ln_rows<float>(hres, w.ln1_g, w.ln1_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin(a, d, w.w_in, w.b_in, qkv, 3 * d, 0, 0));
+    CFB_TRY(mha<float>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
+    CFB_TRY(lin(a, d, w.w_so, w.b_so, hres, d, 0, 1));
+    CFB_CUDA(snap(l, 1));
+    CFB_TRY(ln_rows<float>(hres, w.tb1_g, w.tb1_b, mod1, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin(a, d, w.w_tb1, w.b_tb1, hres, d, 0, 1));
+    CFB_CUDA(snap(l, 2));
+    CFB_TRY(ln_rows<float>(hres, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0, 0));
+    for (int x = 0; x < CFB_N_STREAMS; ++x)
+      ca.att[x] = h->wg_p.as<float>() + h->weg.p_off[x] + (size_t)l * h->ntok * ca.len[x];
+    CFB_TRY(cross_attention<float>(qx, h->mem_hat.as<float>(), qx, ca, n_batch, h->ntok, d, st));
+    CFB_TRY(lin(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, hres, d, 0, 1));
+    CFB_CUDA(snap(l, 3));
+    CFB_TRY(ln_rows<float>(hres, w.tb2_g, w.tb2_b, mod2, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin(a, d, w.w_tb2, w.b_tb2, hres, d, 0, 1));
+    CFB_CUDA(snap(l, 4));
+    CFB_TRY(ln_rows<float>(hres, w.ln3_g, w.ln3_b, nullptr, nullptr, 0, a, R, d, st));
+    CFB_TRY(lin(a, d, w.w_ff1, w.b_ff1, z, ff, 0, 0));                 // pre-activation, kept for the backward
+    CFB_TRY(lin(a, d, w.w_ff1, w.b_ff1, f, ff, CFB_ACT_GELU, 0));
+    CFB_TRY(lin(f, ff, w.w_ff2, w.b_ff2, hres, d, 0, 1));
+  }
+  const long long n_att = (long long)n_batch * L * h->ntok * mem->len[att_stream];
+  CFB_CUDA(cudaMemcpyAsync(att_out, h->wg_p.as<float>() + h->weg.p_off[att_stream], (size_t)n_att * 4, cudaMemcpyDeviceToDevice, st));
+  h->weg.valid = true; h->weg.n_batch = n_batch; h->weg.att_stream = att_stream; h->weg.ca = ca;
+  return CFB_OK;
+}
+
+int cfb_denoiser_weg_backward(cfb_denoiser* h, const float* d_att, float* grad_sample, cfb_stream stream) {
+  CFB_CHECK(h && d_att && grad_sample, "cfb_denoiser_weg_backward: bad argument");
+  CFB_CHECK(h->weg.valid, "cfb_denoiser_weg_backward: no saved forward (call cfb_denoiser_weg_forward on this handle first)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_batch = h->weg.n_batch, d = h->d, L = h->L, R = n_batch * h->ntok, ff = h->ff, sx = h->weg.att_stream;
+  const size_t Rd = (size_t)R * d;
+  CrossArgs ca = h->weg.ca;
+  float* g = h->wg_g.as<float>();
+  float* t1 = h->wg_t1.as<float>();
+  float* t2 = h->wg_t2.as<float>();
+  CFB_CUDA(cudaMemsetAsync(g, 0, Rd * 4, st));
+  auto hs = [&](int l, int k) { return h->wg_h.as<float>() + ((size_t)l * 5 + k) * Rd; };
+  for (int l = L - 1; l >= 0; --l) {
+    const cfb_denoiser_layer& w = h->layers[l];
+    const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
+    const float* mod2 = mod1 + 2 * d;
+    const float* qkv = h->wg_qkv.as<float>() + (size_t)l * Rd * 3;
+    const float* z = h->wg_z.as<float>() + (size_t)l * R * ff;
+    // feed-forward (cross_attention.py:659-661): h5 = h4 + linear2(GELU(linear1(norm3(h4))))
+    CFB_TRY(linear_bwd(g, d, (const float*)w.w_ff2, ff, t1, ff, R, d, ff, 0, st));
+    CFB_TRY(gelu_bwd(z, t1, (long long)R * ff, st));
+    CFB_TRY(linear_bwd(t1, ff, (const float*)w.w_ff1, d, t2, d, R, ff, d, 0, st));
+    CFB_TRY(ln_bwd(hs(l, 4), w.ln3_g, w.ln3_b, nullptr, t2, g, R, d, st));
+    // time_block2 (:655)
+    CFB_TRY(linear_bwd(g, d, (const float*)w.w_tb2, d, t1, d, R, d, d, 0, st));
+    CFB_TRY(ln_bwd(hs(l, 3), w.tb2_g, w.tb2_b, mod2, t1, g, R, d, st));
+    // five folded cross-attentions + att_fuser (:578-652); the loss enters through the maps of stream `sx`
+    CFB_TRY(linear_bwd(g, d, (const float*)w.w_fu, CFB_N_STREAMS * d, t1, CFB_N_STREAMS * d, R, d, CFB_N_STREAMS * d, 0, st));
+    for (int x = 0; x < CFB_N_STREAMS; ++x)
+      ca.att[x] = h->wg_p.as<float>() + h->weg.p_off[x] + (size_t)l * h->ntok * ca.len[x];
+    CFB_TRY(cross_bwd(t1, h->mem_hat.as<float>(), t2, ca, d_att + (size_t)l * h->ntok * ca.len[sx], sx, n_batch, h->ntok, st));
+    CFB_TRY(linear_bwd(t2, CFB_N_STREAMS * d, (const float*)w.w_qx, d, t1, d, R, CFB_N_STREAMS * d, d, 0, st));
+    CFB_TRY(ln_bwd(hs(l, 2), w.ln2_g, w.ln2_b, nullptr, t1, g, R, d, st));
+    // time_block1 (:575)
+    CFB_TRY(linear_bwd(g, d, (const float*)w.w_tb1, d, t1, d, R, d, d, 0, st));
+    CFB_TRY(ln_bwd(hs(l, 1), w.tb1_g, w.tb1_b, mod1, t1, g, R, d, st));
+    // self-attention (:568-572)
+    CFB_TRY(linear_bwd(g, d, (const float*)w.w_so, d, t1, d, R, d, d, 0, st));
+    CFB_TRY(mha_bwd(qkv, t1, t2, n_batch, h->ntok, h->H, d, st));
+    CFB_TRY(linear_bwd(t2, 3 * d, (const float*)w.w_in, d, t1, d, R, 3 * d, d, 0, st));
+    CFB_TRY(ln_bwd(hs(l, 0), w.ln1_g, w.ln1_b, nullptr, t1, g, R, d, st));
+  }
+  // latent_embd (denoiser.py:187): h = x W^T + per-token bias
+  return linear_bwd(g, d, (const float*)h->w.w_embed, h->lat, grad_sample, h->lat, R, d, h->lat, 0, st);
 }
 
 int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem, int n_clips, int n_branch,

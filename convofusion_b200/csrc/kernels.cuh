@@ -65,6 +65,16 @@ template <typename T>
 int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,
                     cudaStream_t st);
 
+// ---- weg.cu: input-gradient kernels of the denoiser's query side (word-excitation guidance)
+int linear_bwd(const float* dY, int ldy, const float* W, int ldw, float* dX, int ldx, int M, int N, int K, int accumulate,
+               cudaStream_t st);
+int ln_bwd(const float* x, const float* gamma, const float* beta, const float* mod, const float* dy, float* g, int rows, int d,
+           cudaStream_t st);
+int gelu_bwd(const float* z, float* df, long long n, cudaStream_t st);
+int mha_bwd(const float* qkv, const float* dO, float* dqkv, int n_batch, int L, int n_heads, int d, cudaStream_t st);
+int cross_bwd(const float* dcat, const float* mem_hat, float* dqx, const CrossArgs& a, const float* d_att, int att_stream,
+              int n_batch, int n_tokens, cudaStream_t st);
+
 // ---- sched.cu
 struct StepArgs {
   const float* eps;        // [n_branch, B, n]

@@ -350,6 +350,46 @@ class Denoiser(_CudaModule):
                                                        att_ptrs, _lib.stream_ptr()))
         return (eps, att)
 
+    # ---- word-excitation guidance: attention maps of one stream and the gradient of a loss on them w.r.t. the latents
+    def weg_forward(self, sample: Tensor, timestep, encoder_hidden_states, mem_mask_dict: Optional[dict] = None,
+                    stream: int = 2) -> Tensor:
+        """Denoiser.forward on the text-only branch as the reference's WEG calls it (convofusion.py:455-461), keeping
+        the activations on the device; returns the attention maps of `stream` (2 = listener text, what the loss reads:
+        :466) as [B, layers, 16, M].  fp32 handles only.  Follow with `weg_backward`."""
+        if self.precision != "fp32":
+            raise _lib.CfbError("word-excitation guidance differentiates the denoiser in fp32: use a precision='fp32' Denoiser")
+        dev = self._device()
+        h = self._ensure()
+        bg, ntok, lat = sample.shape
+        if ntok != self.n_tokens or lat != self.latent_dim:
+            raise ValueError(f"sample must be [B,{self.n_tokens},{self.latent_dim}], got {tuple(sample.shape)}")
+        keep: list = []
+        x = sample.detach().to(device=dev, dtype=torch.float32).contiguous()
+        mem = self._memory(encoder_hidden_states, mem_mask_dict or {}, None, keep)
+        for i in range(5):
+            if mem.n_slots[i] != bg:
+                raise ValueError(f"encoder_hidden_states[{i}] has batch {mem.n_slots[i]}, sample has {bg}")
+        att = torch.empty(bg, self.num_layers, ntok, mem.len[stream], device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cfb_denoiser_weg_forward(h, x.data_ptr(), bg, int(timestep), C.byref(mem), int(stream),
+                                                           att.data_ptr(), _lib.stream_ptr()))
+        self._weg_shape = (tuple(att.shape), (bg, ntok, lat))
+        return att
+
+    def weg_backward(self, d_att: Tensor) -> Tensor:
+        """dLoss/dsample [B,16,latent] for dLoss/dAtt of the last `weg_forward` (torch.autograd.grad(loss, latents) of
+        tools/word_excitation_guidance.py:60, through hand-written input-gradient kernels, csrc/weg.cu)."""
+        att_shape, x_shape = getattr(self, "_weg_shape", (None, None))
+        if att_shape is None or tuple(d_att.shape) != att_shape:
+            raise ValueError(f"d_att must have the shape of the last weg_forward's maps {att_shape}")
+        dev = self._device()
+        h = self._ensure()
+        g = d_att.detach().to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty(x_shape, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cfb_denoiser_weg_backward(h, g.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
+        return out
+
     def sample(self, scheduler, enc: Sequence[Tensor], masks: Dict[str, Optional[Tensor]],
                slots: Sequence[Optional[Tensor]], latents: Tensor, num_steps: int, guidance_scale: float = 7.5,
                eta: float = 0.0, n_branch: int = 7, full_last: Optional[bool] = None,

@@ -1,6 +1,7 @@
 """Sampling orchestration: the reference's test_diffusion_forward / _diffusion_reverse /
 diffusion_reverse_forecast / process_samples call chain (convofusion.py:817-1065, 391-549;
-unbounded_synthesis.py:28-187, 244-512) for synthetic, already-featurised inputs, with WEG off.
+unbounded_synthesis.py:28-187, 244-512) for synthetic, already-featurised inputs; word-excitation guidance (focus
+tokens) runs on the as-written per-step loop with the gradient from the CUDA library (weg.py).
 
 `ConvoFusionSampler` holds the same sub-module names as the reference LightningModule (`denoiser`, `vae`,
 `text_audio_encoder`, `condition_fuser`), so `load_state_dict(ckpt["state_dict"])` accepts a reference
@@ -18,6 +19,7 @@ from .conditioning import (TextAudioController, TextAudioMotionFuser, expand_gui
                            guidance_memory, guidance_slots, guidance_slots_host)
 from .modules import ConvoFusionVae, Denoiser
 from .schedulers import DDIMScheduler, DDPMScheduler
+from .weg import DEFAULT_WEG_PARAMETERS, weg_pre_step
 
 MOTION_FPS = 25.0        # configs/config_cf_beatdnd.yaml:78-87
 WINDOW_FRAMES = 128
@@ -69,6 +71,7 @@ class ConvoFusionSampler(nn.Module):
         self.guidance_scale = guidance_scale
         self.num_inference_timesteps = num_inference_timesteps
         self.eta = eta
+        self.weg_parameters = {k: (dict(v) if isinstance(v, dict) else v) for k, v in DEFAULT_WEG_PARAMETERS.items()}   # :64
         self.clf_guidance_drops = 6                              # convofusion.py:60
         self.do_classifier_free_guidance = guidance_scale > 1.0   # convofusion.py:131
         self.latent_dim = [1, self.denoiser.latent_dim]
@@ -84,13 +87,27 @@ class ConvoFusionSampler(nn.Module):
         return guidance_memory(self.text_audio_encoder, self.condition_fuser, clip, uncond_text, uncond_text_attn)
 
     # ------------------------------------------------------------------ reverse loops
+    def _weg_denoiser(self) -> Denoiser:
+        """fp32 evaluation of the denoiser for the WEG gradient: the module itself, or (bf16 samplers) a twin over the
+        SAME parameter tensors with its own fp32 handle, packed on first use and re-packed when the parameters change."""
+        if self.denoiser.precision == "fp32":
+            return self.denoiser
+        twin = self.__dict__.get("_weg_twin")
+        if twin is None:
+            import copy
+            twin = copy.copy(self.denoiser)            # shares _parameters / _modules, owns no device handle yet
+            twin.precision = "fp32"
+            object.__setattr__(self, "_weg_twin", twin)   # not a registered sub-module: state_dict stays the reference's
+        return twin
+
     def _diffusion_reverse(self, encoder_hidden_states, lengths=None, cond_masks=dict(), focus_indices=[],
-                           init_latents: Optional[Tensor] = None, step_noise: Optional[Tensor] = None):
+                           init_latents: Optional[Tensor] = None, step_noise: Optional[Tensor] = None,
+                           weg_log: Optional[list] = None):
         """The reference's as-written loop (convofusion.py:391-549): one Denoiser.forward on the 7*B batch and one
         scheduler.step per timestep, attention maps kept per step.  Same arithmetic as `sample()`, ~140 launches and
-        two host syncs per step; kept for drop-in parity with callers that pass a pre-expanded 7*B batch."""
-        if len(focus_indices) > 0:
-            raise NotImplementedError("word-excitation guidance needs autograd through the denoiser (SURVEY 8f rank 2)")
+        two host syncs per step; kept for drop-in parity with callers that pass a pre-expanded 7*B batch, and the path
+        word-excitation guidance runs on: with `focus_indices` every step is preceded by the latent update of
+        convofusion.py:437-496 (weg.weg_pre_step, `self.weg_parameters`)."""
         if not self.do_classifier_free_guidance:
             # convofusion.py:398-401,527: guidance_scale <= 1 runs ONE conditional branch and no combine
             raise NotImplementedError("guidance_scale <= 1 (no classifier-free guidance) is not on the B200 hot path")
@@ -106,7 +123,14 @@ class ConvoFusionSampler(nn.Module):
         if "eta" in set(inspect.signature(self.scheduler.step).parameters.keys()):
             extra["eta"] = self.eta
         attention_matrices = dict()
+        use_weg = len(focus_indices) > 0
+        if use_weg:
+            weg_den, scale_range = self._weg_denoiser(), self.weg_parameters["scale_range"]
         for i, t in enumerate(timesteps):
+            if use_weg:
+                latents, scale_range = weg_pre_step(weg_den, latents, i, t, encoder_hidden_states, cond_masks,
+                                                    focus_indices, self.weg_parameters, scale_range, len(timesteps),
+                                                    mult, weg_log)
             x = torch.cat([latents] * mult)
             noise_pred, att_mats = self.denoiser(sample=x, timestep=t, encoder_hidden_states=encoder_hidden_states,
                                                  lengths=None, mem_mask_dict=cond_masks)
@@ -182,6 +206,13 @@ class ConvoFusionSampler(nn.Module):
     def generate(self, clip: Dict[str, Tensor], uncond_text: Tensor, uncond_text_attn: Tensor, lengths: List[int],
                  init_latents: Tensor, **kw):
         """test_diffusion_forward (convofusion.py:817-1036) for one batch of featurised clips."""
+        focus_indices = kw.pop("focus_indices", [])
+        if len(focus_indices) > 0 and len(focus_indices[0]) > 0:      # convofusion.py:942-1023: WEG on the as-written loop
+            enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
+            enc7, masks7 = expand_guidance_batch(enc, masks, init_latents.shape[0])
+            z, att = self._diffusion_reverse(enc7, lengths, masks7, focus_indices=focus_indices, init_latents=init_latents,
+                                             weg_log=kw.pop("weg_log", None))
+            return {"m_rst": self.decode(z, lengths), "lat_t": z, "record": None, "test_attention_maps": att}
         kw.setdefault("spk_is_uncond", self.speaker_is_unconditional(clip, uncond_text, uncond_text_attn))
         enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
         z, rec, att = self.sample(enc, masks, init_latents.shape[0], init_latents, **kw)

@@ -61,8 +61,8 @@ int cfb_set_shared_plan(int enabled);
 int cfb_set_rowblock(int mask);
 /* fp32 handles (precision = CFB_F32): 1 = the denoiser's GEMMs run on the tcgen05 tensor cores as three-way bf16 splits
  * of both fp32 operands (hi + mid + lo, six partial products, fp32 accumulation in tensor memory: fp32-level error at
- * 6x the MMA work of the bf16 mode, csrc/gemm_split.cu) instead of the CUDA-core FFMA GEMM; 0 (default, also env
- * CFB_FP32_TC) = CUDA cores.  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
+ * 6x the MMA work of the bf16 mode, csrc/gemm_split.cu) instead of the CUDA-core FFMA GEMM (the default; env
+ * CFB_FP32_TC); 0 = CUDA cores.  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
 int cfb_set_fp32_tensor_cores(int enabled);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);
@@ -159,6 +159,16 @@ typedef struct {
   const int64_t *timesteps;  /* host [n_steps] */
   const float   *coef;       /* host [n_steps, 8] */
 } cfb_schedule;
+
+/* Word-excitation guidance (Convofusion._diffusion_reverse with focus tokens, convofusion.py:437-496; the iterative
+ * refinement :298-388; tools/word_excitation_guidance.py:55-62 update_latent = torch.autograd.grad through
+ * Denoiser.forward).  fp32 handles.  _forward evaluates the denoiser on `sample` [n_batch, n_tokens, latent] (the
+ * text-only branch: n_batch = clips), keeps the activations and writes the attention maps of stream `att_stream`
+ * (2 = listener text) as [n_batch, n_layers, n_tokens, len] -- the tensor the reference's loss is computed from.
+ * _backward takes dLoss/dAtt in the same layout and returns dLoss/dsample [n_batch, n_tokens, latent]. */
+int cfb_denoiser_weg_forward(cfb_denoiser *h, const float *sample, int n_batch, int64_t timestep, const cfb_memory *mem,
+                             int att_stream, float *att_out, cfb_stream stream);
+int cfb_denoiser_weg_backward(cfb_denoiser *h, const float *d_att, float *grad_sample, cfb_stream stream);
 
 /* Replaces Convofusion._diffusion_reverse (modeltype/convofusion.py:391-549) and
  * diffusion_reverse_forecast (unbounded_synthesis.py:28-187) with WEG off: the whole

@@ -504,8 +504,10 @@ def guidance_combine(noise_pred: Tensor, guidance_scale: float) -> Tensor:
 
 def diffusion_reverse(denoise_fn, scheduler, enc, masks, init_latents: Tensor, num_steps: int,
                       guidance_scale: float = 7.5, eta: float = 0.0,
-                      step_noise: Optional[Tensor] = None, record: Optional[list] = None):
-    """convofusion.py:391-549 with focus_indices=[] (WEG off).
+                      step_noise: Optional[Tensor] = None, record: Optional[list] = None,
+                      focus_indices: Sequence[Sequence[int]] = (), weg: Optional[dict] = None, weg_log: Optional[list] = None):
+    """convofusion.py:391-549; focus_indices=[] is WEG off, otherwise every guided step is preceded by weg_pre_step
+    (needs autograd: call outside torch.no_grad()).
 
     init_latents replaces torch.randn at :412 so the noise is shared with the CUDA path;
     step_noise [num_steps,B,16,latent] replaces the scheduler's internal randn (DDPM / eta>0).
@@ -514,7 +516,11 @@ def diffusion_reverse(denoise_fn, scheduler, enc, masks, init_latents: Tensor, n
     latents = init_latents * scheduler.init_noise_sigma                     # :419
     scheduler.set_timesteps(num_steps)                                      # :421
     att = {}
+    scale_range = weg["scale_range"] if weg else None                        # :395
     for i, t in enumerate(scheduler.timesteps):                             # :435
+        if len(focus_indices) > 0:                                          # :437
+            latents, scale_range = weg_pre_step(denoise_fn, latents, i, t, enc, masks, focus_indices, weg, scale_range,
+                                                len(scheduler.timesteps), weg_log)
         x = torch.cat([latents] * N_BRANCH)                                 # :499
         noise_pred, att_mats = denoise_fn(x, t, enc, masks)                 # :507
         att[int(t)] = [a.chunk(N_BRANCH)[-1] for a in att_mats]             # :519-523
@@ -528,6 +534,80 @@ def diffusion_reverse(denoise_fn, scheduler, enc, masks, init_latents: Tensor, n
         if record is not None:
             record.append(latents.clone())
     return latents.permute(1, 0, 2), att                                     # :548
+
+
+# --------------------------------------------------------------------------- word-excitation guidance (WEG)
+def weg_gaussian_kernel(kernel_size: int = 3, sigma: float = 0.5) -> Tensor:
+    """operator/gaussian_smoothing.py:21-47 for dim=2, channels=1 (note the reference's exp(-((x - mean) / (2 std))^2))."""
+    kernel = 1
+    grids = torch.meshgrid([torch.arange(kernel_size, dtype=torch.float32)] * 2, indexing="ij")
+    for mgrid in grids:
+        mean = (kernel_size - 1) / 2
+        kernel = kernel * (1 / (sigma * math.sqrt(2 * math.pi)) * torch.exp(-((mgrid - mean) / (2 * sigma)) ** 2))
+    kernel = kernel / torch.sum(kernel)
+    return kernel.view(1, 1, kernel_size, kernel_size)
+
+
+def weg_max_attention(att_text: Tensor, focus_indices: Sequence[Sequence[int]], eot_indices: Tensor) -> List[List[Tensor]]:
+    """tools/word_excitation_guidance.py:11-52 as the loops call it (smooth_attentions=True, normalize_eot=True):
+    layer mean, drop BOS / EOS and beyond, softmax over the remaining tokens, 3x3 Gaussian smoothing with reflect padding,
+    max over the 16 motion tokens for every focus token.  att_text [1, layers, 16, T]."""
+    att = torch.mean(att_text, dim=1)                                       # :11-14
+    assert att.shape[0] == 1, "EOS/BOS normalization only works for test batch size 1 currently"   # :25
+    last_idx = int(eot_indices[0])                                          # :26
+    a = torch.softmax(att[:, :, 1:last_idx], dim=-1)                        # :28-30
+    a = F.conv2d(F.pad(a.unsqueeze(1), (1, 1, 1, 1), mode="reflect"), weg_gaussian_kernel().to(a)).squeeze(1)   # :33-36
+    return [[a[b, :, i - 1].max(dim=-1)[0] for i in idxs] for b, idxs in enumerate(focus_indices)]   # :39-51
+
+
+def weg_focus_loss(max_att: List[List[Tensor]]) -> Tensor:
+    """tools/word_excitation_guidance.py:65-83 (no empty samples): mean_b mean_tokens max(0, 1 - max attention)."""
+    losses = [torch.mean(torch.stack([torch.max(torch.zeros_like(t), 1.0 - t) for t in sample]), dim=-1) for sample in max_att]
+    return torch.mean(torch.stack(losses, dim=-1))
+
+
+def weg_evaluate(denoise_fn, latents: Tensor, t, enc_text, masks_text, focus_indices):
+    """One WEG evaluation (convofusion.py:451-471 / :326-343): text-only branch forward, focus loss.
+    Returns (loss, latents_with_grad)."""
+    latents = latents.clone().detach().requires_grad_(True)
+    _, att = denoise_fn(latents, t, enc_text, masks_text)
+    eot = torch.argmax(masks_text["tlsn"].int(), dim=1) - 1                 # :463
+    loss = weg_focus_loss(weg_max_attention(att[2], focus_indices, eot))    # :466-471
+    return loss, latents
+
+
+def weg_pre_step(denoise_fn, latents: Tensor, i: int, t, enc, masks, focus_indices, weg: dict, scale_range, n_steps: int,
+                 log: Optional[list] = None):
+    """convofusion.py:437-496 (== unbounded_synthesis.py:82-142): the latent update that precedes the guided step when
+    focus tokens are given.  `scale_range` is re-assigned to the linspace array on every step exactly like the
+    reference (:442-444), i.e. from the second step on its first two ELEMENTS are the end points.  Returns
+    (latents, scale_range)."""
+    scale_range = np.linspace(scale_range[0], scale_range[1], n_steps)      # :442-444
+    enc_t = [e.chunk(N_BRANCH)[1] for e in enc]                             # :449
+    masks_t = {k: (v.chunk(N_BRANCH)[1] if v is not None else v) for k, v in masks.items()}   # :450
+    loss, latents = weg_evaluate(denoise_fn, latents, t, enc_t, masks_t, focus_indices)
+    thresholds = weg["thresholds"]
+    n_refine = 0
+    if i in thresholds.keys() and loss > 1.0 - thresholds[i]:               # :474
+        # iterative_refinement_step (:298-388)
+        step_size = weg["scale_factor"] * np.sqrt(scale_range[i])
+        target = max(0, 1.0 - thresholds[i])
+        while loss > target:                                                # :326
+            n_refine += 1
+            loss, latents = weg_evaluate(denoise_fn, latents, t, enc_t, masks_t, focus_indices)
+            if loss.all() != 0:                                             # :344
+                grad = torch.autograd.grad(loss, [latents])[0]              # word_excitation_guidance.py:60
+                latents = latents - step_size * grad
+            if n_refine >= weg["max_refinement_steps"]:                     # :363
+                break
+        loss, latents = weg_evaluate(denoise_fn, latents, t, enc_t, masks_t, focus_indices)   # :368-387
+    if i < weg["max_iter_to_alter"]:                                        # :490
+        if loss.all() != 0:                                                 # :493
+            grad = torch.autograd.grad(loss, [latents])[0]
+            latents = latents - weg["scale_factor"] * np.sqrt(scale_range[i]) * grad        # :495
+    if log is not None:
+        log.append({"loss": float(loss.detach()), "n_refine": n_refine})
+    return latents.detach(), scale_range
 
 
 def diffusion_reverse_forecast(denoise_fn, scheduler, noise_scheduler, enc, masks, init_noise: Tensor,

@@ -21,7 +21,7 @@ DEV = "cuda:0"
 def fp32_tc():
     _lib.check(_lib.lib().cfb_set_fp32_tensor_cores(1))
     yield
-    _lib.check(_lib.lib().cfb_set_fp32_tensor_cores(0))
+    _lib.check(_lib.lib().cfb_set_fp32_tensor_cores(1))     # the library default
 
 
 def sampler(steps, scheduler=None):

@@ -265,3 +265,27 @@ def test_scheduler_identities_of_the_published_algorithms():
         out1 = p.step(eps.float(), t, xt.float(), variance_noise=z).prev_sample
         assert torch.allclose(out0.double(), mean, atol=5e-6), t
         assert torch.allclose((out1 - out0).double(), var.sqrt() * z.double(), atol=5e-6), t
+
+
+def test_word_excitation_guidance_matches_the_reference_loop_code():
+    """tests/golden/ref_weg.pt holds the latents of the reference's OWN `_diffusion_reverse` with focus tokens
+    (convofusion.py:437-496, iterative_refinement_step :298-388, tools/word_excitation_guidance.py; autograd through the
+    reference Denoiser; tools/pin_reference_loops.py asserts the oracle loop reproduces it bit for bit with that
+    denoiser).  Here the oracle's loop runs on the oracle's own denoiser: the gradient steps move the result by 70-80 %
+    of its norm, so agreement at 1e-3 pins the loss, the gradient and both update schedules (plain / refinement)."""
+    g = golden("ref_weg.pt")
+    syn = synthetic_clip(1, seed=g["clip_seed"], dyadic=True)
+    enc, masks = oracle_batch(syn)
+    init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(g["init_seed"]))
+    for tag, case in g["cases"].items():
+        log = []
+        z, _ = O.diffusion_reverse(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init,
+                                   g["n_steps"], guidance_scale=7.5, focus_indices=case["focus"], weg=case["params"],
+                                   weg_log=log)
+        err = rel_err(z.detach(), case["z"])
+        print(f"WEG[{tag}]: oracle (own denoiser) vs reference loop: L2 {err:.2e}; refinement iterations "
+              f"{[e['n_refine'] for e in log]}")
+        assert err < 1e-3
+        assert [e["n_refine"] for e in log] == [e["n_refine"] for e in case["log"]]
+    k = O.weg_gaussian_kernel()
+    assert abs(float(k.sum()) - 1.0) < 1e-6 and k.shape == (1, 1, 3, 3)

@@ -323,6 +323,52 @@ out["window_text_cases"] = text_cases
 out["unbounded"] = {"feats": torch.stack(saved), "texts_lsn": texts_lsn, "texts_spk": texts_spk, "n_parts": N_PARTS,
                     "batch_seed": 3400, "uncond_clip_seed": 3300}
 
+# ---- word-excitation guidance (convofusion.py:437-496 + iterative_refinement_step :298-388 + tools/
+# word_excitation_guidance.py): the reference loop with focus tokens, B = 1 (its own assertion), autograd through the
+# reference Denoiser.  Two settings: plain latent updates on every step, and a threshold at step 0 that triggers the
+# iterative refinement.  The oracle's restated loop must reproduce the reference bit for bit with the same denoiser.
+def one_clip_batch(seed):
+    syn1 = synthetic_clip(1, seed=seed, dyadic=True)
+    c1 = dict(syn1["clip"])
+    c1["text_lsn_mask"], c1["text_spk_mask"] = ~c1["text_lsn_attn"].bool(), ~c1["text_spk_attn"].bool()
+    return O.assemble_guidance_batch(sd, c1, syn1["uncond_text"], ~syn1["uncond_text_attn"].bool())
+
+
+weg_out = {"n_steps": N_STEPS, "clip_seed": 3500, "init_seed": SEED + 4, "cases": {}}
+enc1, masks1 = one_clip_batch(3500)
+eot = int(torch.argmax(masks1["tlsn"].chunk(7)[1].int(), dim=1)[0]) - 1
+focus = [[2, max(3, min(5, eot - 2))]]
+print(f"WEG: text-only branch has its EOS at token {eot}; focus tokens {focus}")
+# Random-init weights give nearly uniform text attention (loss = 1 - 1/18 at every step) and gradients of ~1e-6, so the
+# step size is scaled up until the guidance moves the latents by O(1) -- the code path does not depend on it.
+for tag, wp in (("update", {"scale_range": [1.0, 0.5], "thresholds": {}, "scale_factor": 2.0e7, "max_iter_to_alter": 4,
+                            "max_refinement_steps": 3}),
+                ("refine", {"scale_range": [1.0, 0.5], "thresholds": {0: 0.06, 2: 0.5}, "scale_factor": 1.0e7,
+                            "max_iter_to_alter": 25, "max_refinement_steps": 3})):
+    model = stand_in_model(O.DDIMSchedulerOracle(clip_sample=True, **SCHED))
+    model.weg_parameters = {k: (dict(v) if isinstance(v, dict) else (list(v) if isinstance(v, list) else v)) for k, v in wp.items()}
+    model.iterative_refinement_step = types.MethodType(ref_model.Convofusion.iterative_refinement_step, model)
+    torch.manual_seed(SEED + 4)
+    z_ref, att_ref = ref_model.Convofusion._diffusion_reverse(model, list(enc1), lengths=[128], cond_masks=masks1,
+                                                               focus_indices=[list(f) for f in focus])
+    torch.manual_seed(SEED + 4)
+    init = torch.randn(1, 16, 128)
+    log = []
+    z_or, att_or = O.diffusion_reverse(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED), enc1, masks1, init,
+                                       N_STEPS, guidance_scale=7.5, focus_indices=focus,
+                                       weg={k: (dict(v) if isinstance(v, dict) else v) for k, v in wp.items()}, weg_log=log)
+    assert torch.equal(z_ref.detach(), z_or.detach()), f"WEG[{tag}]: oracle loop differs from the reference loop"
+    # the same run without focus tokens must differ (the guidance really moved the latents)
+    with torch.no_grad():
+        z_plain, _ = O.diffusion_reverse(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED), enc1, masks1, init,
+                                         N_STEPS, guidance_scale=7.5)
+    moved = float((z_or.detach() - z_plain).norm() / z_plain.norm())
+    print(f"WEG[{tag}]: oracle loop == reference loop (bit for bit); losses {[round(e['loss'], 4) for e in log]}, "
+          f"refinement iterations {[e['n_refine'] for e in log]}, moved the result by {moved:.3f} (L2)")
+    assert moved > 1e-3
+    weg_out["cases"][tag] = {"z": z_ref.detach().clone(), "params": wp, "focus": focus, "log": log}
+torch.save(weg_out, ROOT / "tests" / "golden" / "ref_weg.pt")
+
 path = ROOT / "tests" / "golden" / "ref_loops.pt"
 torch.save(out, path)
 print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")

@@ -17,11 +17,11 @@ init = torch.randn(8, 16, 128, generator=torch.Generator().manual_seed(6)).cuda(
 out = s.generate(syn["clip"], syn["uncond_text"], syn["uncond_text_attn"], [128] * 8, init, use_graph=False)
 torch.cuda.synchronize(); print("sample ok", float(out["m_rst"].abs().mean()))'
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
-    python -m pytest tests/test_gpu_kernels.py -x -q -k "not writer" > "$out/${tool}_kernels.log" 2>&1
+  timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
+    python -m pytest tests/test_gpu_kernels.py -x -q -k "${SAN_K:-not writer}" > "$out/${tool}_kernels.log" 2>&1
   echo "exit=$?" >> "$out/${tool}_kernels.log"
-  for mask in 0 7; do
-    timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
+  for mask in ${SAN_MASKS:-0 7}; do
+    timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
       python -c "$SAMPLE" $mask > "$out/${tool}_sample_rowblock${mask}.log" 2>&1
     echo "exit=$?" >> "$out/${tool}_sample_rowblock${mask}.log"
   done
