@@ -787,9 +787,12 @@ static int check_epilogue(Epilogue& ep) {
 int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep_in,
             cudaStream_t st, int w_rows) {
   if (debug_skip(16)) return CFB_OK;
+  if (debug_skip(128) && ep_in.accumulate) return CFB_OK;      // diagnosis: drop only the residual-update GEMMs
+  if (debug_skip(256) && !ep_in.accumulate) return CFB_OK;     // ... only the others
   CFB_CHECK(gemm_tc_supported(M, N, K, lda, ldw), "gemm_tc: unsupported shape %dx%dx%d", M, N, K);
   CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_tc: operands must be 16-byte aligned");
   Epilogue ep = ep_in;
+  if (debug_skip(64)) ep.accumulate = 0;                       // diagnosis: plain TMA store instead of the L2 reduce-add
   CFB_TRY(check_epilogue(ep));
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
