@@ -142,6 +142,7 @@ struct SplitCtx {
   void* a_ws; size_t a_ws_bytes;   // stream-ordered scratch for the split of a dynamic A operand
   void* w_ws; size_t w_ws_bytes;   // ... of a dynamic W operand
   SplitCache* cache;               // splits of static operands (weights), filled on first use outside stream capture
+  int scheme;                      // 0: 3 x 3 terms (fp32-accurate), 1: A hi+lo x W bf16, 2: bf16 x bf16 (gemm_split.cu)
 };
 SplitCache* split_cache_create();
 void split_cache_destroy(SplitCache* c);
@@ -162,6 +163,7 @@ struct Epilogue {
   // fp32 operands on the tensor cores (3-way bf16 split, gemm_split.cu): null = CUDA-core GEMM for fp32 operands
   const SplitCtx* split;
   int a_static, w_static;    // the operand is a weight (its split is cached) rather than an activation
+  int a_from_ln;             // precision study (scheme 3): the A operand is a LayerNorm output
 };
 
 // GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.

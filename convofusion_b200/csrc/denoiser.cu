@@ -91,6 +91,7 @@ struct cfb_denoiser {
   DeviceBuf split_ws;
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
+  int split_scheme = 0;   // g_fp32_tc - 1 at the last reserve_split (1: fp32-accurate; 2, 3: precision-study schemes)
   // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
   DeviceBuf rb_prog, rb_blk;
   std::vector<RbStage> rb_host;
@@ -152,6 +153,7 @@ SplitCtx split_ctx(const cfb_denoiser* h, int row, int chain, bool side) {
   c.w_ws = base + 2 * h->split_a_bytes + (size_t)(2 * chain + (side ? 1 : 0)) * h->split_w_bytes;
   c.w_ws_bytes = h->split_w_bytes;
   c.cache = h->split_cache;
+  c.scheme = h->split_scheme;
   return c;
 }
 SplitCtx split_ctx_pre(const cfb_denoiser* h, int which) {
@@ -161,12 +163,14 @@ SplitCtx split_ctx_pre(const cfb_denoiser* h, int which) {
   c.a_ws = base + (size_t)(2 * which) * h->split_w_bytes; c.a_ws_bytes = h->split_w_bytes;
   c.w_ws = base + (size_t)(2 * which + 1) * h->split_w_bytes; c.w_ws_bytes = h->split_w_bytes;
   c.cache = h->split_cache;
+  c.scheme = h->split_scheme;
   return c;
 }
 
 int reserve_split(cfb_denoiser* h, int n_batch, const cfb_memory* mem, bool plan) {
   h->fp32_tc = h->prec == CFB_F32 && g_fp32_tc != 0 && g_gemm_backend != CFB_GEMM_SIMT;
   if (!h->fp32_tc) return CFB_OK;
+  h->split_scheme = g_fp32_tc >= 1 && g_fp32_tc <= 4 ? g_fp32_tc - 1 : 0;
   if (!h->split_cache) h->split_cache = split_cache_create();
   const size_t R = (size_t)n_batch * h->ntok, d = h->d;
   size_t kmax = h->ff > (int)d ? h->ff : d, rows_w = d, k_w = d;
@@ -404,16 +408,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   const SplitCtx* scs = (!tb && h->fp32_tc) ? &sc_side : nullptr;
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
-    ep.split = scm; ep.w_static = 1;
+    ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1;      // every caller passes a = LayerNorm(h)
     return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
   };
   // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
   // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
   //  and are gone; the row-block kernel (rowblock.cu) is what fuses them now.
   auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
-                        const float* mod) {
+                        const float* mod, int a_ln = 0) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
-    ep.split = scm; ep.w_static = 1;
+    ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_ln;
     CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
     CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
     return (int)CFB_OK;
@@ -430,7 +434,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
     } else {
       CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1));          // + time_block1 prologue (:575)
-      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr));     // + norm2 (:578)
+      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 1));  // + norm2 (:578)
     }
     // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
     for (int x = 0; x < CFB_N_STREAMS; ++x)
@@ -473,7 +477,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
             Epilogue e1 = eq; e1.bias = w.b_qx + grp[z].x * d;
             e1.out = qx_abs + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d;
             const SplitCtx sg = split_ctx(h, grp[z].lo, chain, side);   // the group's own rows of the scratch arena
-            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1;
+            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1; e1.a_from_ln = 1;
             CFB_TRY(gemm(a_abs + (size_t)grp[z].lo * d, 0, d, (const float*)w.w_qx + (size_t)grp[z].x * d * d, 0, d,
                          grp[z].rows, d, d, 0, e1, sc));
           }
@@ -510,7 +514,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
-      es.ldo = sp->n_tot; es.replicate = 1; es.split = scm;     // keys Z change every step: split into this chain's W slot
+      es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 1;   // keys Z change every step: this chain's W slot
       CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
@@ -537,7 +541,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
       CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2));   // + time_block2 prologue (:655)
     }
-    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr));      // + norm3 (:659)
+    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 1));   // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
     CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU));
     const bool last = l + 1 == h->L;
@@ -550,7 +554,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
-  ep.split = scm; ep.w_static = 1;
+  ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1;
   return gemm(a, tb, d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
 }
 
@@ -807,8 +811,9 @@ int cfb_set_rowblock(int mask) {
   return CFB_OK;
 }
 
-int cfb_set_fp32_tensor_cores(int enabled) {
-  g_fp32_tc = enabled != 0;
+int cfb_set_fp32_tensor_cores(int mode) {
+  CFB_CHECK(mode >= 0 && mode <= 4, "cfb_set_fp32_tensor_cores: mode %d outside 0..4", mode);
+  g_fp32_tc = mode;
   return CFB_OK;
 }
 
@@ -1141,7 +1146,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (int)h->fp32_tc; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0); key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

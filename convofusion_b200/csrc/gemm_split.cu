@@ -10,6 +10,10 @@
 //     A side:  hi  hi  mid hi  mid lo        W side:  hi  mid hi  lo  mid hi
 // so that block t of A meets block t of W.  Any 64-aligned K slice of an operand is a contiguous 6x wider slice of its
 // split.  Activations are split on the fly into a stream-ordered scratch; weights are split once per handle (cache).
+//
+// Reduced schemes for the precision study (tools/precision_study.py): scheme 1 keeps the
+// activations at two bf16 terms (hi + lo, 16 mantissa bits) against bf16-rounded weights (2 blocks per 64 columns:
+// A hi lo / W hi hi), scheme 2 rounds both operands to bf16 (1 block) -- the bf16 mode's GEMM rounding in isolation.
 #include "common.cuh"
 #include <mutex>
 #include <unordered_map>
@@ -19,9 +23,13 @@ namespace cfb {
 namespace {
 
 struct Key {
-  const void* p; int rows, K; long long ld; int role;
+  const void* p; int rows, K; long long ld; int role;   // role = operand side + 2 * scheme
   bool operator==(const Key& o) const { return p == o.p && rows == o.rows && K == o.K && ld == o.ld && role == o.role; }
 };
+// which term (0 hi, 1 mid, 2 lo) goes into block t of the split operand, per scheme and side
+__constant__ int c_comp[3][2][6] = {{{0, 0, 1, 0, 1, 2}, {0, 1, 0, 2, 1, 0}}, {{0, 1, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}},
+                                    {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}}};
+constexpr int kBlocks[3] = {6, 2, 1};
 struct KeyHash {
   size_t operator()(const Key& k) const {
     size_t h = std::hash<const void*>()(k.p);
@@ -30,10 +38,9 @@ struct KeyHash {
   }
 };
 
-// ROLE 0 = A operand (hi hi mid hi mid lo), ROLE 1 = W operand (hi mid hi lo mid hi)
-template <int ROLE>
+// side 0 = A operand, 1 = W operand; `nblk` blocks of 64 columns per 64 input columns (6 / 2 / 1 by scheme)
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ X, long long ld, bf16* __restrict__ out,
-                                                     int rows, int K) {
+                                                     int rows, int K, int scheme, int side, int nblk) {
   pdl_sync();
   const int c8n = K >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,31 +49,24 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ X
   const float4 x0 = *reinterpret_cast<const float4*>(X + (size_t)r * ld + c);
   const float4 x1 = *reinterpret_cast<const float4*>(X + (size_t)r * ld + c + 4);
   const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-  __align__(16) bf16 hi[8], mid[8], lo[8];
+  __align__(16) bf16 term[3][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    hi[i] = __float2bfloat16_rn(x[i]);
-    const float r1 = x[i] - __bfloat162float(hi[i]);            // exact
-    mid[i] = __float2bfloat16_rn(r1);
-    lo[i] = __float2bfloat16_rn(r1 - __bfloat162float(mid[i]));  // exact difference, rounded once
+    term[0][i] = __float2bfloat16_rn(x[i]);
+    const float r1 = x[i] - __bfloat162float(term[0][i]);            // exact
+    term[1][i] = __float2bfloat16_rn(r1);
+    term[2][i] = __float2bfloat16_rn(r1 - __bfloat162float(term[1][i]));  // exact difference, rounded once
   }
-  bf16* o = out + (size_t)r * 6 * K + (size_t)(c >> 6) * 384 + (c & 63);
-  const uint4 H = *reinterpret_cast<const uint4*>(hi), M = *reinterpret_cast<const uint4*>(mid), L = *reinterpret_cast<const uint4*>(lo);
-  if (ROLE == 0) {
-    *reinterpret_cast<uint4*>(o) = H; *reinterpret_cast<uint4*>(o + 64) = H; *reinterpret_cast<uint4*>(o + 128) = M;
-    *reinterpret_cast<uint4*>(o + 192) = H; *reinterpret_cast<uint4*>(o + 256) = M; *reinterpret_cast<uint4*>(o + 320) = L;
-  } else {
-    *reinterpret_cast<uint4*>(o) = H; *reinterpret_cast<uint4*>(o + 64) = M; *reinterpret_cast<uint4*>(o + 128) = H;
-    *reinterpret_cast<uint4*>(o + 192) = L; *reinterpret_cast<uint4*>(o + 256) = M; *reinterpret_cast<uint4*>(o + 320) = H;
-  }
+  bf16* o = out + (size_t)r * nblk * K + (size_t)(c >> 6) * (64 * nblk) + (c & 63);
+  for (int t = 0; t < nblk; ++t)
+    *reinterpret_cast<uint4*>(o + 64 * t) = *reinterpret_cast<const uint4*>(term[c_comp[scheme][side][t]]);
 }
 
-int split3(const float* X, long long ld, bf16* out, int rows, int K, int role, cudaStream_t st) {
+int split3(const float* X, long long ld, bf16* out, int rows, int K, int side, int scheme, cudaStream_t st) {
   const long long n = (long long)rows * (K >> 3);
   if (n <= 0) return CFB_OK;
   const unsigned grid = (unsigned)((n + 255) / 256);
-  if (role == 0) launch_k(split3_kernel<0>, dim3(grid), dim3(256), 0, st, X, ld, out, rows, K);
-  else launch_k(split3_kernel<1>, dim3(grid), dim3(256), 0, st, X, ld, out, rows, K);
+  launch_k(split3_kernel, dim3(grid), dim3(256), 0, st, X, ld, out, rows, K, scheme, side, kBlocks[scheme]);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -88,19 +88,20 @@ void split_cache_destroy(SplitCache* c) {
 size_t split_cache_bytes(const SplitCache* c) { return c ? c->bytes : 0; }
 
 // Split of a STATIC operand (a weight): computed on first use, kept for the lifetime of the cache.
-int split_static(SplitCache* c, const float* X, int rows, int K, long long ld, int role, cudaStream_t st, const bf16** out) {
+int split_static(SplitCache* c, const float* X, int rows, int K, long long ld, int side, int scheme, cudaStream_t st,
+                 const bf16** out) {
   CFB_CHECK(c != nullptr, "gemm_split: static operand without a cache");
   std::lock_guard<std::mutex> g(c->mu);
-  const Key key{X, rows, K, ld, role};
+  const Key key{X, rows, K, ld, side + 2 * scheme};
   auto it = c->map.find(key);
   if (it != c->map.end()) { *out = reinterpret_cast<const bf16*>(it->second); return CFB_OK; }
   CFB_CHECK(!t_capturing, "gemm_split: a weight would be split inside a stream capture (prefill the cache first)");
   void* p = nullptr;
-  const size_t bytes = (size_t)rows * 6 * K * 2;
+  const size_t bytes = (size_t)rows * kBlocks[scheme] * K * 2;
   CFB_CUDA(cudaMalloc(&p, bytes));
   c->bytes += bytes;
   c->map.emplace(key, p);
-  CFB_TRY(split3(X, ld, reinterpret_cast<bf16*>(p), rows, K, role, st));
+  CFB_TRY(split3(X, ld, reinterpret_cast<bf16*>(p), rows, K, side, scheme, st));
   *out = reinterpret_cast<const bf16*>(p);
   return CFB_OK;
 }
@@ -115,23 +116,27 @@ int gemm_split(const float* A, long long lda, const float* W, long long ldw, int
   CFB_CHECK(sc != nullptr && gemm_split_supported(M, N, K, lda, ldw), "gemm_split: unsupported call %dx%dx%d", M, N, K);
   CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_split: operands must be 16-byte aligned");
   const bf16 *As = nullptr, *Ws = nullptr;
+  // scheme 3 (precision study): hi + lo activations only where the A operand is a LayerNorm output, bf16 elsewhere
+  const int scheme = sc->scheme == 3 ? (ep.a_from_ln ? 1 : 2) : sc->scheme;
+  CFB_CHECK(scheme >= 0 && scheme < 3, "gemm_split: unknown scheme %d", scheme);
+  const int nb = kBlocks[scheme];
   if (ep.a_static) {
-    CFB_TRY(split_static(sc->cache, A, M, K, lda, 0, st, &As));
+    CFB_TRY(split_static(sc->cache, A, M, K, lda, 0, scheme, st, &As));
   } else {
-    CFB_CHECK((size_t)M * 6 * K * 2 <= sc->a_ws_bytes, "gemm_split: A scratch too small (%d x %d)", M, K);
-    CFB_TRY(split3(A, lda, reinterpret_cast<bf16*>(sc->a_ws), M, K, 0, st));
+    CFB_CHECK((size_t)M * nb * K * 2 <= sc->a_ws_bytes, "gemm_split: A scratch too small (%d x %d)", M, K);
+    CFB_TRY(split3(A, lda, reinterpret_cast<bf16*>(sc->a_ws), M, K, 0, scheme, st));
     As = reinterpret_cast<const bf16*>(sc->a_ws);
   }
   if (ep.w_static) {
-    CFB_TRY(split_static(sc->cache, W, N, K, ldw, 1, st, &Ws));
+    CFB_TRY(split_static(sc->cache, W, N, K, ldw, 1, scheme, st, &Ws));
   } else {
-    CFB_CHECK((size_t)N * 6 * K * 2 <= sc->w_ws_bytes, "gemm_split: W scratch too small (%d x %d)", N, K);
-    CFB_TRY(split3(W, ldw, reinterpret_cast<bf16*>(sc->w_ws), N, K, 1, st));
+    CFB_CHECK((size_t)N * nb * K * 2 <= sc->w_ws_bytes, "gemm_split: W scratch too small (%d x %d)", N, K);
+    CFB_TRY(split3(W, ldw, reinterpret_cast<bf16*>(sc->w_ws), N, K, 1, scheme, st));
     Ws = reinterpret_cast<const bf16*>(sc->w_ws);
   }
   Epilogue e2 = ep;
   e2.split = nullptr;
-  return gemm_tc(As, 6 * K, Ws, 6 * K, M, N, 6 * K, e2, st);
+  return gemm_tc(As, nb * K, Ws, nb * K, M, N, nb * K, e2, st);
 }
 
 }  // namespace cfb

@@ -62,8 +62,10 @@ int cfb_set_rowblock(int mask);
 /* fp32 handles (precision = CFB_F32): 1 = the denoiser's GEMMs run on the tcgen05 tensor cores as three-way bf16 splits
  * of both fp32 operands (hi + mid + lo, six partial products, fp32 accumulation in tensor memory: fp32-level error at
  * 6x the MMA work of the bf16 mode, csrc/gemm_split.cu) instead of the CUDA-core FFMA GEMM (the default; env
- * CFB_FP32_TC); 0 = CUDA cores.  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
-int cfb_set_fp32_tensor_cores(int enabled);
+ * CFB_FP32_TC); 0 = CUDA cores.  Modes 2 and 3 are precision-study settings, not production modes: 2 = activations
+ * hi + lo (two bf16 terms) against bf16-rounded weights, 3 = both operands rounded to bf16 (the bf16 mode's GEMM
+ * rounding with everything else in fp32).  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
+int cfb_set_fp32_tensor_cores(int mode);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);
 
