@@ -11,7 +11,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libconvofusion_b200.so"
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_split.cu", "rowops.cu", "attention.cu", "sched.cu", "weg.cu", "rowblock.cu", "denoiser.cu", "vae.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_split.cu", "rowops.cu", "attention.cu", "cross_tc.cu", "sched.cu", "weg.cu", "rowblock.cu", "denoiser.cu", "vae.cu"]
 NVCC_FLAGS = os.environ.get("CFB_EXTRA_NVCC", "").split() + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--threads", "0"]
 

@@ -886,7 +886,9 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
     CFB_CHECK(a.len[x] > 0, "cross_attention: stream %d has no memory tokens", x);
     if (a.len[x] > maxM) maxM = a.len[x];
   }
-  if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernel (in-place u == qx is fine: Q is staged before u is written)
+  if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernels (in-place u == qx is fine: Q is staged before u is written)
+    if (cross_tc_supported(a, n_tokens, d))   // tcgen05 / TMEM / TMA (cross_tc.cu); else mma.sync below
+      return cross_attention_tc(qx, (a.bs_offset + n_batch) * n_tokens, mem_hat, u, a, n_batch, st);
     const int Sp = ((maxM + 7) & ~7) + 8, Pp = ((maxM + 15) & ~15) + 8;
     const size_t smem_mma = (size_t)(16 * QP + CM_NBUF * 16 * XP) * 2 + (size_t)16 * Sp * 4 + (size_t)16 * Pp * 2;
     // CFB_GEMM_SIMT selects the CUDA-core engines everywhere (tests cross-check the two implementations)

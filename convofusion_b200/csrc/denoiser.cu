@@ -23,6 +23,7 @@ namespace cfb {
 
 int init_gemm_tc_kernels();
 int init_attention_kernels();
+extern int g_cross_tc;
 
 struct DeviceBuf {
   void* p = nullptr;
@@ -66,7 +67,7 @@ struct cfb_denoiser {
   std::vector<cfb_denoiser_layer> layers;
   int d, lat, ntok, L, H, ff, prec;
   unsigned epoch = 0;
-  DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
+  DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, mem_hat_t, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
       preseq, slots, masks, uc, sS, sP, zall, z0all, ytall;
   // cached CUDA graph of one sampling step
   cudaGraphExec_t graph_exec = nullptr;
@@ -606,6 +607,18 @@ int prep_memory(cfb_denoiser* h, const cfb_memory* mem, int n_batch, MemLayout* 
   CFB_TRY(h->masks.reserve((size_t)mask_bytes, &h->epoch));
   CFB_TRY(mem_build(mem->cond, mem->n_slots, mem->len, h->w.stream_emb, h->w.pe_mem, h->mem_c.as<float>(), h->d, st));
   memset(ca, 0, sizeof(*ca));
+  long long t_elems = 0;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    ca->n_slots[x] = mem->n_slots[x];
+    ca->lenp[x] = (mem->len[x] + 7) & ~7;
+    ca->t_off[x] = t_elems;
+    t_elems += (long long)mem->n_slots[x] * h->d * ca->lenp[x];
+    t_elems = (t_elems + 63) & ~63LL;                      // tensor maps want 128-byte aligned bases
+  }
+  if (h->prec == CFB_BF16) {                               // transposed copy for the tcgen05 per-pair attention
+    CFB_TRY(h->mem_hat_t.reserve((size_t)t_elems * 2, &h->epoch));
+    ca->mem_hat_t = h->mem_hat_t.as<bf16>();
+  }
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     ca->row_base[x] = ml->row_base[x];
     ca->len[x] = mem->len[x];
@@ -635,6 +648,8 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
     CFB_CUDA(cudaStreamWaitEvent(h->pre_st[0], h->ev_fork, 0));
     CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, h->pre_st[0]));
     CFB_CUDA(cudaEventRecord(h->ev_mh, h->pre_st[0]));
+    if constexpr (sizeof(T) == 2)
+      if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, h->pre_st[0]));
     CFB_CUDA(cudaStreamWaitEvent(h->pre_st[1], h->ev_mh, 0));
     for (int i = 0; i < 2; ++i) {
       CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, i, h->pre_st[i]));
@@ -642,6 +657,8 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
     }
   } else {
     CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
+    if constexpr (sizeof(T) == 2)
+      if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, st));
     if (sp.on) {
       CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, 0, st));
       CFB_TRY(shared_precompute<T>(h, sp, ml, ca.len, 1, st));
@@ -772,6 +789,7 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
   h->ff = w->ff_size; h->prec = w->precision;
   int rc = init_gemm_tc_kernels();
   if (rc == CFB_OK) rc = init_attention_kernels();
+  if (rc == CFB_OK) rc = init_cross_tc_kernels();
   if (rc != CFB_OK) { delete h; return rc; }
   *out = h;
   return CFB_OK;
@@ -800,7 +818,7 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
                        &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws,
-                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2};
+                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2, &h->mem_hat_t};
   for (DeviceBuf* b : bufs) b->release();
   split_cache_destroy(h->split_cache);
   delete h;
@@ -814,6 +832,11 @@ int cfb_set_rowblock(int mask) {
 int cfb_set_fp32_tensor_cores(int mode) {
   CFB_CHECK(mode >= 0 && mode <= 4, "cfb_set_fp32_tensor_cores: mode %d outside 0..4", mode);
   g_fp32_tc = mode;
+  return CFB_OK;
+}
+
+int cfb_set_cross_tc(int enabled) {
+  g_cross_tc = enabled != 0;
   return CFB_OK;
 }
 
@@ -849,6 +872,7 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
   CFB_TRY(reserve_split(h, n_batch, mem, false));
   if (h->prec == CFB_BF16) {
     CFB_TRY(mem_hat<bf16>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<bf16>(), ml.total_rows, h->d, st));
+    if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, st));
     CFB_TRY(embed<bf16>(h, sample, n_batch, 1, st));
     return run_layers<bf16>(h, n_batch, ca, att_out, nullptr, eps_out, st);
   }

@@ -44,7 +44,18 @@ struct CrossArgs {
   const int* step_ptr;
   int skip_slot0;                       // 1: (batch entry, stream) pairs on slot 0 are handled by the shared path
   int bs_offset;                        // first batch entry handled by this launch (blockIdx.x is relative to it)
+  // tcgen05 per-pair kernel (cross_tc.cu): slots per stream and the transposed copy of the memory
+  int n_slots[CFB_N_STREAMS];
+  const bf16* mem_hat_t;                // per stream x at element offset t_off[x]: [n_slots, 512, lenp[x]] or nullptr
+  long long t_off[CFB_N_STREAMS];
+  int lenp[CFB_N_STREAMS];              // len rounded up to a multiple of 8 (16-byte rows)
 };
+// cross_tc.cu
+int init_cross_tc_kernels();
+bool cross_tc_supported(const CrossArgs& a, int n_tokens, int d);
+int mem_transpose(const bf16* mem_hat, bf16* mem_hat_t, const CrossArgs& a, cudaStream_t st);
+int cross_attention_tc(const bf16* qx, int q_rows, const bf16* mem_hat, bf16* u, const CrossArgs& a, int n_batch,
+                       cudaStream_t st);
 // Shared-slot path: scores of every row against slot 0 of every stream come from ONE GEMM (S, fp32, stream x
 // at columns s_off[x] .. +len[x]); this turns them into bf16 probabilities P (stream x at p_off[x] .. +kp[x],
 // zero padded), writing zeros where the pair is conditional (slot != 0) and handled by cross_attention().

@@ -66,6 +66,11 @@ int cfb_set_rowblock(int mask);
  * hi + lo (two bf16 terms) against bf16-rounded weights, 3 = both operands rounded to bf16 (the bf16 mode's GEMM
  * rounding with everything else in fp32).  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
 int cfb_set_fp32_tensor_cores(int mode);
+/* Per-pair cross-attention of bf16 handles (cross_attention.py:593-626: 16 queries against one clip's <= 256 memory
+ * tokens): 1 = the tcgen05 / tensor-memory / TMA kernel (csrc/cross_tc.cu: both products issued transposed, queries as
+ * the N = 16 dimension), 0 (default, also env CFB_CROSS_TC) = the mma.sync m16n8k16 kernel, which is faster for these
+ * 16-row problems. */
+int cfb_set_cross_tc(int enabled);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 unsigned long long cfb_launch_count(void);
 

@@ -46,6 +46,7 @@ def test_optional_paths_agree_with_default(tmp_path):
     for name, env in (("staged_epilogue", {"CFB_TC_TMA_EPI": "0"}),
                       ("softmax_strided", {"CFB_SOFTMAX_STRIDED": "1"}), ("mha_simt", {"CFB_MHA_SIMT": "1"}),
                       ("no_plan", {"CFB_PLAN": "0"}), ("rowblock_all", {"CFB_ROWBLOCK": "7"}),
+                      ("cross_tcgen05", {"CFB_CROSS_TC": "1"}),
                       ("serial", {"CFB_CHAINS": "1", "CFB_PDL": "0", "CFB_OVERLAP": "0"})):
         got = run(tmp_path, name, env)
         err = float((got[0] - base[0]).abs().max()) / scale

@@ -109,6 +109,44 @@ def test_bf16_forward_tensor_core_engines_vs_cuda_core_engines():
     assert float(att_tc[2][masks7["tlsn"][:, None, None, :].expand_as(att_tc[2])].abs().max()) == 0.0
 
 
+def test_tcgen05_per_pair_attention_vs_oracle_and_mma_sync():
+    """csrc/cross_tc.cu (tcgen05 / TMEM / TMA per-pair attention, both products issued transposed) against the oracle and
+    against the mma.sync kernel on the same bf16 operands: all five streams per pair (general path), ragged masks,
+    attention maps, B not a tile multiple; then inside the sampling loop (shared-slot plan, conditional pairs only)."""
+    s = gpu_sampler("bf16")
+    syn = synthetic_clip(3, seed=78, dyadic=True)
+    syn["clip"]["text_lsn_attn"][0] = 0
+    syn["clip"]["text_lsn_attn"][0, :3] = 1
+    enc, masks = gpu_batch(s, syn)
+    enc7, masks7 = expand_guidance_batch(enc, masks, 3)
+    x = torch.randn(21, 16, 128, generator=torch.Generator().manual_seed(6)).to(DEV)
+    eps_mma, att_mma = s.denoiser(x, torch.tensor(500), enc7, None, masks7)
+    _lib.check(_lib.lib().cfb_set_cross_tc(1))
+    try:
+        n0 = _lib.lib().cfb_launch_count()
+        eps_tc, att_tc = s.denoiser(x, torch.tensor(500), enc7, None, masks7)
+        n_tc = _lib.lib().cfb_launch_count() - n0
+        s.num_inference_timesteps = 3
+        init = torch.randn(3, 16, 128, generator=torch.Generator().manual_seed(7)).to(DEV)
+        _, rec_tc, _ = s.sample(enc, masks, 3, init, record=True)
+    finally:
+        _lib.check(_lib.lib().cfb_set_cross_tc(0))
+    _, rec_mma, _ = s.sample(enc, masks, 3, init, record=True)
+    o_enc, o_masks = oracle_batch(syn)
+    want, watt = oracle_denoise(x.cpu(), 500, o_enc, o_masks)
+    e_tc, e_mma = rel_err(eps_tc.cpu(), want), rel_err(eps_mma.cpu(), want)
+    print(f"bf16 eps L2 vs oracle: tcgen05 per-pair attention {e_tc:.2e}, mma.sync {e_mma:.2e}; tc-vs-mma "
+          f"{rel_err(eps_tc, eps_mma):.2e}; launches {n_tc}; 3-step latents tc-vs-mma {rel_err(rec_tc[-1], rec_mma[-1]):.2e}")
+    assert not torch.equal(eps_tc, eps_mma)                       # the switch selects another kernel
+    assert e_tc < BF16_TOL["eps_l2"] and e_tc < 1.5 * e_mma + 1e-3
+    for i in range(5):
+        assert max_rel(att_tc[i].cpu(), watt[i]) < 0.3, i
+        assert max_rel(att_tc[i].cpu(), att_mma[i].cpu()) < 0.1, i
+        assert float(att_tc[i].sum(-1).sub(1).abs().max()) < 1e-4
+    assert float(att_tc[2][masks7["tlsn"][:, None, None, :].expand_as(att_tc[2])].abs().max()) == 0.0
+    assert rel_err(rec_tc[0], rec_mma[0]) < 0.1
+
+
 def test_ragged_and_edge_inputs():
     """Ragged text lengths per clip, a clip whose listener text has one valid token, B not a tile multiple."""
     s = gpu_sampler("fp32")
