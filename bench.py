@@ -305,6 +305,14 @@ def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, cloc
                             "frac_of_sustained_peak": tf / peak_tf, "sustained_peak": peak_tf,
                             "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
                             "peak_source": peak_src, "launches_timed": roof["launches"], "ms_timed": roof["ms"],
+                            "concurrent_streams": roof.get("concurrent_streams"),
+                            "how": "achieved = 2 M N K summed over the timed launches / CUDA-event time of one graph replay of "
+                                   "them, issued with the step's own concurrency (one stream per chain and lane); "
+                                   "one_stream_back_to_back is the same launch list on a single stream (each launch "
+                                   "alone on the GPU: the kernel's latency-bound floor at 28-56 CTAs per launch)",
+                            "one_stream_back_to_back": None if not roof.get("serial") else {
+                                "achieved": roof["serial"]["tflops"], "frac": roof["serial"]["tflops"] / peak_burst,
+                                "ms_timed": roof["serial"]["ms"], "launches_timed": roof["serial"]["launches"]},
                             "shapes": roof.get("shapes"),
                             "whole_step_frac": fl["executed"] / (ms_den * 1e-3) / 1e12 / peak_tf,
                             "whole_step_frac_at_throughput":
@@ -338,7 +346,7 @@ def _graph_time(torch, side, one_pass, iters):
     return e0.elapsed_time(e1) / iters
 
 
-def gemm_roofline(torch, batch, n_branch, dev, chains, iters=20):
+def gemm_roofline(torch, batch, n_branch, dev, chains, iters=20, lanes=1):
     """Device time of the tcgen05 GEMM kernel family over the GEMM shape mix of one denoiser evaluation AT THE SHAPES
     THE STEP LAUNCHES: every chain's row count (n_batch / chains entries x 16 tokens), the eight full-batch operators
     of a layer, the conditional projections (query projection + fuser block of the chain's conditional stream) and the
@@ -386,10 +394,42 @@ def gemm_roofline(torch, batch, n_branch, dev, chains, iters=20):
                     lin(As[k], w, outs["bf16" if kind in ("bf16", "gelu") else "f32"][n], M, n, k, kind)
 
     ms = _graph_time(torch, side, one_pass, iters)
-    return {"tflops": acc["flops"] / (ms * 1e-3) / 1e12, "ms": ms, "launches": acc["n"],
-            "kernel": "gemm_tc_tma_kernel family (tcgen05, TMA store / L2 reduce-add epilogue) at the step's per-chain shapes",
+    serial = {"tflops": acc["flops"] / (ms * 1e-3) / 1e12, "ms": ms, "launches": acc["n"]}
+
+    # The same launches with the concurrency they have inside the step: every chain of every lane on its own stream
+    # (forked from / joined into the captured stream).  The chains of a step are dependent sequences of 5-10 us launches
+    # of 28-56 CTAs each; what the step gets out of the kernel is its aggregate rate with `lanes x chains` of them
+    # side by side, which is what the whole-step figures are built from.
+    n_streams = lanes * len(rows)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    lane_outs = [{"bf16": {n: torch.empty(R, n, device=dev, dtype=torch.bfloat16) for n in (3 * d, 1024, d)},
+                  "f32": {n: torch.zeros(R, n, device=dev) for n in (d, n_tot)}} for _ in range(n_streams)]
+
+    def lin_on(stream, A, W, out, M, n, k, kind):
+        obf = kind in ("bf16", "gelu")
+        _lib.check(lib.cfb_linear(A.data_ptr(), 1, W.data_ptr(), 0, out.data_ptr(), int(obf), M, n, k,
+                                  1 if kind == "gelu" else 0, 0, int(kind == "res"), _lib.GEMM_TCGEN05, stream.cuda_stream))
+        acc["flops"] += 2.0 * M * n * k
+        acc["n"] += 1
+
+    def concurrent_pass():
+        acc["flops"], acc["n"] = 0.0, 0
+        for i, s in enumerate(streams):
+            s.wait_stream(side)
+            M, o = rows[i % len(rows)], lane_outs[i]
+            for layer in Ws:
+                for (n, k, kind), w in zip(spec, layer):
+                    lin_on(s, As[k], w, o["bf16" if kind in ("bf16", "gelu") else "f32"][n], M, n, k, kind)
+        for s in streams:
+            side.wait_stream(s)
+
+    ms_c = _graph_time(torch, side, concurrent_pass, iters)
+    return {"tflops": acc["flops"] / (ms_c * 1e-3) / 1e12, "ms": ms_c, "launches": acc["n"], "concurrent_streams": n_streams,
+            "serial": serial,
+            "kernel": "gemm_tc_tma_kernel family (tcgen05, TMA store / L2 reduce-add epilogue) at the step's per-chain shapes, "
+                      f"{n_streams} chains side by side as in the step ({lanes} batches in flight x {len(rows)} chains)",
             "shapes": {"chain_rows": rows, "per_layer_NK": [(n, k) for n, k, _ in spec],
-                       "memory_side": f"{len(MEM_LEN)} streams x 2 x [len, {L * d}, {d}]"}}
+                       "memory_side": f"{len(MEM_LEN)} streams x 2 x [len, {L * d}, {d}] (serial figure only)"}}
 
 
 def memory_bound_roofline(torch, batch, n_branch, dev, chains):
@@ -660,7 +700,7 @@ def run_ours(args):
                  "decode_ms": ev[2].elapsed_time(ev[3])}
         if rank == 0 and args.precision == "bf16" and not args.no_roofline:
             chains = 3 if F > 1 else 6
-            roof = gemm_roofline(torch, B, n_branch, dev, chains)
+            roof = gemm_roofline(torch, B, n_branch, dev, chains, lanes=max(1, F))
             roof["mem"] = memory_bound_roofline(torch, B, n_branch, dev, chains)
     if per_rank_ms:
         extra["per_rank_ms"] = per_rank_ms
