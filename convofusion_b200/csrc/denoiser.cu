@@ -856,6 +856,7 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
                          float* eps_out, float* const att_out[CFB_N_STREAMS], cfb_stream stream) {
   CFB_CHECK(h && sample && mem && eps_out && n_batch > 0, "cfb_denoiser_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  h->weg.valid = false;     // the workspace the saved activations refer to is about to be reused
   CFB_TRY(reserve_rows(h, n_batch, n_batch));
   h->sched_epoch = ~0u;   // the single-step tables below replace those of the last cfb_sample call
   CFB_TRY(h->tsteps.reserve(4, &h->epoch));
@@ -1025,6 +1026,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
   CFB_CHECK(sched->n_steps > 0 && sched->timesteps && sched->coef, "cfb_sample: empty schedule");
   CFB_CHECK(sched->kind == CFB_SCHED_DDIM || sched->kind == CFB_SCHED_DDPM, "cfb_sample: unknown scheduler kind");
   CFB_CHECK(preseq == nullptr || (preseq_len > 0 && preseq_len <= h->ntok), "cfb_sample: bad preseq_len %d", preseq_len);
+  h->weg.valid = false;     // the workspace the saved activations refer to is about to be reused
   bool want_att = false;
   if (att_out) for (int x = 0; x < CFB_N_STREAMS; ++x) want_att |= att_out[x] != nullptr;
   CFB_CHECK(!want_att || full_last, "cfb_sample: attention maps come from the full-cond branch; evaluate it (full_last=1)");
