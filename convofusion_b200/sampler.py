@@ -19,7 +19,7 @@ from .conditioning import (TextAudioController, TextAudioMotionFuser, expand_gui
                            guidance_memory, guidance_slots, guidance_slots_host)
 from .modules import ConvoFusionVae, Denoiser
 from .schedulers import DDIMScheduler, DDPMScheduler
-from .weg import DEFAULT_WEG_PARAMETERS, weg_pre_step
+from .weg import DEFAULT_WEG_PARAMETERS, FORECAST_WEG_PARAMETERS, weg_pre_step
 
 MOTION_FPS = 25.0        # configs/config_cf_beatdnd.yaml:78-87
 WINDOW_FRAMES = 128
@@ -72,6 +72,7 @@ class ConvoFusionSampler(nn.Module):
         self.num_inference_timesteps = num_inference_timesteps
         self.eta = eta
         self.weg_parameters = {k: (dict(v) if isinstance(v, dict) else v) for k, v in DEFAULT_WEG_PARAMETERS.items()}   # :64
+        self.weg_forecast_parameters = {k: (dict(v) if isinstance(v, dict) else v) for k, v in FORECAST_WEG_PARAMETERS.items()}
         self.clf_guidance_drops = 6                              # convofusion.py:60
         self.do_classifier_free_guidance = guidance_scale > 1.0   # convofusion.py:131
         self.latent_dim = [1, self.denoiser.latent_dim]
@@ -140,6 +141,45 @@ class ConvoFusionSampler(nn.Module):
                 extra["variance_noise"] = step_noise[i]
             latents = self.scheduler.step(noise_pred, t, latents, **extra).prev_sample
         return latents.permute(1, 0, 2), attention_matrices
+
+    def _diffusion_reverse_forecast(self, encoder_hidden_states, lengths=None, preseq: Optional[Tensor] = None,
+                                    cond_masks=dict(), focus_indices=[], init_noise: Optional[Tensor] = None,
+                                    weg_log: Optional[list] = None):
+        """unbounded_synthesis.py:28-187 as written (per-step Denoiser.forward / scheduler.step on the 7*B batch, latent
+        inpainting of `preseq` [B, pl, 128] incl. the aliasing of `latents` and `init_noise` at step 0, :66-76), with the
+        word-excitation update of :78-142 before every guided step when `focus_indices` is given
+        (`self.weg_forecast_parameters` = the script's hard-coded values).  Returns (latents [16,B,128], the last
+        step's full-cond attention maps).  Without focus tokens `sample(preseq=...)` runs the same loop fused."""
+        if not self.do_classifier_free_guidance:
+            raise NotImplementedError("guidance_scale <= 1 (no classifier-free guidance) is not on the B200 hot path")
+        dev = encoder_hidden_states[0].device
+        mult = self.clf_guidance_drops + 1
+        bsz = encoder_hidden_states[0].shape[0] // mult
+        init_noise = (init_noise.clone() if init_noise is not None else torch.randn(
+            (bsz, 16, self.latent_dim[-1]), device=dev, dtype=torch.float)) * self.scheduler.init_noise_sigma
+        self.scheduler.set_timesteps(self.num_inference_timesteps)
+        timesteps = self.scheduler.timesteps.to(dev)
+        extra = {}
+        if "eta" in set(inspect.signature(self.scheduler.step).parameters.keys()):
+            extra["eta"] = self.eta
+        use_weg = len(focus_indices) > 0
+        weg_den = self._weg_denoiser() if use_weg else None
+        latents, att_mats = init_noise, None                              # :66 (alias)
+        for i, t in enumerate(timesteps):
+            if preseq is not None:
+                pl = preseq.shape[1]
+                noised = self.noise_scheduler.add_noise(preseq.clone(), init_noise.clone()[:, :pl, :], t)   # :73-75
+                latents[:, :pl, :] = noised                               # :76 (also rewrites init_noise at step 0)
+            if use_weg:
+                wp = self.weg_forecast_parameters
+                latents, _ = weg_pre_step(weg_den, latents, i, t, encoder_hidden_states, cond_masks, focus_indices, wp,
+                                          wp["scale_range"], len(timesteps), mult, weg_log)
+            x = torch.cat([latents] * mult)
+            noise_pred, att = self.denoiser(sample=x, timestep=t, encoder_hidden_states=encoder_hidden_states,
+                                            lengths=None, mem_mask_dict=cond_masks)
+            att_mats = [a.chunk(mult)[-1] for a in att]
+            latents = self.scheduler.step(self._combine(noise_pred), t, latents, **extra).prev_sample
+        return latents.permute(1, 0, 2), att_mats
 
     def _combine(self, noise_pred: Tensor) -> Tensor:
         # convofusion.py:527-541 through the fused kernel with identity scheduler coefficients:
@@ -221,17 +261,26 @@ class ConvoFusionSampler(nn.Module):
     # ------------------------------------------------------------------ unbounded synthesis
     @torch.no_grad()
     def synthesize_unbounded(self, windows: Sequence[Dict[str, Tensor]], uncond_text: Tensor, uncond_text_attn: Tensor,
-                             init_noise: Sequence[Tensor], use_graph: bool = True):
+                             init_noise: Sequence[Tensor], use_graph: bool = True,
+                             focus_indices: Optional[Sequence[Sequence[Sequence[int]]]] = None):
         """process_samples (unbounded_synthesis.py:244-512): serial windows at 50 % overlap; the last 8 latent tokens
         of window k are inpainted into the first 8 of window k+1 (:442-444, 70-76) and the root x/z of every decoded
         window is re-anchored on the previous one (:461-465).  `windows[k]` is the featurised conditioning of
-        window k for all B streams; returns the list of per-window joints [B,128,189]."""
+        window k for all B streams; returns the list of per-window joints [B,128,189].  `focus_indices[k]` (the word-
+        excitation focus tokens process_samples derives for window k, :402-410; B = 1 like the reference) switches that
+        window to the as-written loop with the WEG update (`_diffusion_reverse_forecast`)."""
         preseq, prev, outs = None, None, []
         for k, clip in enumerate(windows):
             B = clip["mel_lsn"].shape[0]
             enc, masks = self.encode_conditions(clip, uncond_text, uncond_text_attn)
-            z, _, _ = self.sample(enc, masks, B, init_noise[k], preseq=preseq, use_graph=use_graph,
-                                  spk_is_uncond=self.speaker_is_unconditional(clip, uncond_text, uncond_text_attn))
+            focus = focus_indices[k] if focus_indices is not None else []
+            if len(focus) > 0 and len(focus[0]) > 0:
+                enc7, masks7 = expand_guidance_batch(enc, masks, B)
+                z, _ = self._diffusion_reverse_forecast(enc7, [WINDOW_FRAMES] * B, preseq, masks7, focus_indices=focus,
+                                                        init_noise=init_noise[k])
+            else:
+                z, _, _ = self.sample(enc, masks, B, init_noise[k], preseq=preseq, use_graph=use_graph,
+                                      spk_is_uncond=self.speaker_is_unconditional(clip, uncond_text, uncond_text_attn))
             preseq = z[z.shape[0] // 2:].permute(1, 0, 2).contiguous()
             feats = self.decode(z, [WINDOW_FRAMES] * B)
             if prev is not None:

@@ -24,6 +24,9 @@ from torch import Tensor
 # configs/assets.yaml:18-24
 DEFAULT_WEG_PARAMETERS = {"scale_factor": 1000, "scale_range": [1.0, 0.5], "max_iter_to_alter": 800,
                           "thresholds": {0: 0.05, 200: 0.4, 400: 0.6, 600: 0.8}, "max_refinement_steps": 300}
+# unbounded_synthesis.py:82-87: diffusion_reverse_forecast hard-codes its own ("TODO: move to config")
+FORECAST_WEG_PARAMETERS = {"scale_factor": 100, "scale_range": (1.0, 0.5), "max_iter_to_alter": 800,
+                           "thresholds": {0: 0.05, 200: 0.4, 400: 0.6, 600: 0.8}, "max_refinement_steps": 300}
 TEXT_STREAM = 2   # memory order (spkemb, alsn, tlsn, apb, lsnemb): cross_attention.py:579
 
 

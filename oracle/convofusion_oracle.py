@@ -610,11 +610,19 @@ def weg_pre_step(denoise_fn, latents: Tensor, i: int, t, enc, masks, focus_indic
     return latents.detach(), scale_range
 
 
+# unbounded_synthesis.py:82-87: the forecast loop hard-codes its WEG parameters ("TODO: move to config")
+FORECAST_WEG = {"scale_factor": 100, "scale_range": (1.0, 0.5), "max_iter_to_alter": 800,
+                "thresholds": {0: 0.05, 200: 0.4, 400: 0.6, 600: 0.8}, "max_refinement_steps": 300}
+
+
 def diffusion_reverse_forecast(denoise_fn, scheduler, noise_scheduler, enc, masks, init_noise: Tensor,
                                num_steps: int, preseq: Optional[Tensor], guidance_scale: float = 7.5,
                                eta: float = 0.0, step_noise: Optional[Tensor] = None,
-                               record: Optional[list] = None):
-    """unbounded_synthesis.py:28-187 with focus_indices=[].  Reproduces the aliasing quirk:
+                               record: Optional[list] = None, focus_indices: Sequence[Sequence[int]] = (),
+                               weg: Optional[dict] = None, weg_log: Optional[list] = None):
+    """unbounded_synthesis.py:28-187; with focus_indices the latent update of :78-142 precedes every guided step (its
+    parameters are the script's hard-coded ones, FORECAST_WEG, and `scale_range` is the fresh tuple on every step --
+    unlike Convofusion._diffusion_reverse there is no array re-assignment here).  Reproduces the aliasing quirk:
     `latents = init_noise` (:66) shares storage, so the in-place inpaint at step 0 (:76) also
     rewrites init_noise[:, :preseq_len], which later steps then reuse as "noise" (:73)."""
     init_noise = init_noise.clone() * scheduler.init_noise_sigma            # :49
@@ -627,6 +635,10 @@ def diffusion_reverse_forecast(denoise_fn, scheduler, noise_scheduler, enc, mask
             preseq_noise = init_noise.clone()                               # :73
             noised = noise_scheduler.add_noise(preseq.clone(), preseq_noise[:, :pl, :], t)  # :75
             latents[:, :pl, :] = noised                                     # :76
+        if len(focus_indices) > 0:                                          # :78-142 (rebinds latents: the alias ends here)
+            wp = weg if weg is not None else FORECAST_WEG
+            latents, _ = weg_pre_step(denoise_fn, latents, i, t, enc, masks, focus_indices, wp, wp["scale_range"],
+                                      len(scheduler.timesteps), weg_log)
         x = torch.cat([latents] * N_BRANCH)
         noise_pred, att_mats = denoise_fn(x, t, enc, masks)
         att_mats = [a.chunk(N_BRANCH)[-1] for a in att_mats]

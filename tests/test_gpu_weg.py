@@ -95,7 +95,8 @@ def test_weg_loops_vs_reference_loop_code(precision):
     enc7, masks7 = expand_guidance_batch(enc, masks, 1)
     init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(g["init_seed"])).to(DEV)
     z_plain, _ = s._diffusion_reverse(enc7, [128], masks7, init_latents=init)
-    for tag, case in g["cases"].items():
+    for tag in ("update", "refine"):
+        case = g["cases"][tag]
         s.weg_parameters = dict(case["params"])
         log = []
         z, att = s._diffusion_reverse(enc7, [128], masks7, focus_indices=case["focus"], init_latents=init, weg_log=log)
@@ -110,6 +111,43 @@ def test_weg_loops_vs_reference_loop_code(precision):
     if precision == "bf16":
         assert s._weg_denoiser() is not s.denoiser and s._weg_denoiser().precision == "fp32"
         assert "_weg_twin" not in dict(s.named_modules())
+
+
+def test_weg_in_the_forecast_loop_vs_reference_loop_code():
+    """`_diffusion_reverse_forecast` (latent inpainting + WEG, unbounded_synthesis.py:28-187) against the reference's own
+    function (its hard-coded parameters: scale factor 100) and against the oracle's loop with a step size that makes the
+    guidance matter and triggers the refinement at step 0."""
+    g = golden("ref_weg.pt")
+    s = sampler("fp32", g["n_steps"])
+    syn = synthetic_clip(1, seed=g["clip_seed"], dyadic=True)
+    d = to_device(syn, DEV)
+    enc, masks = s.encode_conditions(d["clip"], d["uncond_text"], d["uncond_text_attn"])
+    enc7, masks7 = expand_guidance_batch(enc, masks, 1)
+    for tag in ("forecast", "forecast_big"):
+        case = g["cases"][tag]
+        pre = torch.randn(1, 8, 128, generator=torch.Generator().manual_seed(case["preseq_seed"])).to(DEV)
+        init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(case["init_seed"])).to(DEV)
+        keep = init.clone()
+        s.weg_forecast_parameters = dict(case["params"])
+        log = []
+        z, att = s._diffusion_reverse_forecast(enc7, [128], pre, masks7, focus_indices=case["focus"], init_noise=init,
+                                               weg_log=log)
+        err = rel_err(z.cpu(), case["z"])
+        print(f"WEG[{tag}]: vs reference loop L2 {err:.2e}; refinement iterations {[e['n_refine'] for e in log]}")
+        assert err < (2e-4 if tag == "forecast" else 1e-2)
+        assert [e["n_refine"] for e in log] == [e["n_refine"] for e in case["log"]]
+        assert torch.equal(init, keep) and len(att) == 5           # the caller's noise tensor is not modified
+    # without focus tokens the as-written loop equals the fused cfb_sample(preseq=...) loop
+    z_a, _ = s._diffusion_reverse_forecast(enc7, [128], pre, masks7, init_noise=init)
+    z_b, _, _ = s.sample(enc, masks, 1, init, preseq=pre)
+    assert rel_err(z_a, z_b) < 1e-4
+    # synthesize_unbounded routes windows with focus tokens through it
+    wins = [d["clip"]] * 2
+    inits = [torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(60 + k)).to(DEV) for k in range(2)]
+    plain = s.synthesize_unbounded(wins, d["uncond_text"], d["uncond_text_attn"], inits)
+    s.weg_forecast_parameters = dict(g["cases"]["forecast_big"]["params"])
+    guided = s.synthesize_unbounded(wins, d["uncond_text"], d["uncond_text_attn"], inits, focus_indices=[[[2, 5]], []])
+    assert rel_err(guided[0], plain[0]) > 1e-3 and torch.isfinite(guided[1]).all()
 
 
 def test_generate_with_focus_tokens():

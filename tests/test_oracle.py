@@ -277,7 +277,8 @@ def test_word_excitation_guidance_matches_the_reference_loop_code():
     syn = synthetic_clip(1, seed=g["clip_seed"], dyadic=True)
     enc, masks = oracle_batch(syn)
     init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(g["init_seed"]))
-    for tag, case in g["cases"].items():
+    for tag in ("update", "refine"):
+        case = g["cases"][tag]
         log = []
         z, _ = O.diffusion_reverse(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init,
                                    g["n_steps"], guidance_scale=7.5, focus_indices=case["focus"], weg=case["params"],
@@ -289,3 +290,17 @@ def test_word_excitation_guidance_matches_the_reference_loop_code():
         assert [e["n_refine"] for e in log] == [e["n_refine"] for e in case["log"]]
     k = O.weg_gaussian_kernel()
     assert abs(float(k.sum()) - 1.0) < 1e-6 and k.shape == (1, 1, 3, 3)
+    # the same update inside diffusion_reverse_forecast (unbounded_synthesis.py:78-142), with latent inpainting
+    for tag in ("forecast", "forecast_big"):
+        case = g["cases"][tag]
+        pre = torch.randn(1, 8, 128, generator=torch.Generator().manual_seed(case["preseq_seed"]))
+        init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(case["init_seed"]))
+        log = []
+        z, _ = O.diffusion_reverse_forecast(oracle_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED_KW),
+                                            O.DDPMSchedulerOracle(clip_sample=True, **SCHED_KW), enc, masks, init,
+                                            g["n_steps"], pre, guidance_scale=7.5, focus_indices=case["focus"],
+                                            weg=case["params"], weg_log=log)
+        err = rel_err(z.detach(), case["z"])
+        print(f"WEG[{tag}]: oracle (own denoiser) vs reference diffusion_reverse_forecast: L2 {err:.2e}")
+        assert err < 1e-3
+        assert [e["n_refine"] for e in log] == [e["n_refine"] for e in case["log"]]

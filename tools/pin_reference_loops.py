@@ -367,6 +367,40 @@ for tag, wp in (("update", {"scale_range": [1.0, 0.5], "thresholds": {}, "scale_
           f"refinement iterations {[e['n_refine'] for e in log]}, moved the result by {moved:.3f} (L2)")
     assert moved > 1e-3
     weg_out["cases"][tag] = {"z": z_ref.detach().clone(), "params": wp, "focus": focus, "log": log}
+# the same block inside diffusion_reverse_forecast (unbounded_synthesis.py:78-142: hard-coded parameters, scale factor
+# 100, so with random-init weights the update is ~1e-4 of the latents -- the bit-for-bit comparison still sees it)
+pre1 = torch.randn(1, 8, 128, generator=torch.Generator().manual_seed(79))
+model = stand_in_model(O.DDIMSchedulerOracle(clip_sample=True, **SCHED))
+model.iterative_refinement_step = types.MethodType(ref_model.Convofusion.iterative_refinement_step, model)
+torch.manual_seed(SEED + 5)
+z_ref, _ = ref_script.diffusion_reverse_forecast(model, list(enc1), lengths=[128], preseq=pre1, cond_masks=masks1,
+                                                 focus_indices=[list(f) for f in focus])
+torch.manual_seed(SEED + 5)
+init = torch.randn(1, 16, 128)
+log = []
+z_or, _ = O.diffusion_reverse_forecast(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED),
+                                       O.DDPMSchedulerOracle(clip_sample=True, **SCHED), enc1, masks1, init, N_STEPS, pre1,
+                                       guidance_scale=7.5, focus_indices=focus, weg_log=log)
+assert torch.equal(z_ref.detach(), z_or.detach()), "WEG[forecast]: oracle loop differs from the reference loop"
+with torch.no_grad():
+    z_plain, _ = O.diffusion_reverse_forecast(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED),
+                                              O.DDPMSchedulerOracle(clip_sample=True, **SCHED), enc1, masks1, init, N_STEPS,
+                                              pre1, guidance_scale=7.5)
+moved = float((z_or.detach() - z_plain).norm() / z_plain.norm())
+print(f"WEG[forecast]: oracle loop == reference diffusion_reverse_forecast (bit for bit); moved the result by {moved:.2e}")
+assert 0 < moved
+weg_out["cases"]["forecast"] = {"z": z_ref.detach().clone(), "params": dict(O.FORECAST_WEG), "focus": focus, "log": log,
+                                "preseq_seed": 79, "init_seed": SEED + 5}
+# ... and with a step size that makes the guidance matter (the oracle's loop takes the parameters as an argument)
+big = dict(O.FORECAST_WEG, scale_factor=1.0e7, thresholds={0: 0.06}, max_refinement_steps=2)
+log = []
+z_big, _ = O.diffusion_reverse_forecast(ref_denoise, O.DDIMSchedulerOracle(clip_sample=True, **SCHED),
+                                        O.DDPMSchedulerOracle(clip_sample=True, **SCHED), enc1, masks1, init, N_STEPS, pre1,
+                                        guidance_scale=7.5, focus_indices=focus, weg=big, weg_log=log)
+print(f"WEG[forecast_big]: moved the result by {float((z_big.detach() - z_plain).norm() / z_plain.norm()):.3f}; "
+      f"refinement iterations {[e['n_refine'] for e in log]}")
+weg_out["cases"]["forecast_big"] = {"z": z_big.detach().clone(), "params": big, "focus": focus, "log": log,
+                                    "preseq_seed": 79, "init_seed": SEED + 5}
 torch.save(weg_out, ROOT / "tests" / "golden" / "ref_weg.pt")
 
 path = ROOT / "tests" / "golden" / "ref_loops.pt"
