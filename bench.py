@@ -660,13 +660,24 @@ def run_ours(args):
         sampler.denoiser.step_chains = args.chains
     use_pool = [pool is not None]
 
+    trace_on = bool(os.environ.get("CFB_BENCH_TRACE"))
+    trace_ev = []
+
     def run_steps(fn, n):
         g = Gatherer(n)
+
+        def done(i, out):
+            if trace_on:                       # per-pass completion events (diagnosis of run-to-run variance)
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                trace_ev.append((i, time.perf_counter(), e))
+            g.put(i, out)
+
         if use_pool[0]:
-            pool.map(lambda i, k: fn(i, k), list(range(n)), on_result=g.put)
+            pool.map(lambda i, k: fn(i, k), list(range(n)), on_result=done, keep_results=False)
         else:
             for i in range(n):
-                g.put(i, fn(i, 0))
+                done(i, fn(i, 0))
         g.join()
 
     def timed(fn, warmup, steps, sample_clocks):
@@ -682,6 +693,8 @@ def run_ours(args):
             l0 = _lib.lib().cfb_launch_count()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            t_host0 = time.perf_counter()
+            del trace_ev[:]
             run_steps(fn, steps)
             e1.record()
             torch.cuda.synchronize()
@@ -689,6 +702,10 @@ def run_ours(args):
                 dist.barrier()
                 torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
+            if trace_on and rank == 0:
+                rows = sorted((e0.elapsed_time(e), i, (th - t_host0) * 1e3) for i, th, e in trace_ev)
+                sys.stderr.write(f"[trace] {fn.__name__}: total {ms:.1f} ms; pass i: device-done ms (host-enqueued ms): " +
+                                 " ".join(f"{i}:{d:.0f}({h:.0f})" for d, i, h in rows) + "\n")
             launches = _lib.lib().cfb_launch_count() - l0
             ck = clocks.stop() if clocks else None
         per_rank_ms = None
@@ -701,7 +718,7 @@ def run_ours(args):
         return ms, launches, ck, per_rank_ms
 
     ms_dev, launches, clocks, per_rank_ms = timed(device_pass, args.warmup, n_steps, True)
-    ms_e2e, _, _, _ = timed(e2e_pass, 1, n_steps, False)
+    ms_e2e, _, _, _ = timed(e2e_pass, 2, n_steps, False)
     single = None
     if pool is not None and not args.sweep:
         use_pool[0] = False                              # one batch in flight: the latency view

@@ -62,9 +62,12 @@ class SamplerPool:
         return self._streams
 
     def map(self, fn: Callable[[Any, int], Any], items: Sequence[Any],
-            on_result: Optional[Callable[[int, Any], None]] = None) -> List[Any]:
+            on_result: Optional[Callable[[int, Any], None]] = None, keep_results: bool = True) -> List[Any]:
         """Runs fn(item, lane_index) for every item, `lanes` at a time; results in item order.  on_result(i, result)
-        is called on the lane's thread (lane stream current) as soon as item i has been enqueued.
+        is called on the lane's thread (lane stream current) as soon as item i has been enqueued.  With
+        `keep_results=False` a result is dropped once on_result has seen it (the returned list holds None): a long
+        run that keeps every pass's output alive makes the caching allocator grow, and every cudaMalloc it then issues
+        synchronises the device -- measured as ~90 ms stalls of BOTH lanes in bench.py.
 
         Inside fn the calling thread's current stream is the lane's stream and Denoiser / ConvoFusionVae calls run
         on the lane's handle.  Work already queued on the caller's current stream is visible to every lane, and the
@@ -94,9 +97,12 @@ class SamplerPool:
                             i, it = todo.get_nowait()
                         except queue.Empty:
                             return
-                        results[i] = fn(it, k)
+                        r = fn(it, k)
                         if on_result is not None:
-                            on_result(i, results[i])
+                            on_result(i, r)
+                        if keep_results:
+                            results[i] = r
+                        del r
             except BaseException as exc:      # re-raised on the calling thread
                 errors.append(exc)
 
