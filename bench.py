@@ -34,7 +34,7 @@ MEM_LEN = (32, 161, 32, 8, 1)      # spk text, lsn audio, lsn text, active-passi
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=18)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step (BASELINE.json configs[1])")
@@ -47,12 +47,12 @@ def parse():
     ap.add_argument("--sweep", type=int, default=0,
                     help="configs[4]: this many clips in total, statically sharded over the ranks in batches of --batch, "
                          "per-clip seeds 1234 + clip_id; a step is one batch of the shard and --steps is ignored")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="independent batches kept in flight on one GPU (one sampler handle + stream each); every step "
                          "is still one full pass over one batch of --batch clips, steps of different handles overlap")
     ap.add_argument("--chains", type=int, default=-1,
-                    help="concurrent chains inside every lane's captured step (-1 = SamplerPool default: 3 with lanes, "
-                         "the library default of 6 with one batch in flight)")
+                    help="concurrent chains inside every lane's captured step (-1 = SamplerPool default: 3 with two lanes, "
+                         "2 with three or more, the library default of 6 with one batch in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-the-B200 baseline")
     ap.add_argument("--no-graph", action="store_true")
@@ -745,7 +745,7 @@ def run_ours(args):
         parts = {"conditioning_ms": ev[0].elapsed_time(ev[1]), "loop_ms": ev[1].elapsed_time(ev[2]),
                  "decode_ms": ev[2].elapsed_time(ev[3])}
         if rank == 0 and args.precision == "bf16" and not args.no_roofline:
-            chains = 3 if F > 1 else 6
+            chains = 6 if F <= 1 else 3 if F == 2 else 2
             roof = gemm_roofline(torch, B, n_branch, dev, chains, lanes=max(1, F))
             roof["mem"] = memory_bound_roofline(torch, B, n_branch, dev, chains)
     if per_rank_ms:

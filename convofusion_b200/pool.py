@@ -48,7 +48,8 @@ class SamplerPool:
             raise RuntimeError("CFB_TC_2CTA=1 (cta_group::2 GEMM) is not supported with more than one lane")
         self.sampler = sampler
         self.lanes = int(lanes)
-        self.chains = int(chains) if chains is not None else (3 if lanes > 1 else 0)
+        # measured on the B200 (profiles/r02_lanes_ab.txt): 3 lanes x 2 chains 7.42 k motion-s/s, 2 x 3 7.17 k, 4 x 1 7.26 k
+        self.chains = int(chains) if chains is not None else (0 if lanes <= 1 else 3 if lanes == 2 else 2)
         self.affinity = list(affinity) if affinity else None
         self._streams: Optional[List[torch.cuda.Stream]] = None
 
