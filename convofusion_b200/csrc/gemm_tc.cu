@@ -387,8 +387,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_tma_kernel(const __grid_c
 //     reads both CTAs' shared memory), and the accumulator-ready commit is multicast the same way;
 //   * the epilogue is the TMA store / L2 reduce-add epilogue of gemm_tile, 256 columns in two passes of 128 so that the
 //     staging boxes fit in the idle 96 KB pipeline ring.
+// ONE pair CTA per SM (4-stage ring = 130 KB of shared memory): tcgen05.alloc.cta_group::2 is a collective of the pair that
+// holds each SM's allocation permit until both CTAs have joined.  With two pair CTAs co-resident per SM, pair A's CTA on
+// SM0 and pair B's CTA on SM1 can each hold their SM's permit while their peers wait for the other one -- the round-1
+// hang with two batches in flight (pairs of different kernels interleaved on one TPC).  Single-CTA kernels next to a pair
+// CTA are harmless: cta_group::1 allocations never wait for another SM.
 template <int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
                                                                   const __grid_constant__ CUtensorMap tmO, int M, int N,
                                                                   int K, Epilogue ep) {
@@ -420,6 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_pair_kernel(const __grid_
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  cluster_sync_all();                                // both CTAs of the pair are resident before either asks for tensor memory
   if (warp == 1) tmem_alloc_pair(tmem_slot, BN2);   // the same warp of both CTAs, same shared-memory slot
   tc_fence_before();
   cluster_sync_all();                                // peer barriers initialised, allocation visible
@@ -685,7 +691,7 @@ int g_tc_pair_min_rows = 0;   // env CFB_TC_2CTA_MIN_ROWS: only for GEMMs with a
 
 int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep_in,
                 cudaStream_t st) {
-  using S = Smem<128, 3>;
+  using S = Smem<128, 4>;
   CUtensorMap ta, tb, to;
   Epilogue ep = ep_in;
   CFB_TRY(get_map(A, M, K, lda, 128, &ta));
@@ -700,7 +706,7 @@ int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 2;
-  CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<3>, ta, tb, to, M, N, K, ep));
+  CFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<4>, ta, tb, to, M, N, K, ep));
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -762,7 +768,7 @@ int init_gemm_tc_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
-  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));

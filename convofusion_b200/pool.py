@@ -43,9 +43,9 @@ class SamplerPool:
         affinity[k % len]); several processes per node (one per GPU) then do not migrate over each other."""
         if lanes < 1:
             raise ValueError("lanes must be >= 1")
-        if lanes > 1 and os.environ.get("CFB_TC_2CTA", "0") not in ("", "0"):
-            # the opt-in CTA-pair GEMM is verified single-stream only; one run with two lanes never finished (DESIGN.md 5)
-            raise RuntimeError("CFB_TC_2CTA=1 (cta_group::2 GEMM) is not supported with more than one lane")
+        # (Round 1 refused the opt-in CTA-pair GEMM, CFB_TC_2CTA=1, with several lanes: one such run never finished.  Two
+        # pair CTAs per SM can deadlock on the tensor-memory allocation permits; the kernel now keeps one pair CTA per SM
+        # -- gemm_tc.cu -- and lanes + pair kernel are covered by tests/test_gpu_zz_cta_pair.py.)
         self.sampler = sampler
         self.lanes = int(lanes)
         # measured on the B200 (profiles/r02_lanes_ab.txt): 3 lanes x 2 chains 7.42 k motion-s/s, 2 x 3 7.17 k, 4 x 1 7.26 k
