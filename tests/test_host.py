@@ -194,13 +194,8 @@ def test_lane_context_and_pool_host_logic():
     assert current_lane() == 0 and seen["other"] == 0
     with pytest.raises(ValueError):
         cf.SamplerPool(None, lanes=0)
-    os.environ["CFB_TC_2CTA"] = "1"
-    try:
-        with pytest.raises(RuntimeError):
-            cf.SamplerPool(None, lanes=2)      # the opt-in CTA-pair GEMM is single-stream only
-        cf.SamplerPool(None, lanes=1)
-    finally:
-        del os.environ["CFB_TC_2CTA"]
+    assert cf.SamplerPool(None, lanes=2).chains == 3 and cf.SamplerPool(None, lanes=3).chains == 2   # measured defaults
+    assert cf.SamplerPool(None, lanes=1).chains == 0 and cf.SamplerPool(None, lanes=4, chains=1).chains == 1
     if not torch.cuda.is_available():
         pool = cf.SamplerPool(cf.ConvoFusionSampler(precision="fp32"), lanes=2)
         with pytest.raises(_lib.CfbError):
