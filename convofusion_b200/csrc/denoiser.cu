@@ -58,6 +58,10 @@ int g_rb_trace_kind = -1, g_rb_trace_layer = -1;   // debug: which program to tr
 // the CUDA-core FFMA kernel (default on: 1e-4 parity holds on both, the split is 2.4x faster at batch 16).
 // cfb_set_fp32_tensor_cores / env CFB_FP32_TC=0 selects the CUDA cores.
 int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
+// bf16 handles: LayerNorm outputs (the A operand of six of a layer's ten GEMMs) as TWO bf16 terms per value (hi + lo,
+// 16 mantissa bits) against bf16 weights: removes two thirds of the bf16 mode's trajectory error
+// for twice the MMAs of those GEMMs.  cfb_set_bf16_activation_terms / env CFB_BF16_ACT_TERMS=2; default 1.
+int g_bf16_act_terms = getenv("CFB_BF16_ACT_TERMS") ? atoi(getenv("CFB_BF16_ACT_TERMS")) : 1;
 }
 
 using namespace cfb;
@@ -92,6 +96,7 @@ struct cfb_denoiser {
   DeviceBuf split_ws;
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
+  int act_terms = 1;      // 2: bf16 LayerNorm outputs as [hi | lo] (g_bf16_act_terms at the last reserve_rows)
   int split_scheme = 0;   // g_fp32_tc - 1 at the last reserve_split (1: fp32-accurate; 2, 3: precision-study schemes)
   // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
   DeviceBuf rb_prog, rb_blk;
@@ -269,7 +274,7 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
 int build_rowblock_programs(cfb_denoiser* h, int n_batch, int n_clips, const SharedPlan& sp, bool want_att, cudaStream_t st) {
   h->rb_mask = 0;
   const int R = n_batch * h->ntok;
-  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT || g_rowblock == 0 || R % 128 != 0 || h->d != 512 ||
+  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT || g_rowblock == 0 || h->act_terms == 2 || R % 128 != 0 || h->d != 512 ||
       h->ff % 512 != 0 || h->ntok != 16)
     return CFB_OK;
   int mask = g_rowblock & 5;
@@ -390,10 +395,13 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   if (!aux) aux = &no_aux;
   const int R = n_batch * h->ntok, d = h->d, row0 = b0 * h->ntok, R_total = n_batch_total * h->ntok;
   const int tb = sizeof(T) == 2;
+  // at = 2: LayerNorm outputs are written as [hi | lo] per 64 columns (row stride 2 d) and the GEMMs they feed read both
+  // terms; every other producer of `a` (self-attention) keeps the dense [R, d] layout inside the same buffer
+  const int at = (tb && h->act_terms == 2) ? 2 : 1;
   float* hres = h->h.as<float>() + (size_t)row0 * d;
   T* a_abs = h->a.as<T>();
   T* qx_abs = h->qx.as<T>();
-  T* a = a_abs + (size_t)row0 * d;
+  T* a = a_abs + (size_t)row0 * d * at;
   T* qkv = h->qkv.as<T>() + (size_t)row0 * 3 * d;
   T* qx = qx_abs + (size_t)row0 * CFB_N_STREAMS * d;
   T* f = h->f.as<T>() + (size_t)row0 * h->ff;
@@ -410,7 +418,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1;      // every caller passes a = LayerNorm(h)
-    return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
+    ep.a_terms = at;
+    return gemm(A, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
   };
   // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
   // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
@@ -419,11 +428,12 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
                         const float* mod, int a_ln = 0) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_ln;
-    CFB_TRY(gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st));
-    CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st));
+    ep.a_terms = a_ln ? at : 1;
+    CFB_TRY(gemm(A, tb, (a_ln ? at : 1) * K, W, tb, K, R, d, K, 0, ep, st));
+    CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st, at));
     return (int)CFB_OK;
   };
-  CFB_TRY(ln_rows<T>(hres, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln_rows<T>(hres, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr, nullptr, 0, a, R, d, st, at));
   for (int l = 0; l < h->L; ++l) {
     const cfb_denoiser_layer& w = h->layers[l];
     const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
@@ -472,7 +482,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           for (int z = 0; z < ng; ++z)
             gq[z] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
                             grp[z].lo, grp[z].rows};
-          CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, sc));
+          eq.a_terms = at;
+          CFB_TRY(gemm_tc_grouped(gq, ng, R_total, at * d, d, d, d, eq, sc));
         } else {
           for (int z = 0; z < ng; ++z) {
             Epilogue e1 = eq; e1.bias = w.b_qx + grp[z].x * d;
@@ -516,7 +527,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
       es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 1;   // keys Z change every step: this chain's W slot
-      CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
+      es.a_terms = at;
+      CFB_TRY(gemm(a, tb, at * d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
         sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
@@ -533,7 +545,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         ey.split = scm;
         CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
         CFB_TRY(cond_fuser());
-        CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st));
+        CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st, at));
       }
       shared_done = true;
     }
@@ -555,8 +567,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
-  ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1;
-  return gemm(a, tb, d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
+  ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1; ep.a_terms = at;
+  return gemm(a, tb, at * d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
 }
 
 // time embedding + TimeBlock (scale|shift) tables for S timesteps already in h->tsteps (float)
@@ -578,8 +590,9 @@ int prep_time(cfb_denoiser* h, int S, cudaStream_t st) {
 
 int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   const size_t R = (size_t)n_batch * h->ntok, es = h->prec == CFB_BF16 ? 2 : 4, d = h->d;
+  h->act_terms = (h->prec == CFB_BF16 && g_bf16_act_terms == 2 && g_gemm_backend != CFB_GEMM_SIMT) ? 2 : 1;
   CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
-  CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
+  CFB_TRY(h->a.reserve(R * d * es * h->act_terms, &h->epoch));
   CFB_TRY(h->qkv.reserve(R * 3 * d * es, &h->epoch));
   CFB_TRY(h->qx.reserve(R * CFB_N_STREAMS * d * es, &h->epoch));
   CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
@@ -832,6 +845,12 @@ int cfb_set_rowblock(int mask) {
 int cfb_set_fp32_tensor_cores(int mode) {
   CFB_CHECK(mode >= 0 && mode <= 4, "cfb_set_fp32_tensor_cores: mode %d outside 0..4", mode);
   g_fp32_tc = mode;
+  return CFB_OK;
+}
+
+int cfb_set_bf16_activation_terms(int terms) {
+  CFB_CHECK(terms == 1 || terms == 2, "cfb_set_bf16_activation_terms: %d (1 or 2)", terms);
+  g_bf16_act_terms = terms;
   return CFB_OK;
 }
 
@@ -1172,7 +1191,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0); key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_terms; key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

@@ -45,11 +45,11 @@ __device__ __forceinline__ void trace(int slot) {
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A2 = false>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (A2 ? 2 : 1) * A_BYTES + B_BYTES;   // A2: the hi and the lo tile of the A operand
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int STATS_OFF = BAR_OFF + 128;                             // BN bias floats
   static constexpr int TOTAL = BAR_OFF + 128 + 1024 + 1024;                   // barriers, bias, alignment slack
@@ -61,11 +61,14 @@ struct Smem {
 // Variants that were measured slower on this workload and removed in round 2 (DESIGN.md 5.1 keeps the numbers): cluster
 // TMA multicast of the operands, a 2-stage ring with three CTAs per SM, and three ways of running the following
 // LayerNorm inside this kernel (last-arriving CTA, 4-CTA cluster over DSMEM, a spin-waiting tail).
-template <int BN, int STAGES, bool TMA_ONLY = false>
+// A2: the A operand carries TWO bf16 terms per value (hi + lo: activations at 16 mantissa bits),
+// stored as [hi(64) | lo(64)] per 64 columns (row stride 2 K): a stage holds both tiles and one W tile, and every K step
+// issues two accumulating MMAs (hi . w + lo . w) -- twice the MMAs on an idle tensor pipe, +50 % operand bytes.
+template <int BN, int STAGES, bool TMA_ONLY = false, bool A2 = false>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const CUtensorMap* tmO_p, const int m0,
                                           const int M /* first row NOT to store */, const int n0, const int N,
                                           const int K, const Epilogue& ep) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, A2>;
   const CUtensorMap& tmA = *tmA_p;
   const CUtensorMap& tmB = *tmB_p;
   extern __shared__ uint8_t smem_raw[];
@@ -105,9 +108,10 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_empty + s * 8, ph ^ 1);
-        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + (A2 ? 2 : 1) * S::A_BYTES;
         mbar_expect_tx(bar_full + s * 8, S::STAGE_BYTES);
-        tma_load_2d(sa, &tmA, kb * BK, m0, bar_full + s * 8);
+        tma_load_2d(sa, &tmA, (A2 ? 2 * kb : kb) * BK, m0, bar_full + s * 8);
+        if constexpr (A2) tma_load_2d(sa + S::A_BYTES, &tmA, (2 * kb + 1) * BK, m0, bar_full + s * 8);
         tma_load_2d(sb, &tmB, kb * BK, n0, bar_full + s * 8);
         if (kb == 0) trace(2);
       }
@@ -122,12 +126,14 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
         mbar_wait(bar_full + s * 8, ph);
         tc_fence_after();
         if (kb == 0) trace(4);
-        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + S::A_BYTES;
+        const uint32_t sa = base + s * S::STAGE_BYTES, sb = sa + (A2 ? 2 : 1) * S::A_BYTES;
         const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (addr >> 4) field
           umma_bf16(tmem_acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          if constexpr (A2)
+            umma_bf16(tmem_acc, make_smem_desc(sa + S::A_BYTES) + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
         }
         umma_commit(bar_empty + s * 8);   // frees the smem slot once these MMAs retire
       }
@@ -367,12 +373,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
 
 // TMA-epilogue-only instantiation: no staged ld/st epilogue in the binary (116 registers, 2 CTAs per SM): the phases
 // of co-resident CTAs (prologue, operand latency, main loop, epilogue) overlap on one SM.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A2 = false>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO, int M, int N,
                                                                int K, Epilogue ep) {
-  gemm_tile<BN, STAGES, true>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, true, A2>(&tmA, &tmB, &tmO, blockIdx.y * BM, M, blockIdx.x * BN, N, K, ep);
 }
 
 // ---------------------------------------------------------------- cta_group::2: 256 x 256 tile per CTA pair
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_kernel(const __gr
   gemm_tile<BN, STAGES>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A2 = false>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_tma_kernel(const __grid_constant__ GroupedArgs g, int N,
                                                                           int K, Epilogue ep) {
   const int z = blockIdx.z;
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_grouped_tma_kernel(const 
   if (m0 >= m_end) return;
   ep.bias = g.bias[z];
   ep.out = g.out[z];
-  gemm_tile<BN, STAGES, true>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
+  gemm_tile<BN, STAGES, true, A2>(&g.tmA[z], &g.tmB[z], &g.tmO[z], m0, m_end, blockIdx.x * BN, N, K, ep);
 }
 
 // ---------------------------------------------------------------- host side
@@ -686,6 +692,23 @@ int launch(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, in
   return CFB_OK;
 }
 
+// A operand with two bf16 terms per value ([hi | lo] per 64 columns, row stride lda >= 2 K): TMA epilogue only.
+template <int BN, int STAGES>
+int launch_a2(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int M, int N, int K, const Epilogue& ep_in,
+              cudaStream_t st) {
+  using S = Smem<BN, STAGES, true>;
+  CUtensorMap ta, tb, to;
+  Epilogue ep = ep_in;
+  CFB_TRY(get_map(A, M, 2 * K, lda, BM, &ta));
+  CFB_TRY(get_map(W, w_rows, K, ldw, BN, &tb));
+  ep.tma_out = 1;
+  CFB_TRY(get_map(ep.out, M, N, ep.ldo, 32, &to, ep.out_bf16 ? MAP_OUT_BF16 : MAP_OUT_F32));
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  launch_k(gemm_tc_tma_kernel<BN, STAGES, true>, grid, NTHREADS, S::TOTAL, st, ta, tb, to, M, N, K, ep);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
 int g_tc_pair = 0;            // env CFB_TC_2CTA: 1 = cta_group::2 256x256 tiles for N % 256 == 0
 int g_tc_pair_min_rows = 0;   // env CFB_TC_2CTA_MIN_ROWS: only for GEMMs with at least this many rows
 
@@ -711,17 +734,18 @@ int launch_pair(const bf16* A, int lda, const bf16* W, int ldw, int w_rows, int 
   return CFB_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool A2 = false>
 int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int lda, int ldw, int N, int K,
                    const Epilogue& ep_in, cudaStream_t st) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, A2>;
   GroupedArgs g;
   memset(&g, 0, sizeof(g));
   Epilogue ep = ep_in;
   ep.tma_out = tma_epilogue_ok(ep, BN);
+  if (A2) CFB_CHECK(ep.tma_out && lda >= 2 * K, "gemm_tc_grouped: two-term A operand needs the TMA epilogue and lda >= 2 K");
   int max_rows = 0;
   for (int z = 0; z < n_groups; ++z) {
-    CFB_TRY(get_map(groups[z].A, a_rows_total, K, lda, BM, &g.tmA[z]));
+    CFB_TRY(get_map(groups[z].A, a_rows_total, (A2 ? 2 : 1) * K, lda, BM, &g.tmA[z]));
     CFB_TRY(get_map(groups[z].W, N, K, ldw, BN, &g.tmB[z]));
     if (ep.tma_out && groups[z].rows > 0)   // rows past the group's block are clipped by the map
       CFB_TRY(get_map(groups[z].out, groups[z].row_start + groups[z].rows, N, ep.ldo, 32, &g.tmO[z],
@@ -732,10 +756,14 @@ int launch_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int ld
   }
   if (max_rows <= 0) return CFB_OK;
   dim3 grid(ceil_div(N, BN), ceil_div(max_rows, BM), n_groups);
-  if (ep.tma_out)
-    launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
-  else
-    launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  if constexpr (A2) {
+    launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES, true>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  } else {
+    if (ep.tma_out)
+      launch_k(gemm_tc_grouped_tma_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+    else
+      launch_k(gemm_tc_grouped_kernel<BN, STAGES>, grid, NTHREADS, S::TOTAL, st, g, N, K, ep);
+  }
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -774,6 +802,9 @@ int init_gemm_tc_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<32, 4>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
   CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 3>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2, true>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_tma_kernel<64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 2, true>::TOTAL));
+  CFB_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_tma_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128, 2, true>::TOTAL));
   if (dev < 64) done_mask |= 1ull << dev;
   return CFB_OK;
 }
@@ -803,6 +834,12 @@ int gemm_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K,
   CFB_CHECK((uintptr_t)ep.out % 16 == 0, "gemm_tc: output must be 16-byte aligned");
   CFB_CHECK(ep.bias == nullptr || ((uintptr_t)ep.bias % 16 == 0), "gemm_tc: bias must be 16-byte aligned");
   if (w_rows <= 0 || w_rows > N) w_rows = N;
+  if (ep.a_terms == 2) {
+    CFB_CHECK(lda >= 2 * K && N % 64 == 0 && tma_epilogue_ok(ep, N % 128 == 0 ? 128 : 64),
+              "gemm_tc: two-term A operand needs lda >= 2 K, N %% 64 == 0 and the TMA epilogue (%dx%dx%d)", M, N, K);
+    if (N % 128 == 0) return launch_a2<128, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+    return launch_a2<64, 2>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
+  }
   if (g_tc_pair && N % 256 == 0 && M >= g_tc_pair_min_rows && tma_epilogue_ok(ep, 256))
     return launch_pair(A, lda, W, ldw, w_rows, M, N, K, ep, st);
   if (N % 128 == 0) return launch<128, 3>(A, lda, W, ldw, w_rows, M, N, K, ep, st);
@@ -820,6 +857,7 @@ int gemm_tc_grouped(const TcGroup* groups, int n_groups, int a_rows_total, int l
   for (int z = 0; z < n_groups; ++z)
     CFB_CHECK(((uintptr_t)groups[z].A % 16 == 0) && ((uintptr_t)groups[z].W % 16 == 0) && ((uintptr_t)groups[z].out % 16 == 0) &&
               ((uintptr_t)groups[z].bias % 16 == 0), "gemm_tc_grouped: group %d operands must be 16-byte aligned", z);
+  if (ep.a_terms == 2) return launch_grouped<128, 2, true>(groups, n_groups, a_rows_total, lda, ldw, N, K, ep, st);
   return launch_grouped<128, 3>(groups, n_groups, a_rows_total, lda, ldw, N, K, ep, st);
 }
 

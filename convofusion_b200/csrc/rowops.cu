@@ -11,7 +11,7 @@ namespace cfb {
 namespace {
 
 // out = LN(x) * g + b  [ * (1 + scale) + shift -> SiLU ]           (cross_attention.py:437-438)
-template <typename T, int D>
+template <typename T, int D, bool SPLIT = false>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       const float* __restrict__ b, const float* __restrict__ mod,
                                                       const int* __restrict__ step_ptr, long long mod_step_stride,
@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   RowVec<D> r;
   r.load(x + (size_t)row * D, lane);
   ln_row_finish<D, sizeof(T) == 2>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
-  r.store(out + (size_t)row * D, lane);
+  if constexpr (SPLIT && sizeof(T) == 2) r.store_split(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
+  else r.store(out + (size_t)row * D, lane);
 }
 
 // mem_c[row] = cond[row] + stream_emb[x] + pe[pos]          (denoiser.py:332-353, time-independent part)
@@ -201,17 +202,23 @@ int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStre
 
 template <typename T>
 int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
-            long long mod_step_stride, T* out, int rows, int d, cudaStream_t st) {
+            long long mod_step_stride, T* out, int rows, int d, cudaStream_t st, int terms) {
   if (rows <= 0 || debug_skip(1)) return CFB_OK;
   dim3 grid(ceil_div(rows, 8));
+  if (terms == 2) {      // [hi | lo] per 64 columns, row stride 2 d (bf16 outputs of the denoiser only)
+    CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: two-term output needs bf16 and d = 512");
+    launch_k(ln_rows_kernel<T, 512, true>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  }
   if (d == 512) launch_k(ln_rows_kernel<T, 512>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
   else if (d == 128) launch_k(ln_rows_kernel<T, 128>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
   else { set_error("ln_rows: d_model %d unsupported (128 or 512)", d); return CFB_ERR_INVALID; }
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
-template int ln_rows<float>(const float*, const float*, const float*, const float*, const int*, long long, float*, int, int, cudaStream_t);
-template int ln_rows<bf16>(const float*, const float*, const float*, const float*, const int*, long long, bf16*, int, int, cudaStream_t);
+template int ln_rows<float>(const float*, const float*, const float*, const float*, const int*, long long, float*, int, int, cudaStream_t, int);
+template int ln_rows<bf16>(const float*, const float*, const float*, const float*, const int*, long long, bf16*, int, int, cudaStream_t, int);
 
 int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_STREAMS], const int len[CFB_N_STREAMS],
               const float* stream_emb, const float* pe, float* mem_c, int d, cudaStream_t st) {
