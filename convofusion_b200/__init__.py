@@ -19,14 +19,24 @@ from .writer import MotionWriter
 from .windows import slice_windows, window_spans, window_text
 
 
+ACT_SITE_QKV, ACT_SITE_TIMEBLOCK, ACT_SITE_LINEAR1, ACT_SITE_LATENT_PROJ = 1, 2, 8, 16
+
+
+def set_bf16_activation_sites(mask: int) -> None:
+    """bf16 handles: the LayerNorm outputs feeding the GEMM sites in `mask` (ACT_SITE_*) are kept as two bf16 terms per
+    value (hi + lo).  Default 16 (latent_proj only: free, 0.11 instead of 0.19 latent L2 from the fp32 reference after
+    DDIM-50); 18 adds the TimeBlock linears (0.074); 27 = every site (0.068 at 0.8x the throughput); 0 = plain bf16.
+    Process-wide (cfb_set_bf16_activation_sites)."""
+    from . import _lib
+    _lib.check(_lib.lib().cfb_set_bf16_activation_sites(int(mask)))
+
+
 def set_bf16_activation_terms(terms: int) -> None:
-    """bf16 handles: 2 keeps the LayerNorm outputs as two bf16 terms per value (hi + lo) for the six GEMMs per layer they
-    feed -- a third of the plain bf16 mode's deviation from the fp32 reference (0.068 vs 0.195 latent L2 after DDIM-50)
-    at 0.8x its throughput; 1 (default) = plain bf16 operands.  Process-wide (cfb_set_bf16_activation_terms)."""
+    """Shorthand for `set_bf16_activation_sites`: 2 = every site (27), 1 = none (0)."""
     from . import _lib
     _lib.check(_lib.lib().cfb_set_bf16_activation_terms(int(terms)))
 
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
            "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool", "MotionWriter", "slice_windows", "window_spans", "window_text",
-           "set_bf16_activation_terms"]
+           "set_bf16_activation_terms", "set_bf16_activation_sites"]

@@ -58,10 +58,13 @@ int g_rb_trace_kind = -1, g_rb_trace_layer = -1;   // debug: which program to tr
 // the CUDA-core FFMA kernel (default on: 1e-4 parity holds on both, the split is 2.4x faster at batch 16).
 // cfb_set_fp32_tensor_cores / env CFB_FP32_TC=0 selects the CUDA cores.
 int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
-// bf16 handles: LayerNorm outputs (the A operand of six of a layer's ten GEMMs) as TWO bf16 terms per value (hi + lo,
-// 16 mantissa bits) against bf16 weights: removes two thirds of the bf16 mode's trajectory error
-// for twice the MMAs of those GEMMs.  cfb_set_bf16_activation_terms / env CFB_BF16_ACT_TERMS=2; default 1.
-int g_bf16_act_terms = getenv("CFB_BF16_ACT_TERMS") ? atoi(getenv("CFB_BF16_ACT_TERMS")) : 1;
+// bf16 handles: which LayerNorm outputs are kept as TWO bf16 terms per value (hi + lo, 16 mantissa bits) for the GEMM
+// they feed (two accumulating MMAs per K step against the bf16 weights); bit mask of consumer sites: 1 qkv, 2 the two
+// TimeBlock linears, 8 linear1, 16 latent_proj.  Activation rounding is what the guidance combine amplifies (DESIGN.md
+// section 2, tools/split_sites.py): latent_proj alone (one 128-column GEMM per evaluation, free) removes 43 % of the
+// bf16 mode's deviation from fp32, latent_proj + TimeBlock linears 62 %, every site 68 %.
+// cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 16.
+int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 16;
 }
 
 using namespace cfb;
@@ -71,7 +74,7 @@ struct cfb_denoiser {
   std::vector<cfb_denoiser_layer> layers;
   int d, lat, ntok, L, H, ff, prec;
   unsigned epoch = 0;
-  DeviceBuf h, a, qkv, qx, f, xin, eps, mem_c, mem_hat, mem_hat_t, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
+  DeviceBuf h, a, a2, qkv, qx, f, xin, eps, mem_c, mem_hat, mem_hat_t, tsteps, tsin, t1, temb, tbmod, coef, step, x, inp_noise,
       preseq, slots, masks, uc, sS, sP, zall, z0all, ytall;
   // cached CUDA graph of one sampling step
   cudaGraphExec_t graph_exec = nullptr;
@@ -96,7 +99,7 @@ struct cfb_denoiser {
   DeviceBuf split_ws;
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
-  int act_terms = 1;      // 2: bf16 LayerNorm outputs as [hi | lo] (g_bf16_act_terms at the last reserve_rows)
+  int act_sites = 0;      // bf16: consumer sites whose LayerNorm input is kept as [hi | lo] in `a2` (g_bf16_act_sites)
   int split_scheme = 0;   // g_fp32_tc - 1 at the last reserve_split (1: fp32-accurate; 2, 3: precision-study schemes)
   // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
   DeviceBuf rb_prog, rb_blk;
@@ -274,7 +277,7 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
 int build_rowblock_programs(cfb_denoiser* h, int n_batch, int n_clips, const SharedPlan& sp, bool want_att, cudaStream_t st) {
   h->rb_mask = 0;
   const int R = n_batch * h->ntok;
-  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT || g_rowblock == 0 || h->act_terms == 2 || R % 128 != 0 || h->d != 512 ||
+  if (h->prec != CFB_BF16 || g_gemm_backend == CFB_GEMM_SIMT || g_rowblock == 0 || (h->act_sites & 11) != 0 || R % 128 != 0 || h->d != 512 ||
       h->ff % 512 != 0 || h->ntok != 16)
     return CFB_OK;
   int mask = g_rowblock & 5;
@@ -395,19 +398,25 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   if (!aux) aux = &no_aux;
   const int R = n_batch * h->ntok, d = h->d, row0 = b0 * h->ntok, R_total = n_batch_total * h->ntok;
   const int tb = sizeof(T) == 2;
-  // at = 2: LayerNorm outputs are written as [hi | lo] per 64 columns (row stride 2 d) and the GEMMs they feed read both
-  // terms; every other producer of `a` (self-attention) keeps the dense [R, d] layout inside the same buffer
-  const int at = (tb && h->act_terms == 2) ? 2 : 1;
+  // LayerNorm outputs whose consumer site is in `sites` go to `a2` as [hi(64) | lo(64)] per 64 columns (row stride 2 d)
+  // and that GEMM reads both terms; everything else uses the dense `a`.  Sites: 1 qkv, 2 TimeBlock linears, 8 linear1,
+  // 16 latent_proj (scores / conditional queries address `a` by absolute row and stay plain: no measurable effect).
+  const int sites = tb ? h->act_sites : 0;
+  const long long mod_stride = (long long)h->L * 2 * 2 * d;
   float* hres = h->h.as<float>() + (size_t)row0 * d;
   T* a_abs = h->a.as<T>();
   T* qx_abs = h->qx.as<T>();
-  T* a = a_abs + (size_t)row0 * d * at;
+  T* a = a_abs + (size_t)row0 * d;
+  T* a2 = sites ? h->a2.as<T>() + (size_t)row0 * 2 * d : nullptr;
+  auto ln_to = [&](int site, const float* ln_g, const float* ln_b, const float* mod) {   // LayerNorm for consumer `site`
+    return (sites & site) ? ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a2, R, d, st, 2)
+                          : ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st, 1);
+  };
   T* qkv = h->qkv.as<T>() + (size_t)row0 * 3 * d;
   T* qx = qx_abs + (size_t)row0 * CFB_N_STREAMS * d;
   T* f = h->f.as<T>() + (size_t)row0 * h->ff;
   float* eps_out = eps_out_all + (size_t)row0 * h->lat;
   ca.bs_offset = b0;
-  const long long mod_stride = (long long)h->L * 2 * 2 * d;
   // row-block kernel for the residual chains: whole 128-row blocks of a plan-driven bf16 step only
   const int rb = (sizeof(T) == 2 && use_rb && row0 % 128 == 0 && R % 128 == 0) ? h->rb_mask : 0;
   // fp32 handles with tensor cores enabled: every GEMM below runs as a three-way bf16 split (gemm_split.cu); the
@@ -415,37 +424,43 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   const SplitCtx sc_main = split_ctx(h, row0, chain, false), sc_side = split_ctx(h, row0, chain, true);
   const SplitCtx* scm = (!tb && h->fp32_tc) ? &sc_main : nullptr;
   const SplitCtx* scs = (!tb && h->fp32_tc) ? &sc_side : nullptr;
-  auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
+  // a_from_ln carries a site bit for the precision study (gemm_split scheme 3 + CFB_SPLIT_SITES): 1 qkv, 2 TimeBlock
+  // linears, 4 scores / conditional queries, 8 linear1, 16 latent_proj
+  auto lin_T = [&](int K, const void* W, const float* b, void* out, int N, int act, int site) {   // A = LayerNorm(h) for `site`
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
-    ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1;      // every caller passes a = LayerNorm(h)
+    ep.split = scm; ep.w_static = 1; ep.a_from_ln = site;
+    const int at = (sites & site) ? 2 : 1;
     ep.a_terms = at;
-    return gemm(A, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
+    return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
   };
   // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
   // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
   //  and are gone; the row-block kernel (rowblock.cu) is what fuses them now.
+  // a_site: 0 = A is not a LayerNorm output (attention / GELU / fuser operand, dense), 2 = A is the TimeBlock LayerNorm
+  // output; next_site: the consumer of the LayerNorm run here
   auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
-                        const float* mod, int a_ln = 0) {
+                        const float* mod, int a_site, int next_site) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
-    ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_ln;
-    ep.a_terms = a_ln ? at : 1;
-    CFB_TRY(gemm(A, tb, (a_ln ? at : 1) * K, W, tb, K, R, d, K, 0, ep, st));
-    CFB_TRY(ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st, at));
+    ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_site;
+    const int at = (a_site && (sites & a_site)) ? 2 : 1;
+    ep.a_terms = at;
+    CFB_TRY(gemm(at == 2 ? (const void*)a2 : A, tb, at * K, W, tb, K, R, d, K, 0, ep, st));
+    CFB_TRY(ln_to(next_site, ln_g, ln_b, mod));
     return (int)CFB_OK;
   };
-  CFB_TRY(ln_rows<T>(hres, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr, nullptr, 0, a, R, d, st, at));
+  CFB_TRY(ln_to(1, h->layers[0].ln1_g, h->layers[0].ln1_b, nullptr));
   for (int l = 0; l < h->L; ++l) {
     const cfb_denoiser_layer& w = h->layers[l];
     const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
     const float* mod2 = mod1 + 2 * d;
     // self-attention block (cross_attention.py:568-572); a = norm1(h) on entry
-    CFB_TRY(lin_T(a, d, w.w_in, w.b_in, qkv, 3 * d, 0));
+    CFB_TRY(lin_T(d, w.w_in, w.b_in, qkv, 3 * d, 0, 1));
     CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
     if (rb & 1) {   // out_proj -> time_block1 -> norm2 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
     } else {
-      CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1));          // + time_block1 prologue (:575)
-      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 1));  // + norm2 (:578)
+      CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1, 0, 2));        // + time_block1 prologue (:575)
+      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 2, 4));   // + norm2 (:578)
     }
     // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
     for (int x = 0; x < CFB_N_STREAMS; ++x)
@@ -482,14 +497,13 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           for (int z = 0; z < ng; ++z)
             gq[z] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
                             grp[z].lo, grp[z].rows};
-          eq.a_terms = at;
-          CFB_TRY(gemm_tc_grouped(gq, ng, R_total, at * d, d, d, d, eq, sc));
+          CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, sc));
         } else {
           for (int z = 0; z < ng; ++z) {
             Epilogue e1 = eq; e1.bias = w.b_qx + grp[z].x * d;
             e1.out = qx_abs + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d;
             const SplitCtx sg = split_ctx(h, grp[z].lo, chain, side);   // the group's own rows of the scratch arena
-            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1; e1.a_from_ln = 1;
+            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1; e1.a_from_ln = 4;
             CFB_TRY(gemm(a_abs + (size_t)grp[z].lo * d, 0, d, (const float*)w.w_qx + (size_t)grp[z].x * d * d, 0, d,
                          grp[z].rows, d, d, 0, e1, sc));
           }
@@ -526,9 +540,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       float* sS = h->sS.as<float>() + (size_t)row0 * sp->n_tot;
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
-      es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 1;   // keys Z change every step: this chain's W slot
-      es.a_terms = at;
-      CFB_TRY(gemm(a, tb, at * d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
+      es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 4;   // keys Z change every step: this chain's W slot
+      CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
         sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
@@ -545,30 +558,32 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         ey.split = scm;
         CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
         CFB_TRY(cond_fuser());
-        CFB_TRY(ln_rows<T>(hres, w.tb2_g, w.tb2_b, mod2, step_ptr, mod_stride, a, R, d, st, at));
+        CFB_TRY(ln_to(2, w.tb2_g, w.tb2_b, mod2));
       }
       shared_done = true;
     }
     if (!shared_done) {
-      CFB_TRY(lin_T(a, d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0));
+      CFB_TRY(lin_T(d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0, 4));
       CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
-      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2));   // + time_block2 prologue (:655)
+      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2, 0, 2));   // + time_block2 prologue (:655)
     }
-    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 1));   // + norm3 (:659)
+    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 2, 8));   // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
-    CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU));
+    CFB_TRY(lin_T(d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU, 8));
     const bool last = l + 1 == h->L;
-    if (rb & 4) {   // linear2 -> next norm1 on resident rows (rowblock.cu)
+    if ((rb & 4) && !(last && (sites & 16))) {   // linear2 -> next norm1 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 2, row0, R, R_total, step_ptr, st));
     } else {
       CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
-                         last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr));
+                         last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr, 0, last ? 16 : 1));
     }
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
-  ep.split = scm; ep.w_static = 1; ep.a_from_ln = 1; ep.a_terms = at;
-  return gemm(a, tb, at * d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
+  ep.split = scm; ep.w_static = 1; ep.a_from_ln = 16;
+  const int at = (sites & 16) ? 2 : 1;
+  ep.a_terms = at;
+  return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
 }
 
 // time embedding + TimeBlock (scale|shift) tables for S timesteps already in h->tsteps (float)
@@ -590,9 +605,10 @@ int prep_time(cfb_denoiser* h, int S, cudaStream_t st) {
 
 int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   const size_t R = (size_t)n_batch * h->ntok, es = h->prec == CFB_BF16 ? 2 : 4, d = h->d;
-  h->act_terms = (h->prec == CFB_BF16 && g_bf16_act_terms == 2 && g_gemm_backend != CFB_GEMM_SIMT) ? 2 : 1;
+  h->act_sites = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT) ? (g_bf16_act_sites & 27) : 0;
   CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
-  CFB_TRY(h->a.reserve(R * d * es * h->act_terms, &h->epoch));
+  CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
+  if (h->act_sites) CFB_TRY(h->a2.reserve(R * d * 2 * 2, &h->epoch));
   CFB_TRY(h->qkv.reserve(R * 3 * d * es, &h->epoch));
   CFB_TRY(h->qx.reserve(R * CFB_N_STREAMS * d * es, &h->epoch));
   CFB_TRY(h->f.reserve(R * h->ff * es, &h->epoch));
@@ -831,7 +847,7 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
                        &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws,
-                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2, &h->mem_hat_t};
+                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2, &h->mem_hat_t, &h->a2};
   for (DeviceBuf* b : bufs) b->release();
   split_cache_destroy(h->split_cache);
   delete h;
@@ -848,9 +864,15 @@ int cfb_set_fp32_tensor_cores(int mode) {
   return CFB_OK;
 }
 
-int cfb_set_bf16_activation_terms(int terms) {
+int cfb_set_bf16_activation_terms(int terms) {   // 2: every site, 1: none
   CFB_CHECK(terms == 1 || terms == 2, "cfb_set_bf16_activation_terms: %d (1 or 2)", terms);
-  g_bf16_act_terms = terms;
+  g_bf16_act_sites = terms == 2 ? 27 : 0;
+  return CFB_OK;
+}
+
+int cfb_set_bf16_activation_sites(int sites) {
+  CFB_CHECK(sites >= 0 && (sites & ~27) == 0, "cfb_set_bf16_activation_sites: mask %d outside {1, 2, 8, 16}", sites);
+  g_bf16_act_sites = sites;
   return CFB_OK;
 }
 
@@ -1191,7 +1213,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_terms; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_sites; key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

@@ -15,6 +15,7 @@
 // activations at two bf16 terms (hi + lo, 16 mantissa bits) against bf16-rounded weights (2 blocks per 64 columns:
 // A hi lo / W hi hi), scheme 2 rounds both operands to bf16 (1 block) -- the bf16 mode's GEMM rounding in isolation.
 #include "common.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -117,7 +118,8 @@ int gemm_split(const float* A, long long lda, const float* W, long long ldw, int
   CFB_CHECK(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "gemm_split: operands must be 16-byte aligned");
   const bf16 *As = nullptr, *Ws = nullptr;
   // scheme 3 (precision study): hi + lo activations only where the A operand is a LayerNorm output, bf16 elsewhere
-  const int scheme = sc->scheme == 3 ? (ep.a_from_ln ? 1 : 2) : sc->scheme;
+  static const int sites = getenv("CFB_SPLIT_SITES") ? atoi(getenv("CFB_SPLIT_SITES")) : 31;   // which LayerNorm-fed GEMMs
+  const int scheme = sc->scheme == 3 ? ((ep.a_from_ln & sites) ? 1 : 2) : sc->scheme;
   CFB_CHECK(scheme >= 0 && scheme < 3, "gemm_split: unknown scheme %d", scheme);
   const int nb = kBlocks[scheme];
   if (ep.a_static) {

@@ -66,11 +66,14 @@ int cfb_set_rowblock(int mask);
  * hi + lo (two bf16 terms) against bf16-rounded weights, 3 = both operands rounded to bf16 (the bf16 mode's GEMM
  * rounding with everything else in fp32).  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
 int cfb_set_fp32_tensor_cores(int mode);
-/* bf16 handles: 2 = the LayerNorm outputs (A operand of qkv, both TimeBlock linears, scores / conditional queries,
- * linear1, latent_proj -- six of a layer's ten GEMMs) are kept as TWO bf16 terms per value (hi + lo, 16 mantissa bits)
- * and those GEMMs issue two accumulating tcgen05.mma per K step; the weights stay bf16.  Removes about two thirds of
- * the bf16 mode's deviation from the fp32 reference (activation rounding is what the guidance weights amplify,
- * DESIGN.md section 2) at ~10 % of the step time.  1 (default, also env CFB_BF16_ACT_TERMS) = plain bf16 operands. */
+/* bf16 handles: which LayerNorm outputs are kept as TWO bf16 terms per value (hi + lo, 16 mantissa bits) for the GEMM
+ * they feed (that GEMM issues two accumulating tcgen05.mma per K step; the weights stay bf16).  Bit mask of consumer
+ * sites: 1 qkv, 2 both TimeBlock linears, 8 linear1, 16 latent_proj.  Activation rounding is what the guidance weights
+ * amplify: mask 16 (the default, also env CFB_BF16_ACT_SITES; one 128-column GEMM per evaluation,
+ * no measurable cost) removes ~43 % of the bf16 mode's deviation from the fp32 reference after 50 DDIM steps, 18 ~62 %,
+ * 27 (every site, ~20 % of the throughput) ~68 %; 0 = plain bf16 operands everywhere. */
+int cfb_set_bf16_activation_sites(int mask);
+/* Shorthand: 2 = every site (mask 27), 1 = none (mask 0). */
 int cfb_set_bf16_activation_terms(int terms);
 /* Per-pair cross-attention of bf16 handles (cross_attention.py:593-626: 16 queries against one clip's <= 256 memory
  * tokens): 1 = the tcgen05 / tensor-memory / TMA kernel (csrc/cross_tc.cu: both products issued transposed, queries as

@@ -1,7 +1,8 @@
-"""bf16 handles with two-term activations (`cfb_set_bf16_activation_terms(2)`): LayerNorm outputs are stored as hi + lo
-bf16 terms and the six GEMMs per layer they feed issue two accumulating tcgen05.mma per K step (gemm_tc.cu A2); the
-weights stay bf16.  tools/precision_study.py predicts a third of the plain bf16 mode's deviation from fp32 (activation
-rounding is what the -36.5 / +7.5 guidance weights amplify); checked here against the oracle and the reference golden."""
+"""bf16 handles with two-term activations (`cfb_set_bf16_activation_sites(mask)`): the LayerNorm outputs feeding the GEMM
+sites in the mask (1 qkv, 2 TimeBlock linears, 8 linear1, 16 latent_proj) are stored as hi + lo bf16 terms and those
+GEMMs issue two accumulating tcgen05.mma per K step (gemm_tc.cu A2); the weights stay bf16.  tools/precision_study.py
+and tools/split_sites.py predict the gains (activation rounding is what the -36.5 / +7.5 guidance weights amplify);
+checked here against the oracle and the reference golden.  Mask 16 is the library default."""
 import pytest
 import torch
 
@@ -34,32 +35,39 @@ def test_two_term_activations_cut_the_bf16_error():
     enc7, masks7 = expand_guidance_batch(enc, masks, 3)
     x = torch.randn(21, 16, 128, generator=torch.Generator().manual_seed(6))
     want, _ = oracle_denoise(x, 500, *oracle_batch(syn))
-    eps1, att1 = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
-    _lib.check(lib.cfb_set_bf16_activation_terms(2))
+    # the benchmarked structure (shared-slot plan, chains, graph): B = 1 DDIM-50 golden of the reference modules
+    g = golden("sample_ddim50_clip.pt")
+    syn1 = synthetic_clip(1, seed=1235, dyadic=False)
+    d1 = to_device(syn1, DEV)
+    enc_s, masks_s = s.encode_conditions(d1["clip"], d1["uncond_text"], d1["uncond_text_attn"])
+    init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(100)).to(DEV)
+    eps_default, _ = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
+    e, l = {}, {}
     try:
-        eps2, att2 = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
-        # the benchmarked structure (shared-slot plan, chains, graph): B = 1 DDIM-50 golden of the reference modules
-        g = golden("sample_ddim50_clip.pt")
-        syn1 = synthetic_clip(1, seed=1235, dyadic=False)
-        d1 = to_device(syn1, DEV)
-        enc_s, masks_s = s.encode_conditions(d1["clip"], d1["uncond_text"], d1["uncond_text_attn"])
-        init = torch.randn(1, 16, 128, generator=torch.Generator().manual_seed(100)).to(DEV)
-        _, rec2, _ = s.sample(enc_s, masks_s, 1, init, record=True)
-        _, rec2b, _ = s.sample(enc_s, masks_s, 1, init, record=True, use_graph=False)
+        for mask in (0, 16, 18, 27):
+            _lib.check(lib.cfb_set_bf16_activation_sites(mask))
+            eps, att = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
+            _, rec, _ = s.sample(enc_s, masks_s, 1, init, record=True)
+            _, rec_eager, _ = s.sample(enc_s, masks_s, 1, init, record=True, use_graph=False)
+            assert torch.equal(rec, rec_eager), mask              # graph replay == eager launches in every mode
+            for i in range(5):
+                assert float(att[i].sum(-1).sub(1).abs().max()) < 1e-4
+            e[mask] = rel_err(eps.cpu(), want)
+            l[mask] = [rel_err(rec[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
+            print(f"sites {mask:2d}: one evaluation eps L2 vs oracle {e[mask]:.2e}; DDIM-50 latents L2 vs reference golden "
+                  f"after steps 1 / 25 / 50: {l[mask][0]:.3f} {l[mask][1]:.3f} {l[mask][2]:.3f}")
+            if mask == 16:
+                assert torch.equal(eps, eps_default)              # 16 is the default; switching modes is stateless
+        assert lib.cfb_set_bf16_activation_sites(4) != 0          # scores / conditional queries are not a site
     finally:
-        _lib.check(lib.cfb_set_bf16_activation_terms(1))
-    _, rec1, _ = s.sample(enc_s, masks_s, 1, init, record=True)
-    e1, e2 = rel_err(eps1.cpu(), want), rel_err(eps2.cpu(), want)
-    l1 = [rel_err(rec1[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
-    l2 = [rel_err(rec2[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
-    print(f"one evaluation, eps L2 vs oracle: bf16 {e1:.2e}, two-term activations {e2:.2e}")
-    print(f"DDIM-50 latents L2 vs reference golden after steps 1 / 25 / 50: bf16 {l1[0]:.3f} {l1[1]:.3f} {l1[2]:.3f} | "
-          f"two-term activations {l2[0]:.3f} {l2[1]:.3f} {l2[2]:.3f}")
-    assert e2 < e1          # a single evaluation is dominated by the (branch-common) weight rounding: small gain here
-    assert l2[0] < 0.5 * l1[0] and l2[2] < 0.5 * l1[2] and l2[2] < 0.1
-    assert torch.equal(rec2, rec2b)                               # graph replay == eager launches in this mode too
-    for i in range(5):
-        assert float(att2[i].sum(-1).sub(1).abs().max()) < 1e-4
-    # switching back restores the default path bit for bit
-    eps1b, _ = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
-    assert torch.equal(eps1, eps1b)
+        _lib.check(lib.cfb_set_bf16_activation_sites(16))
+    assert e[27] < e[0]     # a single evaluation is dominated by the (branch-common) weight rounding: small gain here
+    assert l[16][2] < 0.7 * l[0][2] and l[16][0] < 0.7 * l[0][0]  # latent_proj alone (free)
+    assert l[18][2] < 0.5 * l[0][2]                               # + the TimeBlock linears
+    assert l[27][0] < 0.5 * l[0][0] and l[27][2] < 0.5 * l[0][2] and l[27][2] < 0.1
+    _lib.check(lib.cfb_set_bf16_activation_terms(2))              # shorthand: every site
+    try:
+        _, rec27, _ = s.sample(enc_s, masks_s, 1, init, record=True)
+    finally:
+        _lib.check(lib.cfb_set_bf16_activation_sites(16))
+    assert rel_err(rec27[49].cpu(), g["record"][49]) == l[27][2]
