@@ -64,6 +64,7 @@ int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
 // section 2, tools/split_sites.py): latent_proj alone (one 128-column GEMM per evaluation, free) removes 43 % of the
 // bf16 mode's deviation from fp32, latent_proj + TimeBlock linears 62 %, every site 68 %.
 // cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 16.
+bool gemm_tc_two_term_ok();   // gemm_tc.cu
 int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 16;
 }
 
@@ -605,7 +606,8 @@ int prep_time(cfb_denoiser* h, int S, cudaStream_t st) {
 
 int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   const size_t R = (size_t)n_batch * h->ntok, es = h->prec == CFB_BF16 ? 2 : 4, d = h->d;
-  h->act_sites = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT) ? (g_bf16_act_sites & 27) : 0;
+  // (the two-term GEMM variant exists for the TMA-epilogue kernel only: plain operands with CFB_TC_TMA_EPI=0)
+  h->act_sites = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && gemm_tc_two_term_ok()) ? (g_bf16_act_sites & 27) : 0;
   CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
   CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
   if (h->act_sites) CFB_TRY(h->a2.reserve(R * d * 2 * 2, &h->epoch));

@@ -776,6 +776,9 @@ int tc_get_map(const void* p, int rows, int cols, int ld, int box_rows, CUtensor
   return get_map(p, rows, cols, ld, box_rows, out, kind);
 }
 
+// the two-term A operand (Epilogue::a_terms == 2) is implemented by the TMA-epilogue kernels only
+bool gemm_tc_two_term_ok() { return g_tc_tma_epi != 0; }
+
 int tc_trace_read(unsigned long long out[16]) {
   CFB_CUDA(cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 16));
   return CFB_OK;
