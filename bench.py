@@ -305,6 +305,9 @@ def assemble_line(args, *, world, B, F, n_branch, ms_dev, ms_e2e, launches, cloc
         "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
         "config": workload_config(args, B),
         "execution": {"guidance_branches_evaluated": n_branch, "batches_in_flight": F, "chains": getattr(args, "chains", -1),
+                      "operands": ("16-bit GEMM / attention operands (bf16; LayerNorm outputs as fp16 unless CFB_BF16_ACT_F16=0), "
+                                   "fp32 accumulation, residual, LayerNorm, softmax, guidance, scheduler")
+                      if args.precision == "bf16" else "fp32 (three-way bf16 split on the tensor cores unless CFB_FP32_TC=0)",
                       "in_flight": ("every step is one full pass over its own batch of %d clips; %d independent batches "
                                     "overlap on the GPU (SamplerPool lanes), see one_batch_in_flight for the latency view"
                                     % (B, F)) if F > 1 else "one batch at a time"},

@@ -24,11 +24,19 @@ ACT_SITE_QKV, ACT_SITE_TIMEBLOCK, ACT_SITE_LINEAR1, ACT_SITE_LATENT_PROJ = 1, 2,
 
 def set_bf16_activation_sites(mask: int) -> None:
     """bf16 handles: the LayerNorm outputs feeding the GEMM sites in `mask` (ACT_SITE_*) are kept as two bf16 terms per
-    value (hi + lo).  Default 16 (latent_proj only: free, 0.11 instead of 0.19 latent L2 from the fp32 reference after
-    DDIM-50); 18 adds the TimeBlock linears (0.074); 27 = every site (0.068 at 0.8x the throughput); 0 = plain bf16.
+    value (hi + lo, two MMAs per K step).  Default 0: the fp16 form (`set_bf16_activation_f16`) covers the same sites for
+    free; 16 adds a little (0.078 vs 0.084 latent L2 from the fp32 reference after DDIM-50, -0.8 % throughput).
     Process-wide (cfb_set_bf16_activation_sites)."""
     from . import _lib
     _lib.check(_lib.lib().cfb_set_bf16_activation_sites(int(mask)))
+
+
+def set_bf16_activation_f16(enabled: bool) -> None:
+    """bf16 handles: LayerNorm outputs as fp16 (default on: 0.084 instead of 0.195 latent L2 from the fp32 reference
+    after DDIM-50, same throughput) or bf16 operands of the GEMMs they feed; process-wide
+    (cfb_set_bf16_activation_f16)."""
+    from . import _lib
+    _lib.check(_lib.lib().cfb_set_bf16_activation_f16(int(bool(enabled))))
 
 
 def set_bf16_activation_terms(terms: int) -> None:
@@ -39,4 +47,4 @@ def set_bf16_activation_terms(terms: int) -> None:
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
            "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool", "MotionWriter", "slice_windows", "window_spans", "window_text",
-           "set_bf16_activation_terms", "set_bf16_activation_sites"]
+           "set_bf16_activation_terms", "set_bf16_activation_sites", "set_bf16_activation_f16"]

@@ -165,6 +165,7 @@ struct Epilogue {
   int a_static, w_static;    // the operand is a weight (its split is cached) rather than an activation
   int a_from_ln;             // precision study (scheme 3): the A operand is a LayerNorm output
   int a_terms;               // bf16 A operand with 2 terms per value ([hi | lo] per 64 columns, lda >= 2 K); 0 / 1 = plain
+  int ab_f16;                // both 16-bit operands hold fp16, not bf16, values (tcgen05 path only; kind::f16 does not mix)
 };
 
 // GEMM entry points (gemm_simt.cu / gemm_tc.cu). A [M,K] and W [N,K] are K-contiguous.

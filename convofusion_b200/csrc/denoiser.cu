@@ -63,9 +63,19 @@ int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
 // TimeBlock linears, 8 linear1, 16 latent_proj.  Activation rounding is what the guidance combine amplifies (DESIGN.md
 // section 2, tools/split_sites.py): latent_proj alone (one 128-column GEMM per evaluation, free) removes 43 % of the
 // bf16 mode's deviation from fp32, latent_proj + TimeBlock linears 62 %, every site 68 %.
-// cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 16.
+// cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 0 since the fp16 form below covers the same sites
+// for free (16 on top of it: 0.084 -> 0.078 at -0.8 % throughput).
 bool gemm_tc_two_term_ok();   // gemm_tc.cu
-int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 16;
+// bf16 handles: the LayerNorm outputs feeding qkv, the TimeBlock linears, linear1 and latent_proj are stored as fp16
+// instead of bf16 -- 11 instead of 8 significant bits for values that are O(1) by construction (clamped to the fp16
+// range anyway) -- and those GEMMs run tcgen05.mma kind::f16 on fp16 operands: the handle keeps fp16 copies of those
+// bf16 weights (an exact conversion for every weight above the fp16 subnormal range, so the weight rounding stays the
+// bf16 one, which is common to all guidance branches and cancels).  Same bytes, same MMA rate: the activation rounding
+// that the guidance weights amplify shrinks 8x at these sites at no cost.  (kind::f16 cannot mix A = f16 with B = bf16:
+// illegal instruction.)  cfb_set_bf16_activation_f16 / env CFB_BF16_ACT_F16; default 1.  Sites in g_bf16_act_sites
+// keep their two-term bf16 form.
+int g_bf16_act_f16 = getenv("CFB_BF16_ACT_F16") ? atoi(getenv("CFB_BF16_ACT_F16")) : 1;
+int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 0;
 }
 
 using namespace cfb;
@@ -100,6 +110,11 @@ struct cfb_denoiser {
   DeviceBuf split_ws;
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
+  int act_f16 = 0;        // bf16: LayerNorm outputs for the sites of F16_SITES are fp16 (g_bf16_act_f16 at the last reserve_rows)
+  struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
+  std::vector<W16> l16;
+  const bf16* w_out16 = nullptr;
+  DeviceBuf w16;
   int act_sites = 0;      // bf16: consumer sites whose LayerNorm input is kept as [hi | lo] in `a2` (g_bf16_act_sites)
   int split_scheme = 0;   // g_fp32_tc - 1 at the last reserve_split (1: fp32-accurate; 2, 3: precision-study schemes)
   // row-block programs (rowblock.cu): 3 per layer, built once per (workspace epoch, batch layout)
@@ -403,6 +418,9 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // and that GEMM reads both terms; everything else uses the dense `a`.  Sites: 1 qkv, 2 TimeBlock linears, 8 linear1,
   // 16 latent_proj (scores / conditional queries address `a` by absolute row and stay plain: no measurable effect).
   const int sites = tb ? h->act_sites : 0;
+  // fp16 LayerNorm outputs for the sites of F16_SITES (consumers: tcgen05 GEMMs on the fp16 weight copies, Epilogue::ab_f16)
+  const int f16 = (tb && h->act_f16 && !h->l16.empty()) ? 1 : 0;
+  constexpr int F16_SITES = 1 | 2 | 8 | 16;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
   float* hres = h->h.as<float>() + (size_t)row0 * d;
   T* a_abs = h->a.as<T>();
@@ -411,7 +429,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   T* a2 = sites ? h->a2.as<T>() + (size_t)row0 * 2 * d : nullptr;
   auto ln_to = [&](int site, const float* ln_g, const float* ln_b, const float* mod) {   // LayerNorm for consumer `site`
     return (sites & site) ? ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a2, R, d, st, 2)
-                          : ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st, 1);
+                          : ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st,
+                                       (f16 && (site & F16_SITES)) ? 3 : 1);
   };
   T* qkv = h->qkv.as<T>() + (size_t)row0 * 3 * d;
   T* qx = qx_abs + (size_t)row0 * CFB_N_STREAMS * d;
@@ -426,25 +445,30 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   const SplitCtx* scm = (!tb && h->fp32_tc) ? &sc_main : nullptr;
   const SplitCtx* scs = (!tb && h->fp32_tc) ? &sc_side : nullptr;
   // a_from_ln carries a site bit for the precision study (gemm_split scheme 3 + CFB_SPLIT_SITES): 1 qkv, 2 TimeBlock
-  // linears, 4 scores / conditional queries, 8 linear1, 16 latent_proj
-  auto lin_T = [&](int K, const void* W, const float* b, void* out, int N, int act, int site) {   // A = LayerNorm(h) for `site`
+  // linears, 4 scores / conditional queries, 8 linear1, 16 latent_proj; operands that are not LayerNorm outputs:
+  // 32 out_proj (self-attention output), 64 linear2 (GELU output), 128 fuser (per-pair attention output), 256 shared
+  // values (probabilities)
+  // W16: the fp16 copy of W (null: none, e.g. fp32 handles)
+  auto lin_T = [&](int K, const void* W, const void* W16, const float* b, void* out, int N, int act, int site) {   // A = LayerNorm(h) for `site`
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = site;
     const int at = (sites & site) ? 2 : 1;
-    ep.a_terms = at;
+    ep.a_terms = at; ep.ab_f16 = (at == 1 && (site & F16_SITES)) ? f16 : 0;
+    if (ep.ab_f16) W = W16;
     return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
   };
   // Residual update followed by the LayerNorm that feeds the next GEMM (optionally with TimeBlock modulation).  Three
   // ways of running that LayerNorm inside the producing GEMM were measured slower than the separate row kernel
   //  and are gone; the row-block kernel (rowblock.cu) is what fuses them now.
-  // a_site: 0 = A is not a LayerNorm output (attention / GELU / fuser operand, dense), 2 = A is the TimeBlock LayerNorm
-  // output; next_site: the consumer of the LayerNorm run here
-  auto lin_res_ln = [&](const void* A, int K, const void* W, const float* b, const float* ln_g, const float* ln_b,
-                        const float* mod, int a_site, int next_site) {
+  // a_site: 2 = A is the TimeBlock LayerNorm output, >= 32 = A is not a LayerNorm output (attention / GELU / fuser
+  // operand, always dense bf16); next_site: the consumer of the LayerNorm run here
+  auto lin_res_ln = [&](const void* A, int K, const void* W, const void* W16, const float* b, const float* ln_g,
+                        const float* ln_b, const float* mod, int a_site, int next_site) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_site;
     const int at = (a_site && (sites & a_site)) ? 2 : 1;
-    ep.a_terms = at;
+    ep.a_terms = at; ep.ab_f16 = (at == 1 && (a_site & F16_SITES)) ? f16 : 0;
+    if (ep.ab_f16) W = W16;
     CFB_TRY(gemm(at == 2 ? (const void*)a2 : A, tb, at * K, W, tb, K, R, d, K, 0, ep, st));
     CFB_TRY(ln_to(next_site, ln_g, ln_b, mod));
     return (int)CFB_OK;
@@ -455,13 +479,14 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
     const float* mod2 = mod1 + 2 * d;
     // self-attention block (cross_attention.py:568-572); a = norm1(h) on entry
-    CFB_TRY(lin_T(d, w.w_in, w.b_in, qkv, 3 * d, 0, 1));
+    const cfb_denoiser::W16 w16 = f16 ? h->l16[l] : cfb_denoiser::W16{};
+    CFB_TRY(lin_T(d, w.w_in, w16.w_in, w.b_in, qkv, 3 * d, 0, 1));
     CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
     if (rb & 1) {   // out_proj -> time_block1 -> norm2 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
     } else {
-      CFB_TRY(lin_res_ln(a, d, w.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1, 0, 2));        // + time_block1 prologue (:575)
-      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 2, 4));   // + norm2 (:578)
+      CFB_TRY(lin_res_ln(a, d, w.w_so, nullptr, w.b_so, w.tb1_g, w.tb1_b, mod1, 32, 2));              // + time_block1 prologue (:575)
+      CFB_TRY(lin_res_ln(a, d, w.w_tb1, w16.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 2, 4));       // + norm2 (:578)
     }
     // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
     for (int x = 0; x < CFB_N_STREAMS; ++x)
@@ -530,7 +555,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           for (int z = 0; z < ng; ++z) {   // one stream: sequential accumulation, overlapping row blocks are fine
             Epilogue e1 = eg; e1.out = h_abs + (size_t)grp[z].lo * d;
             const SplitCtx sg = split_ctx(h, grp[z].lo, chain, false);
-            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1;
+            e1.split = h->fp32_tc ? &sg : nullptr; e1.w_static = 1; e1.a_from_ln = 128;
             CFB_TRY(gemm(uc + (size_t)grp[z].lo * CFB_N_STREAMS * d + grp[z].x * d, 0, CFB_N_STREAMS * d,
                          (const float*)w.w_fu + grp[z].x * d, 0, CFB_N_STREAMS * d, grp[z].rows, d, d, 0, e1, st));
           }
@@ -556,7 +581,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         rb2_done = true;
       } else {
         Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-        ey.split = scm;
+        ey.split = scm; ey.a_from_ln = 256;
         CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
         CFB_TRY(cond_fuser());
         CFB_TRY(ln_to(2, w.tb2_g, w.tb2_b, mod2));
@@ -564,27 +589,28 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       shared_done = true;
     }
     if (!shared_done) {
-      CFB_TRY(lin_T(d, w.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0, 4));
+      CFB_TRY(lin_T(d, w.w_qx, nullptr, w.b_qx, qx, CFB_N_STREAMS * d, 0, 4));
       CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
-      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2, 0, 2));   // + time_block2 prologue (:655)
+      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, nullptr, w.b_fu, w.tb2_g, w.tb2_b, mod2, 128, 2));   // + time_block2 prologue (:655)
     }
-    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 2, 8));   // + norm3 (:659)
+    if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w16.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 2, 8));   // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
-    CFB_TRY(lin_T(d, w.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU, 8));
+    CFB_TRY(lin_T(d, w.w_ff1, w16.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU, 8));
     const bool last = l + 1 == h->L;
     if ((rb & 4) && !(last && (sites & 16))) {   // linear2 -> next norm1 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 2, row0, R, R_total, step_ptr, st));
     } else {
-      CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
-                         last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr, 0, last ? 16 : 1));
+      CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, nullptr, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
+                         last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr, 64, last ? 16 : 1));
     }
   }
   // latent_proj on a = decoder.norm(h) (cross_attention.py:238-239, denoiser.py:382)
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
   ep.split = scm; ep.w_static = 1; ep.a_from_ln = 16;
   const int at = (sites & 16) ? 2 : 1;
-  ep.a_terms = at;
-  return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * d, h->w.w_out, tb, d, R, h->lat, d, 0, ep, st);
+  ep.a_terms = at; ep.ab_f16 = at == 1 ? f16 : 0;
+  return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * d, ep.ab_f16 ? (const void*)h->w_out16 : h->w.w_out, tb, d,
+              R, h->lat, d, 0, ep, st);
 }
 
 // time embedding + TimeBlock (scale|shift) tables for S timesteps already in h->tsteps (float)
@@ -608,6 +634,8 @@ int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   const size_t R = (size_t)n_batch * h->ntok, es = h->prec == CFB_BF16 ? 2 : 4, d = h->d;
   // (the two-term GEMM variant exists for the TMA-epilogue kernel only: plain operands with CFB_TC_TMA_EPI=0)
   h->act_sites = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && gemm_tc_two_term_ok()) ? (g_bf16_act_sites & 27) : 0;
+  // (the row-block programs write their LayerNorm outputs as bf16)
+  h->act_f16 = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && g_bf16_act_f16 && g_rowblock == 0) ? 1 : 0;
   CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
   CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
   if (h->act_sites) CFB_TRY(h->a2.reserve(R * d * 2 * 2, &h->epoch));
@@ -821,7 +849,31 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
   int rc = init_gemm_tc_kernels();
   if (rc == CFB_OK) rc = init_attention_kernels();
   if (rc == CFB_OK) rc = init_cross_tc_kernels();
-  if (rc != CFB_OK) { delete h; return rc; }
+  // fp16 copies of the weights fed by LayerNorm outputs (g_bf16_act_f16): qkv, TimeBlock linears, linear1, latent_proj
+  if (rc == CFB_OK && h->prec == CFB_BF16) {
+    auto make16 = [&]() -> int {
+      const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = 5 * d2 + ffd, outn = (size_t)h->lat * h->d;
+      CFB_TRY(h->w16.reserve((per * h->L + outn) * 2, nullptr));
+      bf16* p = h->w16.as<bf16>();
+      auto conv = [&](const void* src, size_t n, const bf16** dst) -> int {
+        CFB_TRY(bf16_to_f16((const bf16*)src, p, n, nullptr));
+        *dst = p; p += n;
+        return CFB_OK;
+      };
+      h->l16.resize(h->L);
+      for (int l = 0; l < h->L; ++l) {
+        CFB_TRY(conv(h->layers[l].w_in, 3 * d2, &h->l16[l].w_in));
+        CFB_TRY(conv(h->layers[l].w_tb1, d2, &h->l16[l].w_tb1));
+        CFB_TRY(conv(h->layers[l].w_tb2, d2, &h->l16[l].w_tb2));
+        CFB_TRY(conv(h->layers[l].w_ff1, ffd, &h->l16[l].w_ff1));
+      }
+      CFB_TRY(conv(h->w.w_out, outn, &h->w_out16));
+      CFB_CUDA(cudaStreamSynchronize(nullptr));
+      return CFB_OK;
+    };
+    rc = make16();
+  }
+  if (rc != CFB_OK) { cfb_denoiser_destroy(h); return rc; }
   *out = h;
   return CFB_OK;
 }
@@ -849,7 +901,7 @@ void cfb_denoiser_destroy(cfb_denoiser* h) {
   DeviceBuf* bufs[] = {&h->h, &h->a, &h->qkv, &h->qx, &h->f, &h->xin, &h->eps, &h->mem_c, &h->mem_hat, &h->tsteps,
                        &h->tsin, &h->t1, &h->temb, &h->tbmod, &h->coef, &h->step, &h->x, &h->inp_noise, &h->preseq,
                        &h->slots, &h->masks, &h->uc, &h->sS, &h->sP, &h->zall, &h->z0all, &h->ytall, &h->rb_prog, &h->rb_blk, &h->split_ws,
-                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2, &h->mem_hat_t, &h->a2};
+                       &h->wg_h, &h->wg_qkv, &h->wg_z, &h->wg_p, &h->wg_g, &h->wg_t1, &h->wg_t2, &h->mem_hat_t, &h->a2, &h->w16};
   for (DeviceBuf* b : bufs) b->release();
   split_cache_destroy(h->split_cache);
   delete h;
@@ -869,6 +921,11 @@ int cfb_set_fp32_tensor_cores(int mode) {
 int cfb_set_bf16_activation_terms(int terms) {   // 2: every site, 1: none
   CFB_CHECK(terms == 1 || terms == 2, "cfb_set_bf16_activation_terms: %d (1 or 2)", terms);
   g_bf16_act_sites = terms == 2 ? 27 : 0;
+  return CFB_OK;
+}
+
+int cfb_set_bf16_activation_f16(int enabled) {
+  g_bf16_act_f16 = enabled ? 1 : 0;
   return CFB_OK;
 }
 
@@ -1215,7 +1272,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_sites; key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_sites + (h->act_f16 << 20); key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

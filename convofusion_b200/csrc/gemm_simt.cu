@@ -129,7 +129,7 @@ int gemm(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw,
     CFB_CHECK(tc_ok, "gemm: tcgen05 backend forced but shape %dx%dx%d (bf16=%d/%d) unsupported", M, N, K, a_bf16, w_bf16);
   if (tc_ok && g_gemm_backend != CFB_GEMM_SIMT)
     return gemm_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, st);
-  CFB_CHECK(ep.a_terms != 2, "gemm: a two-term A operand needs the tcgen05 path (%dx%dx%d)", M, N, K);
+  CFB_CHECK(ep.a_terms != 2 && !ep.ab_f16, "gemm: a two-term / fp16 A operand needs the tcgen05 path (%dx%dx%d)", M, N, K);
   // fp32 operands: three-way bf16 split on the tensor cores when the caller supplies the resources for it
   if (!a_bf16 && !w_bf16 && !a_act && ep.split != nullptr && !ep.out_bf16 && g_gemm_backend != CFB_GEMM_SIMT &&
       gemm_split_supported(M, N, K, lda, ldw))

@@ -119,7 +119,8 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      // bits 7 / 10 cleared = A and B hold fp16 (Epilogue::ab_f16; A = f16 with B = bf16 traps as an illegal instruction)
+      const uint32_t idesc = make_idesc(BM, BN) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc(256, BN2);
+      const uint32_t idesc = make_idesc(256, BN2) & ~(ep.ab_f16 ? ((1u << 7) | (1u << 10)) : 0u);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;

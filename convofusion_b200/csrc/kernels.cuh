@@ -8,6 +8,8 @@ namespace cfb {
 template <typename T>
 int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
             long long mod_step_stride, T* out, int rows, int d, cudaStream_t st, int terms = 1);
+// 16-bit payload conversion bf16 -> fp16 (values clamped to the fp16 range; exact above its subnormal range)
+int bf16_to_f16(const bf16* in, bf16* out, size_t n, cudaStream_t st);
 int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_STREAMS], const int len[CFB_N_STREAMS],
               const float* stream_emb, const float* pe, float* mem_c, int d, cudaStream_t st);
 template <typename T>

@@ -2,6 +2,7 @@
 // A operand, conditioning-memory construction / per-step normalisation, timestep sinusoid, casts.
 // One warp owns one row of D floats (D = 512 denoiser, 128 VAE): 128-bit loads, statistics by warp
 // shuffle, two-pass variance (mean first, then sum of squared deviations) like ATen's LayerNorm.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.cuh"
 #include "rowvec.cuh"
@@ -11,7 +12,8 @@ namespace cfb {
 namespace {
 
 // out = LN(x) * g + b  [ * (1 + scale) + shift -> SiLU ]           (cross_attention.py:437-438)
-template <typename T, int D, bool SPLIT = false>
+// OUT: 1 = T, 2 = two bf16 terms [hi | lo] (LN_OUT_SPLIT), 3 = fp16 in the bf16 buffer (LN_OUT_F16)
+template <typename T, int D, int OUT = 1>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       const float* __restrict__ b, const float* __restrict__ mod,
                                                       const int* __restrict__ step_ptr, long long mod_step_stride,
@@ -22,8 +24,14 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   RowVec<D> r;
   r.load(x + (size_t)row * D, lane);
   ln_row_finish<D, sizeof(T) == 2>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
-  if constexpr (SPLIT && sizeof(T) == 2) r.store_split(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
+  if constexpr (OUT == 2 && sizeof(T) == 2) r.store_split(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
+  else if constexpr (OUT == 3 && sizeof(T) == 2) r.store_f16(reinterpret_cast<bf16*>(out) + (size_t)row * D, lane);
   else r.store(out + (size_t)row * D, lane);
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f16_kernel(const bf16* __restrict__ in, __half* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    out[i] = __float2half_rn(fminf(fmaxf(__bfloat162float(in[i]), -65504.f), 65504.f));
 }
 
 // mem_c[row] = cond[row] + stream_emb[x] + pe[pos]          (denoiser.py:332-353, time-independent part)
@@ -200,6 +208,13 @@ int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStre
   return CFB_OK;
 }
 
+int bf16_to_f16(const bf16* in, bf16* out, size_t n, cudaStream_t st) {
+  if (n == 0) return CFB_OK;
+  bf16_to_f16_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(in, reinterpret_cast<__half*>(out), n);
+  CFB_LAUNCH_CHECK();
+  return CFB_OK;
+}
+
 template <typename T>
 int ln_rows(const float* x, const float* g, const float* b, const float* mod, const int* step_ptr,
             long long mod_step_stride, T* out, int rows, int d, cudaStream_t st, int terms) {
@@ -207,7 +222,13 @@ int ln_rows(const float* x, const float* g, const float* b, const float* mod, co
   dim3 grid(ceil_div(rows, 8));
   if (terms == 2) {      // [hi | lo] per 64 columns, row stride 2 d (bf16 outputs of the denoiser only)
     CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: two-term output needs bf16 and d = 512");
-    launch_k(ln_rows_kernel<T, 512, true>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    launch_k(ln_rows_kernel<T, 512, 2>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  }
+  if (terms == 3) {      // fp16 values in the bf16 buffer (same layout)
+    CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: fp16 output needs a 16-bit buffer and d = 512");
+    launch_k(ln_rows_kernel<T, 512, 3>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
     CFB_LAUNCH_CHECK();
     return CFB_OK;
   }

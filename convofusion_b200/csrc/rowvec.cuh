@@ -2,6 +2,7 @@
 // then the sum of squared deviations) like ATen's LayerNorm.  Shared by the row kernels (rowops.cu) and the LayerNorm
 // tail of the tcgen05 GEMM (gemm_tc.cu), so both produce bit-identical rows.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace cfb {
@@ -69,6 +70,20 @@ struct RowVec {
         uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(row + i * 128 + lane * 4) = pk;
       }
+    }
+  }
+  // fp16 instead of bf16 (11 instead of 8 significant bits; the values are LayerNorm outputs, far inside the fp16 range,
+  // and are clamped to it anyway): the A operand of a tcgen05 GEMM whose instruction descriptor says A = f16 (gemm_tc.cu).
+  __device__ __forceinline__ void store_f16(bf16* __restrict__ row, int lane) const {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = fminf(fmaxf(v[i * 4 + j], -65504.f), 65504.f);
+      __half2 a = __floats2half2_rn(c[0], c[1]);
+      __half2 b = __floats2half2_rn(c[2], c[3]);
+      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(row + i * 128 + lane * 4) = pk;
     }
   }
   // Two bf16 terms per value (hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits), laid out [hi(64) | lo(64)] per 64

@@ -66,14 +66,25 @@ int cfb_set_rowblock(int mask);
  * hi + lo (two bf16 terms) against bf16-rounded weights, 3 = both operands rounded to bf16 (the bf16 mode's GEMM
  * rounding with everything else in fp32).  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
 int cfb_set_fp32_tensor_cores(int mode);
-/* bf16 handles: which LayerNorm outputs are kept as TWO bf16 terms per value (hi + lo, 16 mantissa bits) for the GEMM
- * they feed (that GEMM issues two accumulating tcgen05.mma per K step; the weights stay bf16).  Bit mask of consumer
- * sites: 1 qkv, 2 both TimeBlock linears, 8 linear1, 16 latent_proj.  Activation rounding is what the guidance weights
- * amplify: mask 16 (the default, also env CFB_BF16_ACT_SITES; one 128-column GEMM per evaluation,
- * no measurable cost) removes ~43 % of the bf16 mode's deviation from the fp32 reference after 50 DDIM steps, 18 ~62 %,
- * 27 (every site, ~20 % of the throughput) ~68 %; 0 = plain bf16 operands everywhere. */
+/* bf16 handles, activation precision at the GEMMs fed by a LayerNorm.  Activation rounding is what the guidance
+ * weights (-36.5 / +7.5) amplify; weight rounding is common to all branches and cancels.
+ *
+ * cfb_set_bf16_activation_f16: 1 (default, also env CFB_BF16_ACT_F16) = the LayerNorm outputs feeding qkv, both
+ * TimeBlock linears, linear1 and latent_proj are stored as fp16 instead of bf16 (11 instead of 8 significant bits; the
+ * values are O(1) by construction and clamped to the fp16 range) and those GEMMs run tcgen05.mma kind::f16 on fp16
+ * operands -- the handle keeps fp16 copies of those bf16 weights (exact conversion above the fp16 subnormal range).
+ * Same bytes, same MMA rate: DDIM-50 deviation from the fp32 reference 0.195 -> 0.084 at unchanged throughput.
+ * 0 = bf16 activations everywhere (round-1 behaviour).
+ *
+ * cfb_set_bf16_activation_sites: bit mask of consumer sites (1 qkv, 2 both TimeBlock linears, 8 linear1, 16
+ * latent_proj) whose LayerNorm input is kept as TWO bf16 terms per value (hi + lo, 16 significant bits); that GEMM
+ * issues two accumulating tcgen05.mma per K step against the bf16 weights.  Default 0 (also env CFB_BF16_ACT_SITES):
+ * on top of the fp16 form the gain is small (16: 0.078 at -0.8 % throughput; 27: 0.078 at -17 %); with fp16 off:
+ * 16 -> 0.117, 18 -> 0.076, 27 -> 0.078.
+ *
+ * cfb_set_bf16_activation_terms: shorthand, 2 = every site (mask 27), 1 = none (mask 0). */
+int cfb_set_bf16_activation_f16(int enabled);
 int cfb_set_bf16_activation_sites(int mask);
-/* Shorthand: 2 = every site (mask 27), 1 = none (mask 0). */
 int cfb_set_bf16_activation_terms(int terms);
 /* Per-pair cross-attention of bf16 handles (cross_attention.py:593-626: 16 queries against one clip's <= 256 memory
  * tokens): 1 = the tcgen05 / tensor-memory / TMA kernel (csrc/cross_tc.cu: both products issued transposed, queries as

@@ -14,6 +14,7 @@ from helpers import SCHED_KW, golden, oracle_batch, oracle_denoise, rel_err, sta
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+DEFAULT = (1, 0)   # library defaults: (cfb_set_bf16_activation_f16, cfb_set_bf16_activation_sites)
 
 
 def sampler(steps):
@@ -44,30 +45,38 @@ def test_two_term_activations_cut_the_bf16_error():
     eps_default, _ = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
     e, l = {}, {}
     try:
-        for mask in (0, 16, 18, 27):
+        for f16, mask in ((0, 0), (1, 0), (0, 16), (1, 16), (1, 18), (0, 27), (1, 27)):
+            _lib.check(lib.cfb_set_bf16_activation_f16(f16))
             _lib.check(lib.cfb_set_bf16_activation_sites(mask))
             eps, att = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
             _, rec, _ = s.sample(enc_s, masks_s, 1, init, record=True)
             _, rec_eager, _ = s.sample(enc_s, masks_s, 1, init, record=True, use_graph=False)
-            assert torch.equal(rec, rec_eager), mask              # graph replay == eager launches in every mode
+            assert torch.equal(rec, rec_eager), (f16, mask)       # graph replay == eager launches in every mode
             for i in range(5):
                 assert float(att[i].sum(-1).sub(1).abs().max()) < 1e-4
-            e[mask] = rel_err(eps.cpu(), want)
-            l[mask] = [rel_err(rec[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
-            print(f"sites {mask:2d}: one evaluation eps L2 vs oracle {e[mask]:.2e}; DDIM-50 latents L2 vs reference golden "
-                  f"after steps 1 / 25 / 50: {l[mask][0]:.3f} {l[mask][1]:.3f} {l[mask][2]:.3f}")
-            if mask == 16:
-                assert torch.equal(eps, eps_default)              # 16 is the default; switching modes is stateless
-        assert lib.cfb_set_bf16_activation_sites(4) != 0          # scores / conditional queries are not a site
+            k = (f16, mask)
+            e[k] = rel_err(eps.cpu(), want)
+            l[k] = [rel_err(rec[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
+            print(f"LayerNorm outputs {'fp16' if f16 else 'bf16'}, two-term sites {mask:2d}: one evaluation eps L2 vs oracle "
+                  f"{e[k]:.2e}; DDIM-50 latents L2 vs reference golden after steps 1 / 25 / 50: "
+                  f"{l[k][0]:.3f} {l[k][1]:.3f} {l[k][2]:.3f}")
+            if k == DEFAULT:
+                assert torch.equal(eps, eps_default)              # the library default; switching modes is stateless
+        assert lib.cfb_set_bf16_activation_sites(4) != 0          # scores / conditional queries are not a two-term site
     finally:
-        _lib.check(lib.cfb_set_bf16_activation_sites(16))
-    assert e[27] < e[0]     # a single evaluation is dominated by the (branch-common) weight rounding: small gain here
-    assert l[16][2] < 0.7 * l[0][2] and l[16][0] < 0.7 * l[0][0]  # latent_proj alone (free)
-    assert l[18][2] < 0.5 * l[0][2]                               # + the TimeBlock linears
-    assert l[27][0] < 0.5 * l[0][0] and l[27][2] < 0.5 * l[0][2] and l[27][2] < 0.1
+        _lib.check(lib.cfb_set_bf16_activation_f16(DEFAULT[0]))
+        _lib.check(lib.cfb_set_bf16_activation_sites(DEFAULT[1]))
+    plain = l[(0, 0)]
+    assert e[(0, 27)] < e[(0, 0)]   # a single evaluation is dominated by the (branch-common) weight rounding: small gain
+    assert l[(0, 16)][2] < 0.7 * plain[2] and l[(0, 16)][0] < 0.7 * plain[0]   # latent_proj alone
+    assert l[(0, 27)][0] < 0.5 * plain[0] and l[(0, 27)][2] < 0.5 * plain[2] and l[(0, 27)][2] < 0.1
+    # fp16 LayerNorm outputs: every LayerNorm-fed site at 11 bits for free
+    assert l[(1, 0)][0] < 0.5 * plain[0] and l[(1, 0)][2] < 0.5 * plain[2] and l[(1, 0)][2] < 0.1
     _lib.check(lib.cfb_set_bf16_activation_terms(2))              # shorthand: every site
+    _lib.check(lib.cfb_set_bf16_activation_f16(0))
     try:
         _, rec27, _ = s.sample(enc_s, masks_s, 1, init, record=True)
     finally:
-        _lib.check(lib.cfb_set_bf16_activation_sites(16))
-    assert rel_err(rec27[49].cpu(), g["record"][49]) == l[27][2]
+        _lib.check(lib.cfb_set_bf16_activation_f16(DEFAULT[0]))
+        _lib.check(lib.cfb_set_bf16_activation_sites(DEFAULT[1]))
+    assert rel_err(rec27[49].cpu(), g["record"][49]) == l[(0, 27)][2]

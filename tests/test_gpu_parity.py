@@ -17,14 +17,15 @@ from helpers import SCHED_KW, frac_within, golden, max_rel, oracle_batch, oracle
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# bf16 mode: operands of every GEMM and the attention memory are bf16 (8 mantissa bits, ~4e-3 per rounding);
+# bf16 mode: operands of every GEMM and the attention memory are 16-bit -- bf16 (8 significant bits, ~4e-3 per rounding)
+# except the LayerNorm outputs, which feed their GEMMs as fp16 (11 bits, cfb_set_bf16_activation_f16, default on);
 # residual stream, LayerNorm statistics, softmax, guidance combine and scheduler stay fp32.  Measured on the B200
-# (round 2): one denoiser evaluation 4.2e-3 relative L2; the -36.5/+7.5 guidance weights amplify branch-differential
-# rounding and random-init weights make the trajectory chaotic, so over 50 DDIM steps the latents drift to 0.16-0.20
-# relative L2 (0.05-0.06 after the first step) with >= 58 % of the elements within 5e-2 of the tensor scale at every
-# step and >= 90 % within 0.3 of it, and the decoded joints land within 2.5e-2 max-relative.  Every entry is at most
-# 2x its measured value.
-BF16_TOL = {"eps_l2": 8e-3, "latent_frac_tol": 5e-2, "latent_frac": 0.5, "latent_l2": 0.3, "joints": 5e-2,
+# (round 2, profiles/r02_pytest_gpu_full.log): one denoiser evaluation 3.2-3.5e-3 relative L2; the -36.5/+7.5 guidance
+# weights amplify branch-differential rounding and random-init weights make the trajectory chaotic, so over 50 DDIM
+# steps the latents drift to 0.085 relative L2 (0.024 after the first step; 0.195 / 0.060 with bf16 LayerNorm outputs)
+# with >= 89 % of the elements within 5e-2 of the tensor scale at every step, and the decoded joints land within
+# 1.6e-2 max-relative.  Every entry is at most 2x its measured value.
+BF16_TOL = {"eps_l2": 7e-3, "latent_frac_tol": 5e-2, "latent_frac": 0.8, "latent_l2": 0.17, "joints": 3.2e-2,
             "latent_frac90_tol": 0.3}
 
 _samplers = {}

@@ -47,6 +47,8 @@ def run(B=8, steps=2, dyadic=True, masks=(1, 2, 4, 7), scale=1.0, dev="cuda:0", 
     lib = _lib.lib()
     try:
         _lib.check(lib.cfb_set_rowblock(0))
+        # the row-block programs write bf16 LayerNorm outputs: compare with the operator path in the same format
+        _lib.check(lib.cfb_set_bf16_activation_f16(0))
         _, base, _ = sb.sample(enc, masks_, B, init, record=True, spk_is_uncond=mono)
         torch.cuda.synchronize()
         res["operator_vs_fp32"] = (rel(base[0], ref32[0]), rel(base[-1], ref32[-1]))
@@ -62,6 +64,7 @@ def run(B=8, steps=2, dyadic=True, masks=(1, 2, 4, 7), scale=1.0, dev="cuda:0", 
         raise
     finally:
         lib.cfb_set_rowblock(0)
+        lib.cfb_set_bf16_activation_f16(1)
     if verbose:
         print(f"B={B} steps={steps} dyadic={dyadic} guidance_scale={scale}")
         print(f"  operator path vs fp32: first {res['operator_vs_fp32'][0]:.3e} last {res['operator_vs_fp32'][1]:.3e}")
