@@ -24,19 +24,22 @@ ACT_SITE_QKV, ACT_SITE_TIMEBLOCK, ACT_SITE_LINEAR1, ACT_SITE_LATENT_PROJ = 1, 2,
 
 def set_bf16_activation_sites(mask: int) -> None:
     """bf16 handles: the LayerNorm outputs feeding the GEMM sites in `mask` (ACT_SITE_*) are kept as two bf16 terms per
-    value (hi + lo, two MMAs per K step).  Default 0: the fp16 form (`set_bf16_activation_f16`) covers the same sites for
-    free; 16 adds a little (0.078 vs 0.084 latent L2 from the fp32 reference after DDIM-50, -0.8 % throughput).
+    value (hi + lo, two MMAs per K step).  Default 16 (latent_proj, whose output is eps itself: 0.017 instead of 0.028
+    latent L2 from the fp32 reference after DDIM-50 for -0.8 % throughput); 0 = none.
     Process-wide (cfb_set_bf16_activation_sites)."""
     from . import _lib
     _lib.check(_lib.lib().cfb_set_bf16_activation_sites(int(mask)))
 
 
-def set_bf16_activation_f16(enabled: bool) -> None:
-    """bf16 handles: LayerNorm outputs as fp16 (default on: 0.084 instead of 0.195 latent L2 from the fp32 reference
-    after DDIM-50, same throughput) or bf16 operands of the GEMMs they feed; process-wide
-    (cfb_set_bf16_activation_f16)."""
+def set_bf16_activation_f16(enabled) -> None:
+    """bf16 handles: which 16-bit activation operands are kept as fp16 (11 significant bits) instead of bf16 (8) and fed
+    to fp16 x fp16 tensor-core products -- same bytes, same speed.  True (default) = every group, False = none (bf16
+    everywhere, the round-1 behaviour), or a bit mask: 1 LayerNorm outputs, 2 shared-slot probabilities / values and the
+    per-pair attention output, 4 norm2 output / per-step keys, 8 self-attention q / k / v, 16 per-pair attention operands.
+    Process-wide (cfb_set_bf16_activation_f16)."""
     from . import _lib
-    _lib.check(_lib.lib().cfb_set_bf16_activation_f16(int(bool(enabled))))
+    mask = (31 if enabled else 0) if isinstance(enabled, bool) else int(enabled)
+    _lib.check(_lib.lib().cfb_set_bf16_activation_f16(mask))
 
 
 def set_bf16_activation_terms(terms: int) -> None:

@@ -6,6 +6,7 @@
 //    already carries W_k (qx = A_x norm2(tgt) + a_x), keys AND values are the affine-free
 //    normalised memory rows, so one block per (batch entry, stream) computes
 //    softmax(qx . mem_hat^T) . mem_hat over head_dim = d_model = 512.
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.cuh"
 #include <cstdlib>
@@ -87,6 +88,11 @@ __device__ __forceinline__ void load_row16(const T* __restrict__ row, int lane, 
     if constexpr (sizeof(T) == 4) {
       float4 t = *reinterpret_cast<const float4*>(row + i * 128 + lane * 4);
       v[i * 4] = t.x; v[i * 4 + 1] = t.y; v[i * 4 + 2] = t.z; v[i * 4 + 3] = t.w;
+    } else if constexpr (std::is_same<T, __half>::value) {
+      uint2 t = *reinterpret_cast<const uint2*>(row + i * 128 + lane * 4);
+      const float2 a = __half22float2(*reinterpret_cast<__half2*>(&t.x));
+      const float2 b = __half22float2(*reinterpret_cast<__half2*>(&t.y));
+      v[i * 4] = a.x; v[i * 4 + 1] = a.y; v[i * 4 + 2] = b.x; v[i * 4 + 3] = b.y;
     } else {
       uint2 t = *reinterpret_cast<const uint2*>(row + i * 128 + lane * 4);
       __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
@@ -275,10 +281,24 @@ __device__ __forceinline__ void mma_bf16_16816(float c[4], const uint32_t a[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16-bit operands of either format: bf16, or fp16 when F16 (same fragment layouts)
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+  if constexpr (F16) mma_f16_16816(c, a, b0, b1);
+  else mma_bf16_16816(c, a, b0, b1);
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// F16: qx and mem_hat hold fp16, the probabilities are rounded to fp16, both products run as f16 MMAs
+template <bool F16>
 __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__ qx, const bf16* __restrict__ mem_hat,
                                                         bf16* __restrict__ u, CrossArgs a, int n_tokens, int Sp, int Pp) {
   pdl_sync();
@@ -342,8 +362,8 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
       const uint4 qa = *reinterpret_cast<const uint4*>(Qs + g * QP + 32 * j + 8 * t);
       const uint4 qb = *reinterpret_cast<const uint4*>(Qs + (g + 8) * QP + 32 * j + 8 * t);
       const uint32_t a0[4] = {qa.x, qb.x, qa.y, qb.y}, a1[4] = {qa.z, qb.z, qa.w, qb.w};
-      mma_bf16_16816(c, a0, kb[j].x, kb[j].y);
-      mma_bf16_16816(c, a1, kb[j].z, kb[j].w);
+      mma_16816<F16>(c, a0, kb[j].x, kb[j].y);
+      mma_16816<F16>(c, a1, kb[j].z, kb[j].w);
     }
     const int j0 = key0 + 2 * t, j1 = j0 + 1;
     const bool m0 = j0 >= M || (msk && msk[j0]), m1 = j1 >= M || (msk && msk[min(j1, M - 1)]);
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
     float* srow = Ss + qi * Sp;
     bf16* prow = Ps + qi * Pp;
     if (qi >= n_tokens) {
-      for (int j = lane; j < nkt * 16; j += 32) prow[j] = __float2bfloat16_rn(0.f);
+      for (int j = lane; j < nkt * 16; j += 32) prow[j] = __float2bfloat16_rn(0.f);   // zero in either format
       continue;
     }
     float mx = -INFINITY;
@@ -383,7 +403,8 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
         p = srow[j] * inv;
         if (arow) arow[j] = p;
       }
-      prow[j] = __float2bfloat16_rn(p);
+      if constexpr (F16) reinterpret_cast<__half*>(prow)[j] = __float2half_rn(p);
+      else prow[j] = __float2bfloat16_rn(p);
     }
   }
   // ---- values
@@ -404,17 +425,17 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
     for (int nn = 0; nn < 4; ++nn) {
       uint32_t bf[4];
       ldsm_x4_trans(bf, xs_addr + (uint32_t)(((buf * 16 + brow) * XP + bcol + nn * 16) * 2));
-      mma_bf16_16816(acc[2 * nn], af, bf[0], bf[1]);
-      mma_bf16_16816(acc[2 * nn + 1], af, bf[2], bf[3]);
+      mma_16816<F16>(acc[2 * nn], af, bf[0], bf[1]);
+      mma_16816<F16>(acc[2 * nn + 1], af, bf[2], bf[3]);
     }
   }
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int col = x * CROSS_D + warp * 64 + n * 8 + 2 * t;
     if (g < n_tokens)
-      *reinterpret_cast<__nv_bfloat162*>(u + (size_t)(bs * n_tokens + g) * ld + col) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
+      *reinterpret_cast<uint32_t*>(u + (size_t)(bs * n_tokens + g) * ld + col) = pack16(acc[n][0], acc[n][1], a.out_f16);
     if (g + 8 < n_tokens)
-      *reinterpret_cast<__nv_bfloat162*>(u + (size_t)(bs * n_tokens + g + 8) * ld + col) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+      *reinterpret_cast<uint32_t*>(u + (size_t)(bs * n_tokens + g + 8) * ld + col) = pack16(acc[n][2], acc[n][3], a.out_f16);
   }
 }
 
@@ -425,7 +446,9 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
 // layout of the second product, so softmax(S) is normalised, rounded to bf16 and fed to P V without leaving the
 // warp.  Used for the denoiser self-attention (16 x 16, head_dim 128) and the VAE attentions (head_dim 64; 128 x 128
 // self, 128 x 8 cross, 18 x 18 encoder).
-template <int HD, int NKT>
+// F16: q, k, v hold fp16 (written by an fp16-output GEMM epilogue), the probabilities are rounded to fp16 and both
+// products run as f16 MMAs; the output stays bf16.
+template <int HD, int NKT, bool F16 = false>
 __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
                                                       const bf16* __restrict__ v, int ldk, bf16* __restrict__ out, int ldo,
                                                       int Lq, int Lk, const int* __restrict__ kv_len, float scale) {
@@ -475,8 +498,8 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
     for (int j = 0; j < NKT; ++j) {
       uint32_t bf[4];
       ldsm_x4(bf, ks_addr + (uint32_t)(((j * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * P + kk * 16 + ((lane >> 3) & 1) * 8) * 2));
-      mma_bf16_16816(s[2 * j], af, bf[0], bf[1]);
-      mma_bf16_16816(s[2 * j + 1], af, bf[2], bf[3]);
+      mma_16816<F16>(s[2 * j], af, bf[0], bf[1]);
+      mma_16816<F16>(s[2 * j + 1], af, bf[2], bf[3]);
     }
   }
   // ---- softmax over the valid keys (rows g and g + 8 of this warp's tile; a row lives in one quad)
@@ -514,20 +537,18 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
   for (int j = 0; j < NKT; ++j) {
     uint32_t af[4];
     {
-      const __nv_bfloat162 a0 = __floats2bfloat162_rn(s[2 * j][0] * inv0, s[2 * j][1] * inv0);
-      const __nv_bfloat162 a1 = __floats2bfloat162_rn(s[2 * j][2] * inv1, s[2 * j][3] * inv1);
-      const __nv_bfloat162 a2 = __floats2bfloat162_rn(s[2 * j + 1][0] * inv0, s[2 * j + 1][1] * inv0);
-      const __nv_bfloat162 a3 = __floats2bfloat162_rn(s[2 * j + 1][2] * inv1, s[2 * j + 1][3] * inv1);
-      af[0] = *reinterpret_cast<const uint32_t*>(&a0); af[1] = *reinterpret_cast<const uint32_t*>(&a1);
-      af[2] = *reinterpret_cast<const uint32_t*>(&a2); af[3] = *reinterpret_cast<const uint32_t*>(&a3);
+      af[0] = pack16(s[2 * j][0] * inv0, s[2 * j][1] * inv0, F16);
+      af[1] = pack16(s[2 * j][2] * inv1, s[2 * j][3] * inv1, F16);
+      af[2] = pack16(s[2 * j + 1][0] * inv0, s[2 * j + 1][1] * inv0, F16);
+      af[3] = pack16(s[2 * j + 1][2] * inv1, s[2 * j + 1][3] * inv1, F16);
     }
     const int brow = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
     for (int nn = 0; nn < HD / 16; ++nn) {
       uint32_t bf[4];
       ldsm_x4_trans(bf, vs_addr + (uint32_t)((brow * P + nn * 16 + (lane >> 4) * 8) * 2));
-      mma_bf16_16816(o[2 * nn], af, bf[0], bf[1]);
-      mma_bf16_16816(o[2 * nn + 1], af, bf[2], bf[3]);
+      mma_16816<F16>(o[2 * nn], af, bf[0], bf[1]);
+      mma_16816<F16>(o[2 * nn + 1], af, bf[2], bf[3]);
     }
   }
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
@@ -539,13 +560,13 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
   }
 }
 
-template <int HD, int NKT>
+template <int HD, int NKT, bool F16 = false>
 int launch_mha_mma(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
                    int n_heads, const int* kv_len, cudaStream_t st) {
   const int warps = Lq >= 64 ? 4 : ceil_div(Lq, 16);
   const size_t smem = (size_t)(2 * NKT * 16 + warps * 16) * (HD + 8) * 2;
   dim3 grid(n, n_heads, ceil_div(Lq, 64));
-  launch_k(mha_mma_kernel<HD, NKT>, grid, warps * 32, smem, st, q, ldq, k, v, ldk, out, ldo, Lq, Lk, kv_len,
+  launch_k(mha_mma_kernel<HD, NKT, F16>, grid, warps * 32, smem, st, q, ldq, k, v, ldk, out, ldo, Lq, Lk, kv_len,
            sqrtf(1.0f / (float)HD));
   CFB_LAUNCH_CHECK();
   return CFB_OK;
@@ -789,7 +810,7 @@ __global__ void __launch_bounds__(256) z0_kernel(const T* __restrict__ mem_hat, 
 template <typename T>
 int shared_key_bias(const T* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
                     const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
-                    int n_layers, int n_tot, cudaStream_t st) {
+                    int n_layers, int n_tot, cudaStream_t st, int f16) {
   Z0Args a;
   int tok = 0;
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
@@ -797,12 +818,14 @@ int shared_key_bias(const T* mem_hat, float* z0, const float* const a_zx[CFB_N_S
     a.tok_base[x] = tok; tok += len[x];
   }
   a.tok_base[CFB_N_STREAMS] = tok;
-  launch_k(z0_kernel<T>, ceil_div(tok, 8), 256, 0, st, mem_hat, z0, a, n_layers, n_tot);
+  if (f16 && sizeof(T) == 2)
+    launch_k(z0_kernel<__half>, ceil_div(tok, 8), 256, 0, st, reinterpret_cast<const __half*>(mem_hat), z0, a, n_layers, n_tot);
+  else launch_k(z0_kernel<T>, ceil_div(tok, 8), 256, 0, st, mem_hat, z0, a, n_layers, n_tot);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
-template int shared_key_bias<bf16>(const bf16*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t);
-template int shared_key_bias<float>(const float*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t);
+template int shared_key_bias<bf16>(const bf16*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t, int);
+template int shared_key_bias<float>(const float*, float*, const float* const*, const int*, const int*, const int*, int, int, cudaStream_t, int);
 
 template <typename TP>
 int softmax_shared(const float* S, TP* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st) {
@@ -811,6 +834,15 @@ int softmax_shared(const float* S, TP* P, const SharedAttnArgs& a, int n_batch, 
   static const bool strided = getenv("CFB_SOFTMAX_STRIDED") && atoi(getenv("CFB_SOFTMAX_STRIDED"));
   bool fits = true;
   for (int x = 0; x < CFB_N_STREAMS; ++x) fits = fits && a.len[x] <= 32 * SMX_MAXJ;
+  if constexpr (sizeof(TP) == 2) {
+    if (a.p_f16) {     // same layout, fp16 payload
+      __half* Ph = reinterpret_cast<__half*>(P);
+      if (fits && !strided) launch_k(softmax_shared_reg_kernel<__half>, ceil_div(rows * CFB_N_STREAMS, 8), 256, 0, st, S, Ph, a, rows, n_tokens);
+      else launch_k(softmax_shared_kernel<__half>, ceil_div(rows, 8), 256, 0, st, S, Ph, a, rows, n_tokens);
+      CFB_LAUNCH_CHECK();
+      return CFB_OK;
+    }
+  }
   if (fits && !strided) launch_k(softmax_shared_reg_kernel<TP>, ceil_div(rows * CFB_N_STREAMS, 8), 256, 0, st, S, P, a, rows, n_tokens);
   else launch_k(softmax_shared_kernel<TP>, ceil_div(rows, 8), 256, 0, st, S, P, a, rows, n_tokens);
   CFB_LAUNCH_CHECK();
@@ -835,11 +867,25 @@ int init_attention_kernels() {
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
-  CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(self_attn16_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SA_SMEM));
   if (dev < 64) done_mask |= 1ull << dev;
   return CFB_OK;
+}
+
+// Self-attention on fp16 q / k / v (the denoiser's 16 x 16, head_dim 128 case on the mma.sync kernel); bf16 output.
+bool mha_f16_supported(int Lk, int head_dim) {
+  return head_dim == 128 && Lk <= 16 && g_gemm_backend != CFB_GEMM_SIMT && !g_mha_simt;
+}
+int mha_f16(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
+            int n_heads, int head_dim, cudaStream_t st) {
+  if (n <= 0 || debug_skip(2)) return CFB_OK;
+  const bool aligned = ldq % 8 == 0 && ldk % 8 == 0 && ldo % 2 == 0 && ((uintptr_t)q % 16 == 0) &&
+                       ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 4 == 0);
+  CFB_CHECK(aligned && mha_f16_supported(Lk, head_dim), "mha_f16: unsupported (Lk=%d head_dim=%d)", Lk, head_dim);
+  return launch_mha_mma<128, 1, true>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, nullptr, st);
 }
 
 template <typename T>
@@ -887,18 +933,21 @@ int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int
     if (a.len[x] > maxM) maxM = a.len[x];
   }
   if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernels (in-place u == qx is fine: Q is staged before u is written)
-    if (cross_tc_supported(a, n_tokens, d))   // tcgen05 / TMEM / TMA (cross_tc.cu); else mma.sync below
+    if (!a.out_f16 && !a.in_f16 && cross_tc_supported(a, n_tokens, d))   // tcgen05 / TMEM / TMA (cross_tc.cu); else mma.sync below
       return cross_attention_tc(qx, (a.bs_offset + n_batch) * n_tokens, mem_hat, u, a, n_batch, st);
     const int Sp = ((maxM + 7) & ~7) + 8, Pp = ((maxM + 15) & ~15) + 8;
     const size_t smem_mma = (size_t)(16 * QP + CM_NBUF * 16 * XP) * 2 + (size_t)16 * Sp * 4 + (size_t)16 * Pp * 2;
     // CFB_GEMM_SIMT selects the CUDA-core engines everywhere (tests cross-check the two implementations)
     if (smem_mma <= (size_t)ATT_MAX_SMEM && g_gemm_backend != CFB_GEMM_SIMT) {
       dim3 grid(n_batch, CFB_N_STREAMS);
-      launch_k(cross_mma_kernel, grid, 256, smem_mma, st, qx, mem_hat, u, a, n_tokens, Sp, Pp);
+      if (a.in_f16) launch_k(cross_mma_kernel<true>, grid, 256, smem_mma, st, qx, mem_hat, u, a, n_tokens, Sp, Pp);
+      else launch_k(cross_mma_kernel<false>, grid, 256, smem_mma, st, qx, mem_hat, u, a, n_tokens, Sp, Pp);
       CFB_LAUNCH_CHECK();
       return CFB_OK;
     }
   }
+  CFB_CHECK(!a.out_f16 && !a.in_f16, "cross_attention: fp16 operands exist for the mma.sync kernel only (%d memory tokens; "
+            "cfb_set_bf16_activation_f16(0) selects bf16 outputs)", maxM);
   const size_t smem = ((size_t)QPB * CROSS_D + (size_t)QPB * maxM) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "cross_attention: %d memory tokens exceed the shared-memory budget", maxM);
   dim3 grid(n_batch, CFB_N_STREAMS, ceil_div(n_tokens, QPB));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -95,6 +96,16 @@ template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfl
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// Two floats -> one 32-bit pair of 16-bit values: bf16, or fp16 (clamped to its range) when f16 is set.
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  if (f16) {
+    const __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t*>(&t);
+  }
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {
@@ -165,6 +176,7 @@ struct Epilogue {
   int a_static, w_static;    // the operand is a weight (its split is cached) rather than an activation
   int a_from_ln;             // precision study (scheme 3): the A operand is a LayerNorm output
   int a_terms;               // bf16 A operand with 2 terms per value ([hi | lo] per 64 columns, lda >= 2 K); 0 / 1 = plain
+  int out_f16;               // out_bf16 outputs are written as fp16 (clamped) instead of bf16
   int ab_f16;                // both 16-bit operands hold fp16, not bf16, values (tcgen05 path only; kind::f16 does not mix)
 };
 

@@ -63,8 +63,8 @@ int g_fp32_tc = getenv("CFB_FP32_TC") ? atoi(getenv("CFB_FP32_TC")) : 1;
 // TimeBlock linears, 8 linear1, 16 latent_proj.  Activation rounding is what the guidance combine amplifies (DESIGN.md
 // section 2, tools/split_sites.py): latent_proj alone (one 128-column GEMM per evaluation, free) removes 43 % of the
 // bf16 mode's deviation from fp32, latent_proj + TimeBlock linears 62 %, every site 68 %.
-// cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 0 since the fp16 form below covers the same sites
-// for free (16 on top of it: 0.084 -> 0.078 at -0.8 % throughput).
+// cfb_set_bf16_activation_sites / env CFB_BF16_ACT_SITES; default 16: the fp16 form below covers every site for free,
+// and latent_proj -- whose output IS eps -- is worth its second term on top of it (0.028 -> 0.017 at -0.8 % throughput).
 bool gemm_tc_two_term_ok();   // gemm_tc.cu
 // bf16 handles: the LayerNorm outputs feeding qkv, the TimeBlock linears, linear1 and latent_proj are stored as fp16
 // instead of bf16 -- 11 instead of 8 significant bits for values that are O(1) by construction (clamped to the fp16
@@ -74,8 +74,11 @@ bool gemm_tc_two_term_ok();   // gemm_tc.cu
 // that the guidance weights amplify shrinks 8x at these sites at no cost.  (kind::f16 cannot mix A = f16 with B = bf16:
 // illegal instruction.)  cfb_set_bf16_activation_f16 / env CFB_BF16_ACT_F16; default 1.  Sites in g_bf16_act_sites
 // keep their two-term bf16 form.
-int g_bf16_act_f16 = getenv("CFB_BF16_ACT_F16") ? atoi(getenv("CFB_BF16_ACT_F16")) : 1;
-int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 0;
+// Bit mask of operand groups: 1 the LayerNorm outputs above, 2 the shared-slot probabilities with their per-step values
+// and the per-pair attention output feeding the fuser, 4 norm2's output with the per-step keys (scores / conditional
+// queries), 8 q / k / v of the self-attention, 16 queries and memory of the per-pair attention.
+int g_bf16_act_f16 = getenv("CFB_BF16_ACT_F16") ? atoi(getenv("CFB_BF16_ACT_F16")) : 31;
+int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 16;
 }
 
 using namespace cfb;
@@ -110,10 +113,11 @@ struct cfb_denoiser {
   DeviceBuf split_ws;
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
-  int act_f16 = 0;        // bf16: LayerNorm outputs for the sites of F16_SITES are fp16 (g_bf16_act_f16 at the last reserve_rows)
-  struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
+  int act_f16 = 0;        // bf16: operand groups kept as fp16 (g_bf16_act_f16 at the last reserve_rows)
+  struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1, *w_fu, *w_qx; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
   std::vector<W16> l16;
   const bf16* w_out16 = nullptr;
+  const bf16 *w_zx16[CFB_N_STREAMS] = {}, *w_yx16[CFB_N_STREAMS] = {};   // memory-side pre-projections [L d, d]
   DeviceBuf w16;
   int act_sites = 0;      // bf16: consumer sites whose LayerNorm input is kept as [hi | lo] in `a2` (g_bf16_act_sites)
   int split_scheme = 0;   // g_fp32_tc - 1 at the last reserve_split (1: fp32-accurate; 2, 3: precision-study schemes)
@@ -250,6 +254,11 @@ int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaSt
   return gemm(h->xin.p, sizeof(T) == 2, h->lat, h->w.w_embed, sizeof(T) == 2, h->lat, rows, h->d, h->lat, 0, ep, st);
 }
 
+// bf16 handles: queries and memory of the per-pair attention as fp16 (group 16 of g_bf16_act_f16; mma.sync kernel only)
+inline int pair_f16(const cfb_denoiser* h) {
+  return (h->prec == CFB_BF16 && !h->l16.empty() && (h->act_f16 & 16) && !g_cross_tc) ? 1 : 0;
+}
+
 // Per-step memory-side precompute of the shared-slot plan for all layers: keys Z + key bias z0 (which = 0) or values
 // Y^T (which = 1).  The two halves are independent and run on separate streams.  T = bf16: tcgen05 GEMMs; T = float
 // (parity mode): the same algebra on the CUDA-core GEMM, so the plan itself is checked against the oracle at 1e-4.
@@ -266,20 +275,25 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
     const T* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
     if (which == 0) {
       Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = tb; ez.out = h->zall.as<T>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
-      if constexpr (tb) CFB_TRY(gemm_tc(m0, d, (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
+      ez.out_f16 = tb && (h->act_f16 & 4) && !h->l16.empty();   // the scores GEMM runs on the fp16 norm2 output (run_layers)
+      ez.ab_f16 = pair_f16(h);                                   // the memory is fp16 then (mem_hat)
+      if constexpr (tb) CFB_TRY(gemm_tc(m0, d, ez.ab_f16 ? h->w_zx16[x] : (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
       else { ez.split = scp; ez.w_static = 1; CFB_TRY(gemm(m0, 0, d, h->w.w_zx[x], 0, d, len[x], Ld, d, 0, ez, st)); }
     } else {
       const int rows_avail = ml.total_rows - ml.row_base[x];
       Epilogue ey{}; ey.bias_period = 1; ey.out_bf16 = tb; ey.out = h->ytall.as<T>() + sp.p_off[x]; ey.ldo = sp.k_tot; ey.replicate = 1;
+      ey.out_f16 = tb && (h->act_f16 & 2) && !h->l16.empty();   // the values GEMM runs on fp16 probabilities (run_layers)
       const int w_rows = sp.kp[x] < rows_avail ? sp.kp[x] : rows_avail;   // columns past len[x] meet P == 0
-      if constexpr (tb) CFB_TRY(gemm_tc((const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
+      ey.ab_f16 = pair_f16(h);
+      if constexpr (tb) CFB_TRY(gemm_tc(ey.ab_f16 ? h->w_yx16[x] : (const bf16*)h->w.w_yx[x], d, m0, d, Ld, sp.kp[x], d, ey, st, w_rows));
       else {   // columns past w_rows stay zero
         ey.split = scp; ey.a_static = 1;
         CFB_TRY(gemm(h->w.w_yx[x], 0, d, m0, 0, d, Ld, w_rows, d, 0, ey, st));
       }
     }
   }
-  if (which == 0) return shared_key_bias<T>(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st);
+  if (which == 0)
+    return shared_key_bias<T>(mh, h->z0all.as<float>(), h->w.a_zx, ml.row_base, len, sp.s_off, h->L, sp.n_tot, st, pair_f16(h));
   return CFB_OK;
 }
 
@@ -418,9 +432,16 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // and that GEMM reads both terms; everything else uses the dense `a`.  Sites: 1 qkv, 2 TimeBlock linears, 8 linear1,
   // 16 latent_proj (scores / conditional queries address `a` by absolute row and stay plain: no measurable effect).
   const int sites = tb ? h->act_sites : 0;
-  // fp16 LayerNorm outputs for the sites of F16_SITES (consumers: tcgen05 GEMMs on the fp16 weight copies, Epilogue::ab_f16)
-  const int f16 = (tb && h->act_f16 && !h->l16.empty()) ? 1 : 0;
-  constexpr int F16_SITES = 1 | 2 | 8 | 16;
+  // fp16 instead of bf16 operands (g_bf16_act_f16): consumers are tcgen05 GEMMs on fp16 weight copies (Epilogue::ab_f16)
+  // or the f16 mma.sync attention kernels.  F16_SITES: LayerNorm consumer sites whose `a` is fp16; 128 = the per-pair
+  // attention output feeding the fuser (mma.sync kernel only).
+  const int fm = (tb && !h->l16.empty()) ? h->act_f16 : 0;
+  const int uc_f16 = ((fm & 2) && !g_cross_tc) ? 1 : 0;
+  const int pv_f16 = (fm & 2) ? 1 : 0;                                   // shared-slot probabilities x per-step values
+  const int self_f16 = ((fm & 8) && mha_f16_supported(h->ntok, d / h->H)) ? 1 : 0;   // q / k / v of the self-attention
+  const int F16_SITES = ((fm & 1) ? (1 | 2 | 8 | 16) : 0) | ((fm & 4) ? 4 : 0) | (uc_f16 ? 128 : 0);
+  const int pr_f16 = tb ? pair_f16(h) : 0;                                 // queries / memory of the per-pair attention
+  ca.out_f16 = uc_f16; ca.in_f16 = pr_f16;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
   float* hres = h->h.as<float>() + (size_t)row0 * d;
   T* a_abs = h->a.as<T>();
@@ -430,7 +451,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   auto ln_to = [&](int site, const float* ln_g, const float* ln_b, const float* mod) {   // LayerNorm for consumer `site`
     return (sites & site) ? ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a2, R, d, st, 2)
                           : ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st,
-                                       (f16 && (site & F16_SITES)) ? 3 : 1);
+                                       (site & F16_SITES) ? 3 : 1);
   };
   T* qkv = h->qkv.as<T>() + (size_t)row0 * 3 * d;
   T* qx = qx_abs + (size_t)row0 * CFB_N_STREAMS * d;
@@ -449,11 +470,13 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // 32 out_proj (self-attention output), 64 linear2 (GELU output), 128 fuser (per-pair attention output), 256 shared
   // values (probabilities)
   // W16: the fp16 copy of W (null: none, e.g. fp32 handles)
-  auto lin_T = [&](int K, const void* W, const void* W16, const float* b, void* out, int N, int act, int site) {   // A = LayerNorm(h) for `site`
+  auto lin_T = [&](int K, const void* W, const void* W16, const float* b, void* out, int N, int act, int site,
+                   int out_f16 = 0) {   // A = LayerNorm(h) for `site`
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    ep.out_f16 = out_f16;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = site;
     const int at = (sites & site) ? 2 : 1;
-    ep.a_terms = at; ep.ab_f16 = (at == 1 && (site & F16_SITES)) ? f16 : 0;
+    ep.a_terms = at; ep.ab_f16 = (at == 1 && (site & F16_SITES)) ? 1 : 0;
     if (ep.ab_f16) W = W16;
     return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
   };
@@ -467,7 +490,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_site;
     const int at = (a_site && (sites & a_site)) ? 2 : 1;
-    ep.a_terms = at; ep.ab_f16 = (at == 1 && (a_site & F16_SITES)) ? f16 : 0;
+    ep.a_terms = at; ep.ab_f16 = (at == 1 && (a_site & F16_SITES)) ? 1 : 0;
     if (ep.ab_f16) W = W16;
     CFB_TRY(gemm(at == 2 ? (const void*)a2 : A, tb, at * K, W, tb, K, R, d, K, 0, ep, st));
     CFB_TRY(ln_to(next_site, ln_g, ln_b, mod));
@@ -479,9 +502,14 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     const float* mod1 = h->tbmod.as<float>() + (size_t)(2 * l) * 2 * d;
     const float* mod2 = mod1 + 2 * d;
     // self-attention block (cross_attention.py:568-572); a = norm1(h) on entry
-    const cfb_denoiser::W16 w16 = f16 ? h->l16[l] : cfb_denoiser::W16{};
-    CFB_TRY(lin_T(d, w.w_in, w16.w_in, w.b_in, qkv, 3 * d, 0, 1));
-    CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
+    const cfb_denoiser::W16 w16 = fm ? h->l16[l] : cfb_denoiser::W16{};
+    CFB_TRY(lin_T(d, w.w_in, w16.w_in, w.b_in, qkv, 3 * d, 0, 1, self_f16));
+    if (self_f16) {
+      if constexpr (tb)
+        CFB_TRY(mha_f16(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, st));
+    } else {
+      CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
+    }
     if (rb & 1) {   // out_proj -> time_block1 -> norm2 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
     } else {
@@ -518,10 +546,12 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           CFB_CUDA(cudaStreamWaitEvent(sc, aux->ev_a, 0));
         }
         Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = tb; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
+        eq.ab_f16 = (fm & 4) ? 1 : 0; eq.out_f16 = pr_f16;
         if constexpr (sizeof(T) == 2) {
+          const bf16* wqx = (fm & 4) ? w16.w_qx : (const bf16*)w.w_qx;
           TcGroup gq[TC_MAX_GROUPS];
           for (int z = 0; z < ng; ++z)
-            gq[z] = TcGroup{a_abs, (const bf16*)w.w_qx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
+            gq[z] = TcGroup{a_abs, wqx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
                             grp[z].lo, grp[z].rows};
           CFB_TRY(gemm_tc_grouped(gq, ng, R_total, d, d, d, d, eq, sc));
         } else {
@@ -542,13 +572,15 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         if (ng == 0) return CFB_OK;
         if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
         Epilogue eg{}; eg.bias_period = 1; eg.accumulate = 1; eg.ldo = d; eg.replicate = 1;
+        eg.ab_f16 = uc_f16;
+        const bf16* wfu = uc_f16 ? w16.w_fu : (const bf16*)w.w_fu;
         if constexpr (sizeof(T) == 2) {
           for (int r = 0; r < sp->n_rounds; ++r) {
             TcGroup round[TC_MAX_GROUPS];
             int n = 0;
             for (int z = 0; z < ng; ++z)
               if (grp[z].round == r)
-                round[n++] = TcGroup{uc + grp[z].x * d, (const bf16*)w.w_fu + grp[z].x * d, nullptr, h_abs, grp[z].lo, grp[z].rows};
+                round[n++] = TcGroup{uc + grp[z].x * d, wfu + grp[z].x * d, nullptr, h_abs, grp[z].lo, grp[z].rows};
             if (n > 0) CFB_TRY(gemm_tc_grouped(round, n, R_total, CFB_N_STREAMS * d, CFB_N_STREAMS * d, d, d, eg, st));
           }
         } else {
@@ -567,13 +599,14 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
       es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 4;   // keys Z change every step: this chain's W slot
+      es.ab_f16 = (fm & 4) ? 1 : 0;                                               // fp16 norm2 output x fp16 keys (shared_precompute)
       CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
         sa.len[x] = ca.len[x]; sa.s_off[x] = sp->s_off[x]; sa.p_off[x] = sp->p_off[x]; sa.kp[x] = sp->kp[x];
         sa.slot[x] = ca.slot[x]; sa.mask[x] = ca.mask[x];
       }
-      sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0;
+      sa.ld_s = sp->n_tot; sa.ld_p = sp->k_tot; sa.bs_offset = b0; sa.p_f16 = pv_f16;
       CFB_TRY(softmax_shared<T>(sS, sP, sa, n_batch, h->ntok, st));
       if (rb & 2) {   // fuser block + shared values -> time_block2 -> norm3 on resident rows (rowblock.cu)
         if (side) CFB_CUDA(cudaStreamWaitEvent(st, aux->ev_b, 0));
@@ -581,7 +614,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
         rb2_done = true;
       } else {
         Epilogue ey{}; ey.bias = w.b_fu; ey.bias_period = 1; ey.accumulate = 1; ey.out = hres; ey.ldo = d; ey.replicate = 1;
-        ey.split = scm; ey.a_from_ln = 256;
+        ey.split = scm; ey.a_from_ln = 256; ey.ab_f16 = pv_f16;   // fp16 probabilities x fp16 values (shared_precompute)
         CFB_TRY(gemm(sP, tb, sp->k_tot, h->ytall.as<T>() + (size_t)l * d * sp->k_tot, tb, sp->k_tot, R, d, sp->k_tot, 0, ey, st));
         CFB_TRY(cond_fuser());
         CFB_TRY(ln_to(2, w.tb2_g, w.tb2_b, mod2));
@@ -589,9 +622,9 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       shared_done = true;
     }
     if (!shared_done) {
-      CFB_TRY(lin_T(d, w.w_qx, nullptr, w.b_qx, qx, CFB_N_STREAMS * d, 0, 4));
+      CFB_TRY(lin_T(d, w.w_qx, w16.w_qx, w.b_qx, qx, CFB_N_STREAMS * d, 0, 4, pr_f16));
       CFB_TRY(cross_attention<T>(qx_abs, h->mem_hat.as<T>(), qx_abs, ca, n_batch, h->ntok, d, st));
-      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, nullptr, w.b_fu, w.tb2_g, w.tb2_b, mod2, 128, 2));   // + time_block2 prologue (:655)
+      CFB_TRY(lin_res_ln(qx, CFB_N_STREAMS * d, w.w_fu, w16.w_fu, w.b_fu, w.tb2_g, w.tb2_b, mod2, 128, 2));   // + time_block2 prologue (:655)
     }
     if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w16.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 2, 8));   // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
@@ -608,7 +641,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
   ep.split = scm; ep.w_static = 1; ep.a_from_ln = 16;
   const int at = (sites & 16) ? 2 : 1;
-  ep.a_terms = at; ep.ab_f16 = at == 1 ? f16 : 0;
+  ep.a_terms = at; ep.ab_f16 = (at == 1 && (F16_SITES & 16)) ? 1 : 0;
   return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * d, ep.ab_f16 ? (const void*)h->w_out16 : h->w.w_out, tb, d,
               R, h->lat, d, 0, ep, st);
 }
@@ -635,7 +668,7 @@ int reserve_rows(cfb_denoiser* h, int n_batch, int n_in) {
   // (the two-term GEMM variant exists for the TMA-epilogue kernel only: plain operands with CFB_TC_TMA_EPI=0)
   h->act_sites = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && gemm_tc_two_term_ok()) ? (g_bf16_act_sites & 27) : 0;
   // (the row-block programs write their LayerNorm outputs as bf16)
-  h->act_f16 = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && g_bf16_act_f16 && g_rowblock == 0) ? 1 : 0;
+  h->act_f16 = (h->prec == CFB_BF16 && g_gemm_backend != CFB_GEMM_SIMT && g_rowblock == 0) ? (g_bf16_act_f16 & 31) : 0;
   CFB_TRY(h->h.reserve(R * d * 4, &h->epoch));
   CFB_TRY(h->a.reserve(R * d * es, &h->epoch));
   if (h->act_sites) CFB_TRY(h->a2.reserve(R * d * 2 * 2, &h->epoch));
@@ -705,7 +738,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
     // cross-attention, so they leave the critical path entirely: two side streams, joined by ev_pre in run_layers.
     CFB_CUDA(cudaEventRecord(h->ev_fork, st));
     CFB_CUDA(cudaStreamWaitEvent(h->pre_st[0], h->ev_fork, 0));
-    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, h->pre_st[0]));
+    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, h->pre_st[0], pair_f16(h)));
     CFB_CUDA(cudaEventRecord(h->ev_mh, h->pre_st[0]));
     if constexpr (sizeof(T) == 2)
       if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, h->pre_st[0]));
@@ -715,7 +748,7 @@ int step_body(cfb_denoiser* h, int n_clips, int n_branch, const MemLayout& ml, c
       CFB_CUDA(cudaEventRecord(h->ev_pre[i], h->pre_st[i]));
     }
   } else {
-    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st));
+    CFB_TRY(mem_hat<T>(h->mem_c.as<float>(), h->temb.as<float>(), step_ptr, h->mem_hat.as<T>(), ml.total_rows, h->d, st, pair_f16(h)));
     if constexpr (sizeof(T) == 2)
       if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, st));
     if (sp.on) {
@@ -852,8 +885,10 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
   // fp16 copies of the weights fed by LayerNorm outputs (g_bf16_act_f16): qkv, TimeBlock linears, linear1, latent_proj
   if (rc == CFB_OK && h->prec == CFB_BF16) {
     auto make16 = [&]() -> int {
-      const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = 5 * d2 + ffd, outn = (size_t)h->lat * h->d;
-      CFB_TRY(h->w16.reserve((per * h->L + outn) * 2, nullptr));
+      const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = (5 + 2 * CFB_N_STREAMS) * d2 + ffd;
+      const size_t outn = (size_t)h->lat * h->d;
+      const size_t pre = (size_t)h->L * d2;
+      CFB_TRY(h->w16.reserve((per * h->L + outn + 2 * CFB_N_STREAMS * pre) * 2, nullptr));
       bf16* p = h->w16.as<bf16>();
       auto conv = [&](const void* src, size_t n, const bf16** dst) -> int {
         CFB_TRY(bf16_to_f16((const bf16*)src, p, n, nullptr));
@@ -866,8 +901,14 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
         CFB_TRY(conv(h->layers[l].w_tb1, d2, &h->l16[l].w_tb1));
         CFB_TRY(conv(h->layers[l].w_tb2, d2, &h->l16[l].w_tb2));
         CFB_TRY(conv(h->layers[l].w_ff1, ffd, &h->l16[l].w_ff1));
+        CFB_TRY(conv(h->layers[l].w_fu, CFB_N_STREAMS * d2, &h->l16[l].w_fu));
+        CFB_TRY(conv(h->layers[l].w_qx, CFB_N_STREAMS * d2, &h->l16[l].w_qx));
       }
       CFB_TRY(conv(h->w.w_out, outn, &h->w_out16));
+      for (int x = 0; x < CFB_N_STREAMS; ++x) {
+        CFB_TRY(conv(h->w.w_zx[x], pre, &h->w_zx16[x]));
+        CFB_TRY(conv(h->w.w_yx[x], pre, &h->w_yx16[x]));
+      }
       CFB_CUDA(cudaStreamSynchronize(nullptr));
       return CFB_OK;
     };
@@ -924,8 +965,9 @@ int cfb_set_bf16_activation_terms(int terms) {   // 2: every site, 1: none
   return CFB_OK;
 }
 
-int cfb_set_bf16_activation_f16(int enabled) {
-  g_bf16_act_f16 = enabled ? 1 : 0;
+int cfb_set_bf16_activation_f16(int mask) {
+  CFB_CHECK(mask >= 0 && mask <= 31, "cfb_set_bf16_activation_f16: mask %d outside 0..31", mask);
+  g_bf16_act_f16 = mask;
   return CFB_OK;
 }
 
@@ -972,7 +1014,7 @@ int cfb_denoiser_forward(cfb_denoiser* h, const float* sample, int n_batch, int6
   ca.att_first_batch = 0; ca.step_ptr = nullptr;
   CFB_TRY(reserve_split(h, n_batch, mem, false));
   if (h->prec == CFB_BF16) {
-    CFB_TRY(mem_hat<bf16>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<bf16>(), ml.total_rows, h->d, st));
+    CFB_TRY(mem_hat<bf16>(h->mem_c.as<float>(), h->temb.as<float>(), nullptr, h->mem_hat.as<bf16>(), ml.total_rows, h->d, st, pair_f16(h)));
     if (cross_tc_supported(ca, h->ntok, h->d)) CFB_TRY(mem_transpose(h->mem_hat.as<bf16>(), h->mem_hat_t.as<bf16>(), ca, st));
     CFB_TRY(embed<bf16>(h, sample, n_batch, 1, st));
     return run_layers<bf16>(h, n_batch, ca, att_out, nullptr, eps_out, st);

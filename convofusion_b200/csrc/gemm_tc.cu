@@ -212,10 +212,7 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
             for (int j = 0; j < 4; ++j) {
               uint32_t pk[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-                pk[e] = *reinterpret_cast<const uint32_t*>(&t);
-              }
+              for (int e = 0; e < 4; ++e) pk[e] = pack16(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], ep.out_f16);
               st_shared_v4(box + (((uint32_t)((c & 1) * 4 + j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             }
             if (c & 1) {
@@ -337,15 +334,13 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmA_p, const CUtens
           } else {
             bf16* o = reinterpret_cast<bf16*>(ep.out) + off;
             if constexpr (CPL == 4) {
-              const __nv_bfloat162 t0 = __floats2bfloat162_rn(v[i][0], v[i][1]);
-              const __nv_bfloat162 t1 = __floats2bfloat162_rn(v[i][2], v[i][3]);
               uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&t0); pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+              pk.x = pack16(v[i][0], v[i][1], ep.out_f16); pk.y = pack16(v[i][2], v[i][3], ep.out_f16);
               *reinterpret_cast<uint2*>(o) = pk;
             } else if constexpr (CPL == 2) {
-              *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v[i][0], v[i][1]);
+              *reinterpret_cast<uint32_t*>(o) = pack16(v[i][0], v[i][1], ep.out_f16);
             } else {
-              *o = __float2bfloat16_rn(v[i][0]);
+              *reinterpret_cast<uint16_t*>(o) = (uint16_t)(pack16(v[i][0], 0.f, ep.out_f16) & 0xffffu);
             }
           }
         }
@@ -536,10 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_
           for (int j = 0; j < 4; ++j) {
             uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-              pk[e] = *reinterpret_cast<const uint32_t*>(&t);
-            }
+            for (int e = 0; e < 4; ++e) pk[e] = pack16(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], ep.out_f16);
             st_shared_v4(box + (((uint32_t)((c & 1) * 4 + j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           if (c & 1) {

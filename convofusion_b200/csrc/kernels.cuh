@@ -13,7 +13,8 @@ int bf16_to_f16(const bf16* in, bf16* out, size_t n, cudaStream_t st);
 int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_STREAMS], const int len[CFB_N_STREAMS],
               const float* stream_emb, const float* pe, float* mem_c, int d, cudaStream_t st);
 template <typename T>
-int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st);
+int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st,
+            int f16 = 0);   // f16: 16-bit output holds fp16
 int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st);
 template <typename T> int cast_rows(const float* in, T* out, long long n, cudaStream_t st);
 template <typename T> int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st);
@@ -31,6 +32,10 @@ int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStre
 template <typename T>
 int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, int n, int Lq, int Lk, int n_heads,
         int head_dim, const int* kv_len, cudaStream_t st);
+// bf16 handles with fp16 activations: q / k / v hold fp16, output bf16 (attention.cu)
+bool mha_f16_supported(int Lk, int head_dim);
+int mha_f16(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
+            int n_heads, int head_dim, cudaStream_t st);
 
 // The denoiser's five folded single-head cross-attentions for every (batch entry, stream):
 //   P = softmax(qx[bs, x] . mem_hat[slot]^T + mask),  u[bs, x] = P . mem_hat[slot]
@@ -51,6 +56,8 @@ struct CrossArgs {
   const bf16* mem_hat_t;                // per stream x at element offset t_off[x]: [n_slots, 512, lenp[x]] or nullptr
   long long t_off[CFB_N_STREAMS];
   int lenp[CFB_N_STREAMS];              // len rounded up to a multiple of 8 (16-byte rows)
+  int out_f16;                          // bf16 path: u is written as fp16 (mma.sync kernel only; A operand of an fp16 GEMM)
+  int in_f16;                           // bf16 path: qx and mem_hat hold fp16 (mma.sync kernel only: f16 MMAs)
 };
 // cross_tc.cu
 int init_cross_tc_kernels();
@@ -67,13 +74,14 @@ struct SharedAttnArgs {
   const uint8_t* mask[CFB_N_STREAMS];   // key padding mask of slot 0 or nullptr
   int ld_s, ld_p;
   int bs_offset;                        // batch entry of row 0 of S / P as passed to the launch
+  int p_f16;                            // 16-bit P holds fp16 instead of bf16 (A operand of an fp16 GEMM)
 };
 template <typename TP>
 int softmax_shared(const float* S, TP* P, const SharedAttnArgs& a, int n_batch, int n_tokens, cudaStream_t st);
 template <typename T>
 int shared_key_bias(const T* mem_hat, float* z0, const float* const a_zx[CFB_N_STREAMS],
                     const int row_base[CFB_N_STREAMS], const int len[CFB_N_STREAMS], const int s_off[CFB_N_STREAMS],
-                    int n_layers, int n_tot, cudaStream_t st);
+                    int n_layers, int n_tot, cudaStream_t st, int f16 = 0);   // f16: 16-bit mem_hat holds fp16
 template <typename T>
 int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,
                     cudaStream_t st);

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) mem_build_kernel(MemBuildArgs a, const fl
 
 // mem_hat[row] = (mem_c[row] + temb - mean) * rstd : the affine-free LayerNorm every layer's
 // {stream}_norm shares (denoiser.py:255-261 + cross_attention.py:581-585; gamma/beta live in w_qx/w_fu).
-template <typename T, int D>
+template <typename T, int D, bool F16 = false>
 __global__ void __launch_bounds__(256) mem_hat_kernel(const float* __restrict__ mem_c, const float* __restrict__ temb,
                                                       const int* __restrict__ step_ptr, T* __restrict__ out, int rows) {
   pdl_sync();
@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) mem_hat_kernel(const float* __restrict__ 
   r.load(mem_c + (size_t)row * D, lane);
   r.add(temb + (step_ptr ? (size_t)(*step_ptr) * D : 0), lane);
   r.normalize();
-  r.store(out + (size_t)row * D, lane);
+  if constexpr (F16 && sizeof(T) == 2) r.store_f16(reinterpret_cast<bf16*>(out) + (size_t)row * D, lane);
+  else r.store(out + (size_t)row * D, lane);
 }
 
 // embeddings.py:245-285 with flip_sin_to_cos=True, freq_shift=0: [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k / half)
@@ -258,15 +259,16 @@ int mem_build(const float* const cond[CFB_N_STREAMS], const int n_slots[CFB_N_ST
 }
 
 template <typename T>
-int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st) {
+int mem_hat(const float* mem_c, const float* temb, const int* step_ptr, T* out, int rows, int d, cudaStream_t st, int f16) {
   CFB_CHECK(d == 512, "mem_hat: d_model %d unsupported", d);
   if (rows <= 0) return CFB_OK;
-  launch_k(mem_hat_kernel<T, 512>, ceil_div(rows, 8), 256, 0, st, mem_c, temb, step_ptr, out, rows);
+  if (f16 && sizeof(T) == 2) launch_k(mem_hat_kernel<T, 512, true>, ceil_div(rows, 8), 256, 0, st, mem_c, temb, step_ptr, out, rows);
+  else launch_k(mem_hat_kernel<T, 512>, ceil_div(rows, 8), 256, 0, st, mem_c, temb, step_ptr, out, rows);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
-template int mem_hat<float>(const float*, const float*, const int*, float*, int, int, cudaStream_t);
-template int mem_hat<bf16>(const float*, const float*, const int*, bf16*, int, int, cudaStream_t);
+template int mem_hat<float>(const float*, const float*, const int*, float*, int, int, cudaStream_t, int);
+template int mem_hat<bf16>(const float*, const float*, const int*, bf16*, int, int, cudaStream_t, int);
 
 int time_sinusoid(const float* t, float* out, int n, int dim, cudaStream_t st) {
   const int total = n * (dim / 2);

@@ -66,24 +66,33 @@ int cfb_set_rowblock(int mask);
  * hi + lo (two bf16 terms) against bf16-rounded weights, 3 = both operands rounded to bf16 (the bf16 mode's GEMM
  * rounding with everything else in fp32).  Same operator surface as Denoiser.forward in float32 (denoiser.py:173-386). */
 int cfb_set_fp32_tensor_cores(int mode);
-/* bf16 handles, activation precision at the GEMMs fed by a LayerNorm.  Activation rounding is what the guidance
- * weights (-36.5 / +7.5) amplify; weight rounding is common to all branches and cancels.
+/* bf16 handles, precision of the 16-bit ACTIVATION operands.  Activation rounding is what the guidance weights
+ * (-36.5 / +7.5) amplify; weight rounding is common to all branches and cancels.
  *
- * cfb_set_bf16_activation_f16: 1 (default, also env CFB_BF16_ACT_F16) = the LayerNorm outputs feeding qkv, both
- * TimeBlock linears, linear1 and latent_proj are stored as fp16 instead of bf16 (11 instead of 8 significant bits; the
- * values are O(1) by construction and clamped to the fp16 range) and those GEMMs run tcgen05.mma kind::f16 on fp16
- * operands -- the handle keeps fp16 copies of those bf16 weights (exact conversion above the fp16 subnormal range).
- * Same bytes, same MMA rate: DDIM-50 deviation from the fp32 reference 0.195 -> 0.084 at unchanged throughput.
- * 0 = bf16 activations everywhere (round-1 behaviour).
+ * cfb_set_bf16_activation_f16(mask): activation operands kept as fp16 (11 significant bits) instead of bf16 (8) --
+ * they are O(1) by construction (LayerNorm outputs, probabilities, convex combinations of normalised memory, q / k / v;
+ * every store clamps to the fp16 range) -- and consumed by fp16 x fp16 products: tcgen05.mma kind::f16 with both
+ * operand formats f16 against fp16 copies of the bf16 weights made once per handle (exact above the fp16 subnormal
+ * range; kind::f16 cannot mix an f16 A with a bf16 B), or the f16 form of the mma.sync attention kernels.  Same bytes,
+ * same instruction counts, same kernels.  Bit mask of operand groups (default 31 = all, also env CFB_BF16_ACT_F16):
+ *    1  LayerNorm outputs feeding qkv, both TimeBlock linears, linear1, latent_proj
+ *    2  shared-slot probabilities with the per-step pre-projected values; per-pair attention output feeding the fuser
+ *    4  norm2 output with the per-step pre-projected keys (scores) and the conditional-query projection
+ *    8  q / k / v of the self-attention
+ *   16  queries and normalised memory of the per-pair attention (and the memory-side pre-projections that read it)
+ * DDIM-50 deviation from the fp32 reference (latent L2): 0.195 (mask 0) -> 0.084 (1) -> 0.049 (3) -> 0.028 (31) at
+ * unchanged throughput.  0 = bf16 activations everywhere (round-1 behaviour).  Groups 2 (attention output) and 16 need
+ * the mma.sync per-pair kernel: they are off while cfb_set_cross_tc(1); everything is off with cfb_set_rowblock != 0
+ * and on the CUDA-core GEMM backend.
  *
- * cfb_set_bf16_activation_sites: bit mask of consumer sites (1 qkv, 2 both TimeBlock linears, 8 linear1, 16
- * latent_proj) whose LayerNorm input is kept as TWO bf16 terms per value (hi + lo, 16 significant bits); that GEMM
- * issues two accumulating tcgen05.mma per K step against the bf16 weights.  Default 0 (also env CFB_BF16_ACT_SITES):
- * on top of the fp16 form the gain is small (16: 0.078 at -0.8 % throughput; 27: 0.078 at -17 %); with fp16 off:
- * 16 -> 0.117, 18 -> 0.076, 27 -> 0.078.
+ * cfb_set_bf16_activation_sites(mask): consumer sites (1 qkv, 2 both TimeBlock linears, 8 linear1, 16 latent_proj)
+ * whose LayerNorm input is kept as TWO bf16 terms per value (hi + lo, 16 significant bits); that GEMM issues two
+ * accumulating tcgen05.mma per K step against the bf16 weights.  Default 16 (also env CFB_BF16_ACT_SITES):
+ * latent_proj's output IS eps, so its operand rounding reaches the guidance combine unattenuated -- 0.028 -> 0.017
+ * for -0.8 % throughput.  With fp16 off: 16 -> 0.117, 18 -> 0.076 (-8 %), 27 -> 0.078 (-17 %).
  *
  * cfb_set_bf16_activation_terms: shorthand, 2 = every site (mask 27), 1 = none (mask 0). */
-int cfb_set_bf16_activation_f16(int enabled);
+int cfb_set_bf16_activation_f16(int mask);
 int cfb_set_bf16_activation_sites(int mask);
 int cfb_set_bf16_activation_terms(int terms);
 /* Per-pair cross-attention of bf16 handles (cross_attention.py:593-626: 16 queries against one clip's <= 256 memory

@@ -14,7 +14,7 @@ from helpers import SCHED_KW, golden, oracle_batch, oracle_denoise, rel_err, sta
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-DEFAULT = (1, 0)   # library defaults: (cfb_set_bf16_activation_f16, cfb_set_bf16_activation_sites)
+DEFAULT = (31, 16)   # library defaults: (cfb_set_bf16_activation_f16, cfb_set_bf16_activation_sites)
 
 
 def sampler(steps):
@@ -45,7 +45,7 @@ def test_two_term_activations_cut_the_bf16_error():
     eps_default, _ = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
     e, l = {}, {}
     try:
-        for f16, mask in ((0, 0), (1, 0), (0, 16), (1, 16), (1, 18), (0, 27), (1, 27)):
+        for f16, mask in ((0, 0), (1, 0), (3, 0), (7, 0), (15, 0), (31, 0), (0, 16), (31, 16), (0, 27)):
             _lib.check(lib.cfb_set_bf16_activation_f16(f16))
             _lib.check(lib.cfb_set_bf16_activation_sites(mask))
             eps, att = s.denoiser(x.to(DEV), torch.tensor(500), enc7, None, masks7)
@@ -57,7 +57,7 @@ def test_two_term_activations_cut_the_bf16_error():
             k = (f16, mask)
             e[k] = rel_err(eps.cpu(), want)
             l[k] = [rel_err(rec[i].cpu(), g["record"][i]) for i in (0, 24, 49)]
-            print(f"LayerNorm outputs {'fp16' if f16 else 'bf16'}, two-term sites {mask:2d}: one evaluation eps L2 vs oracle "
+            print(f"fp16 operand groups {f16:2d}, two-term sites {mask:2d}: one evaluation eps L2 vs oracle "
                   f"{e[k]:.2e}; DDIM-50 latents L2 vs reference golden after steps 1 / 25 / 50: "
                   f"{l[k][0]:.3f} {l[k][1]:.3f} {l[k][2]:.3f}")
             if k == DEFAULT:
@@ -70,8 +70,9 @@ def test_two_term_activations_cut_the_bf16_error():
     assert e[(0, 27)] < e[(0, 0)]   # a single evaluation is dominated by the (branch-common) weight rounding: small gain
     assert l[(0, 16)][2] < 0.7 * plain[2] and l[(0, 16)][0] < 0.7 * plain[0]   # latent_proj alone
     assert l[(0, 27)][0] < 0.5 * plain[0] and l[(0, 27)][2] < 0.5 * plain[2] and l[(0, 27)][2] < 0.1
-    # fp16 LayerNorm outputs: every LayerNorm-fed site at 11 bits for free
+    # fp16 LayerNorm outputs: every LayerNorm-fed site at 11 bits for free; all operand groups: a quarter of the error
     assert l[(1, 0)][0] < 0.5 * plain[0] and l[(1, 0)][2] < 0.5 * plain[2] and l[(1, 0)][2] < 0.1
+    assert l[(31, 0)][0] < 0.3 * plain[0] and l[(31, 0)][2] < 0.3 * plain[2]
     _lib.check(lib.cfb_set_bf16_activation_terms(2))              # shorthand: every site
     _lib.check(lib.cfb_set_bf16_activation_f16(0))
     try:

@@ -64,6 +64,8 @@ def test_optional_paths_agree_with_default(tmp_path):
             # mha_simt: CUDA-core attention keeps the probabilities in fp32, the tensor-core kernel rounds them to bf16
             # before P.V; no_plan: the general per-pair path rounds the projected queries instead of the pre-projected
             # keys / values; rowblock: other summation order + one-pass LayerNorm statistics.  Each moves bf16 rounding
-            # sites, amplified like every other one (measured 0.079 / 0.094; bf16-vs-fp32 first step: ~0.06)
-            assert l2 < 0.15, name
+            # sites, amplified like every other one.  Measured with fp16 activations (the default): mha_simt 0.006,
+            # no_plan 0.008, cross_tcgen05 0.017 (bf16 queries / memory in that kernel), rowblock_all 0.037 (the row-block
+            # programs keep bf16 activations)
+            assert l2 < 0.08, name
 

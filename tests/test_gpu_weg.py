@@ -106,7 +106,7 @@ def test_weg_loops_vs_reference_loop_code(precision):
               f"losses {[round(e['loss'], 4) for e in log]}, refinement iterations {[e['n_refine'] for e in log]}")
         assert [e["n_refine"] for e in log] == [e["n_refine"] for e in case["log"]]
         assert moved > 0.3
-        assert err < (1e-2 if precision == "fp32" else 0.3)
+        assert err < (1e-2 if precision == "fp32" else 0.15)   # bf16 measured 0.028 / 0.073
         assert len(att) == g["n_steps"]
     if precision == "bf16":
         assert s._weg_denoiser() is not s.denoiser and s._weg_denoiser().precision == "fp32"

@@ -64,7 +64,7 @@ def run(B=8, steps=2, dyadic=True, masks=(1, 2, 4, 7), scale=1.0, dev="cuda:0", 
         raise
     finally:
         lib.cfb_set_rowblock(0)
-        lib.cfb_set_bf16_activation_f16(1)
+        lib.cfb_set_bf16_activation_f16(31)
     if verbose:
         print(f"B={B} steps={steps} dyadic={dyadic} guidance_scale={scale}")
         print(f"  operator path vs fp32: first {res['operator_vs_fp32'][0]:.3e} last {res['operator_vs_fp32'][1]:.3e}")
