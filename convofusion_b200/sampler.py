@@ -9,6 +9,8 @@ checkpoint (its T5 body is stripped on save, base.py:83-104).
 """
 from __future__ import annotations
 
+import os
+
 import inspect
 from typing import Dict, List, Optional, Sequence
 
@@ -60,10 +62,14 @@ def default_scheduler(kind: str = "ddim"):
 class ConvoFusionSampler(nn.Module):
     def __init__(self, denoiser: Optional[Denoiser] = None, vae: Optional[ConvoFusionVae] = None, scheduler=None,
                  noise_scheduler=None, guidance_scale: float = 7.5, num_inference_timesteps: int = 50,
-                 eta: float = 0.0, precision: str = "bf16"):
+                 eta: float = 0.0, precision: str = "bf16", vae_precision: Optional[str] = None):
+        """vae_precision: precision of the VAE handle when it differs from the denoiser's (also env
+        CONVOFUSION_B200_VAE_PRECISION).  The decode runs once per pass, so `precision="bf16", vae_precision="fp32"` buys
+        the decoder's fp32 accuracy for the final joints at a few per cent of the pass."""
         super().__init__()
+        vae_precision = vae_precision or os.environ.get("CONVOFUSION_B200_VAE_PRECISION") or precision
         self.denoiser = denoiser if denoiser is not None else default_denoiser(precision)
-        self.vae = vae if vae is not None else default_vae(precision)
+        self.vae = vae if vae is not None else default_vae(vae_precision)
         self.text_audio_encoder = TextAudioController(512)
         self.condition_fuser = TextAudioMotionFuser(512, self.denoiser.latent_dim)
         self.scheduler = scheduler if scheduler is not None else default_scheduler("ddim")
