@@ -42,6 +42,14 @@ def set_bf16_activation_f16(enabled) -> None:
     _lib.check(_lib.lib().cfb_set_bf16_activation_f16(mask))
 
 
+def set_vae_f16(enabled: bool) -> None:
+    """16-bit `ConvoFusionVae` handles: fp16 (default) or bf16 weights and activations.  Read when a module packs its
+    weights: call `vae.pack()` (or change it before the first call) for it to take effect.  Process-wide
+    (cfb_set_vae_f16)."""
+    from . import _lib
+    _lib.check(_lib.lib().cfb_set_vae_f16(int(bool(enabled))))
+
+
 def set_bf16_activation_terms(terms: int) -> None:
     """Shorthand for `set_bf16_activation_sites`: 2 = every site (27), 1 = none (0)."""
     from . import _lib
@@ -50,4 +58,4 @@ def set_bf16_activation_terms(terms: int) -> None:
 __all__ = ["Denoiser", "ConvoFusionVae", "DDIMScheduler", "DDPMScheduler", "ConvoFusionSampler",
            "AudioConvEncoder", "T5TextEncoder", "TextAudioController", "TextAudioMotionFuser",
            "default_denoiser", "default_vae", "default_scheduler", "keypoints3d", "SamplerPool", "MotionWriter", "slice_windows", "window_spans", "window_text",
-           "set_bf16_activation_terms", "set_bf16_activation_sites", "set_bf16_activation_f16"]
+           "set_bf16_activation_terms", "set_bf16_activation_sites", "set_bf16_activation_f16", "set_vae_f16"]

@@ -89,6 +89,8 @@ PROTOTYPES = {
     "cfb_set_bf16_activation_terms": (C.c_int, [_I]),
     "cfb_set_bf16_activation_sites": (C.c_int, [_I]),
     "cfb_set_bf16_activation_f16": (C.c_int, [_I]),
+    "cfb_set_vae_f16": (C.c_int, [_I]),
+    "cfb_get_vae_f16": (C.c_int, []),
     "cfb_launch_count": (C.c_ulonglong, []),
     "cfb_denoiser_create": (C.c_int, [C.POINTER(DenoiserWeights), C.POINTER(_P)]),
     "cfb_denoiser_destroy": (None, [_P]),

@@ -447,11 +447,12 @@ __global__ void __launch_bounds__(256) cross_mma_kernel(const bf16* __restrict__
 // warp.  Used for the denoiser self-attention (16 x 16, head_dim 128) and the VAE attentions (head_dim 64; 128 x 128
 // self, 128 x 8 cross, 18 x 18 encoder).
 // F16: q, k, v hold fp16 (written by an fp16-output GEMM epilogue), the probabilities are rounded to fp16 and both
-// products run as f16 MMAs; the output stays bf16.
+// products run as f16 MMAs; out_f16 selects the output format (bf16 for the denoiser's out_proj, fp16 in the fp16 VAE).
 template <int HD, int NKT, bool F16 = false>
 __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
                                                       const bf16* __restrict__ v, int ldk, bf16* __restrict__ out, int ldo,
-                                                      int Lq, int Lk, const int* __restrict__ kv_len, float scale) {
+                                                      int Lq, int Lk, const int* __restrict__ kv_len, float scale,
+                                                      int out_f16) {
   pdl_sync();
   constexpr int P = HD + 8;                    // bf16 row pitch: rows shift by 16 B -> conflict-free ldmatrix
   constexpr int CH = HD / 8;                   // 16-byte chunks per row
@@ -555,19 +556,19 @@ __global__ void __launch_bounds__(128) mha_mma_kernel(const bf16* __restrict__ q
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) {
     const int col = h * HD + n * 8 + 2 * t;
-    if (r_lo < Lq) *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(b * Lq + r_lo) * ldo + col) = __floats2bfloat162_rn(o[n][0], o[n][1]);
-    if (r_hi < Lq) *reinterpret_cast<__nv_bfloat162*>(out + (size_t)(b * Lq + r_hi) * ldo + col) = __floats2bfloat162_rn(o[n][2], o[n][3]);
+    if (r_lo < Lq) *reinterpret_cast<uint32_t*>(out + (size_t)(b * Lq + r_lo) * ldo + col) = pack16(o[n][0], o[n][1], out_f16);
+    if (r_hi < Lq) *reinterpret_cast<uint32_t*>(out + (size_t)(b * Lq + r_hi) * ldo + col) = pack16(o[n][2], o[n][3], out_f16);
   }
 }
 
 template <int HD, int NKT, bool F16 = false>
 int launch_mha_mma(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
-                   int n_heads, const int* kv_len, cudaStream_t st) {
+                   int n_heads, const int* kv_len, cudaStream_t st, int out_f16 = 0) {
   const int warps = Lq >= 64 ? 4 : ceil_div(Lq, 16);
   const size_t smem = (size_t)(2 * NKT * 16 + warps * 16) * (HD + 8) * 2;
   dim3 grid(n, n_heads, ceil_div(Lq, 64));
   launch_k(mha_mma_kernel<HD, NKT, F16>, grid, warps * 32, smem, st, q, ldq, k, v, ldk, out, ldo, Lq, Lk, kv_len,
-           sqrtf(1.0f / (float)HD));
+           sqrtf(1.0f / (float)HD), out_f16);
   CFB_LAUNCH_CHECK();
   return CFB_OK;
 }
@@ -865,6 +866,7 @@ int init_attention_kernels() {
   if (const char* e = getenv("CFB_MHA_SIMT")) g_mha_simt = atoi(e);
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(mha_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
+  CFB_CUDA(cudaFuncSetAttribute(mha_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
   CFB_CUDA(cudaFuncSetAttribute(cross_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_MAX_SMEM));
@@ -893,23 +895,28 @@ int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, i
         int head_dim, const int* kv_len, cudaStream_t st) {
   if (n <= 0 || debug_skip(2)) return CFB_OK;
   CFB_CHECK(Lq > 0 && Lk > 0 && head_dim > 0 && n_heads > 0, "mha: bad shape");
-  if constexpr (sizeof(T) == 2) {   // bf16: tensor-core kernel (CFB_GEMM_SIMT keeps the CUDA-core engines for cross-checks)
+  constexpr bool HF = std::is_same<T, __half>::value;   // fp16 VAE: f16 MMAs, fp16 output
+  if constexpr (sizeof(T) == 2) {   // 16-bit: tensor-core kernel (CFB_GEMM_SIMT keeps the CUDA-core engines for cross-checks)
     const bool aligned = ldq % 8 == 0 && ldk % 8 == 0 && ldo % 2 == 0 && ((uintptr_t)q % 16 == 0) &&
                          ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 4 == 0);
     if (aligned && g_gemm_backend != CFB_GEMM_SIMT && !g_mha_simt) {
-      if (head_dim == 128 && Lk <= 16) return launch_mha_mma<128, 1>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
-      if (head_dim == 64 && Lk <= 16) return launch_mha_mma<64, 1>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
-      if (head_dim == 64 && Lk <= 32) return launch_mha_mma<64, 2>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
-      if (head_dim == 64 && Lk <= 128) return launch_mha_mma<64, 8>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, kv_len, st);
+      const bf16 *q_ = (const bf16*)q, *k_ = (const bf16*)k, *v_ = (const bf16*)v;
+      bf16* o_ = (bf16*)out;
+      if (head_dim == 128 && Lk <= 16) return launch_mha_mma<128, 1, HF>(q_, ldq, k_, v_, ldk, o_, ldo, n, Lq, Lk, n_heads, kv_len, st, HF);
+      if (head_dim == 64 && Lk <= 16) return launch_mha_mma<64, 1, HF>(q_, ldq, k_, v_, ldk, o_, ldo, n, Lq, Lk, n_heads, kv_len, st, HF);
+      if (head_dim == 64 && Lk <= 32) return launch_mha_mma<64, 2, HF>(q_, ldq, k_, v_, ldk, o_, ldo, n, Lq, Lk, n_heads, kv_len, st, HF);
+      if (head_dim == 64 && Lk <= 128) return launch_mha_mma<64, 8, HF>(q_, ldq, k_, v_, ldk, o_, ldo, n, Lq, Lk, n_heads, kv_len, st, HF);
     }
   }
   // packed self-attention of the denoiser: q, k, v are column blocks of one [rows, 3E] matrix
-  if (Lq == SA_L && Lk == SA_L && head_dim == SA_HD && kv_len == nullptr && ldq == ldk &&
-      k == q + n_heads * head_dim && v == q + 2 * n_heads * head_dim && ldq % 4 == 0 && ldo % 4 == 0) {
-    dim3 grid(n, n_heads);
-    launch_k(self_attn16_kernel<T>, grid, 32, SA_SMEM, st, q, ldq, n_heads * head_dim, out, ldo, n_heads);
-    CFB_LAUNCH_CHECK();
-    return CFB_OK;
+  if constexpr (!HF) {   // (its 16-bit loads / stores are bf16; the fp16 element type takes the generic kernel below)
+    if (Lq == SA_L && Lk == SA_L && head_dim == SA_HD && kv_len == nullptr && ldq == ldk &&
+        k == q + n_heads * head_dim && v == q + 2 * n_heads * head_dim && ldq % 4 == 0 && ldo % 4 == 0) {
+      dim3 grid(n, n_heads);
+      launch_k(self_attn16_kernel<T>, grid, 32, SA_SMEM, st, q, ldq, n_heads * head_dim, out, ldo, n_heads);
+      CFB_LAUNCH_CHECK();
+      return CFB_OK;
+    }
   }
   const size_t smem = ((size_t)Lk * (head_dim + 1) + (size_t)Lk * head_dim + 4 * head_dim + 4 * Lk) * sizeof(float);
   CFB_CHECK(smem <= (size_t)ATT_MAX_SMEM, "mha: Lk=%d head_dim=%d needs %zu B of shared memory", Lk, head_dim, smem);
@@ -921,6 +928,7 @@ int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, i
 }
 template int mha<float>(const float*, int, const float*, const float*, int, float*, int, int, int, int, int, int, const int*, cudaStream_t);
 template int mha<bf16>(const bf16*, int, const bf16*, const bf16*, int, bf16*, int, int, int, int, int, int, const int*, cudaStream_t);
+template int mha<__half>(const __half*, int, const __half*, const __half*, int, __half*, int, int, int, int, int, int, const int*, cudaStream_t);
 
 template <typename T>
 int cross_attention(const T* qx, const T* mem_hat, T* u, const CrossArgs& a, int n_batch, int n_tokens, int d,

@@ -4,6 +4,7 @@
 // kernel does not take (K not a multiple of 64, tiny row counts such as the per-schedule time
 // tables), (3) the on-device cross-check for gemm_tc.cu in tests.  64x64x16 tiles, 256 threads,
 // 4x4 outputs per thread, operands staged transposed in shared memory as float.
+#include <type_traits>
 #include "common.cuh"
 
 namespace cfb {
@@ -21,6 +22,11 @@ __device__ __forceinline__ void load4(const T* __restrict__ base, int ld, int ro
       if constexpr (sizeof(T) == 4) {
         float4 v = *reinterpret_cast<const float4*>(p);
         out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+      } else if constexpr (std::is_same<T, __half>::value) {
+        uint2 v = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&v.x));
+        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&v.y));
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
       } else {
         uint2 v = *reinterpret_cast<const uint2*>(p);
         __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x);
@@ -85,7 +91,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
       for (int c = 0; c < ep.replicate; ++c) {
         const size_t off = (size_t)c * ep.rep_stride + (size_t)r * ep.ldo + n;
         if (ep.out_bf16) {
-          reinterpret_cast<bf16*>(ep.out)[off] = __float2bfloat16_rn(v);
+          if (ep.out_f16) reinterpret_cast<__half*>(ep.out)[off] = from_f32<__half>(v);
+          else reinterpret_cast<bf16*>(ep.out)[off] = __float2bfloat16_rn(v);
         } else {
           float* o = reinterpret_cast<float*>(ep.out) + off;
           *o = ep.accumulate ? (*o + v) : v;
@@ -108,7 +115,10 @@ int gemm_simt(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int
   const int ea = a_bf16 ? 2 : 4, ew = w_bf16 ? 2 : 4;
   const bool vec_a = ((uintptr_t)A % (4 * ea) == 0) && (lda % 4 == 0);
   const bool vec_w = ((uintptr_t)W % (4 * ew) == 0) && (ldw % 4 == 0);
-  if (a_bf16 && w_bf16)
+  CFB_CHECK(!ep.ab_f16 || (a_bf16 && w_bf16), "gemm_simt: fp16 operands must both be 16-bit");
+  if (ep.ab_f16)
+    launch_k(gemm_simt_kernel<__half, __half>, grid, 256, 0, st, (const __half*)A, lda, (const __half*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
+  else if (a_bf16 && w_bf16)
     launch_k(gemm_simt_kernel<bf16, bf16>, grid, 256, 0, st, (const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
   else if (!a_bf16 && !w_bf16)
     launch_k(gemm_simt_kernel<float, float>, grid, 256, 0, st, (const float*)A, lda, (const float*)W, ldw, M, N, K, a_act, vec_a, vec_w, ep);
@@ -129,7 +139,7 @@ int gemm(const void* A, int a_bf16, int lda, const void* W, int w_bf16, int ldw,
     CFB_CHECK(tc_ok, "gemm: tcgen05 backend forced but shape %dx%dx%d (bf16=%d/%d) unsupported", M, N, K, a_bf16, w_bf16);
   if (tc_ok && g_gemm_backend != CFB_GEMM_SIMT)
     return gemm_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, st);
-  CFB_CHECK(ep.a_terms != 2 && !ep.ab_f16, "gemm: a two-term / fp16 A operand needs the tcgen05 path (%dx%dx%d)", M, N, K);
+  CFB_CHECK(ep.a_terms != 2, "gemm: a two-term A operand needs the tcgen05 path (%dx%dx%d)", M, N, K);
   // fp32 operands: three-way bf16 split on the tensor cores when the caller supplies the resources for it
   if (!a_bf16 && !w_bf16 && !a_act && ep.split != nullptr && !ep.out_bf16 && g_gemm_backend != CFB_GEMM_SIMT &&
       gemm_split_supported(M, N, K, lda, ldw))

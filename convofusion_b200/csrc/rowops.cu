@@ -228,8 +228,9 @@ int ln_rows(const float* x, const float* g, const float* b, const float* mod, co
     return CFB_OK;
   }
   if (terms == 3) {      // fp16 values in the bf16 buffer (same layout)
-    CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: fp16 output needs a 16-bit buffer and d = 512");
-    launch_k(ln_rows_kernel<T, 512, 3>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    CFB_CHECK(sizeof(T) == 2 && (d == 512 || d == 128), "ln_rows: fp16 output needs a 16-bit buffer and d = 512 or 128");
+    if (d == 512) launch_k(ln_rows_kernel<T, 512, 3>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    else launch_k(ln_rows_kernel<T, 128, 3>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
     CFB_LAUNCH_CHECK();
     return CFB_OK;
   }
@@ -296,6 +297,7 @@ int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_
 }
 template int concat2<float>(const float*, const float*, float*, int, int, cudaStream_t);
 template int concat2<bf16>(const float*, const float*, bf16*, int, int, cudaStream_t);
+template int concat2<__half>(const float*, const float*, __half*, int, int, cudaStream_t);
 
 template <typename T>
 int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d, cudaStream_t st) {
@@ -306,6 +308,7 @@ int add_pe(const float* src, const float* pe, T* out, int n_batch, int L, int d,
 }
 template int add_pe<float>(const float*, const float*, float*, int, int, int, cudaStream_t);
 template int add_pe<bf16>(const float*, const float*, bf16*, int, int, int, cudaStream_t);
+template int add_pe<__half>(const float*, const float*, __half*, int, int, int, cudaStream_t);
 
 int mask_frames(float* out, const int* lengths, int n_batch, int L, int d, cudaStream_t st) {
   const long long n = (long long)n_batch * L * d;

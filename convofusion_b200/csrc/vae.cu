@@ -4,9 +4,16 @@
 // Rows are clip-major (row = clip * n_frames + frame); the residual stream stays fp32.
 #include "common.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace cfb {
+// 16-bit VAE handles: weights (packed as fp16 by the host when this is set) and activations are fp16, not bf16 -- 11
+// instead of 8 significant bits at the same bytes and MMA rate; the VAE's values are O(1)-O(100) and every store
+// clamps to the fp16 range.  cfb_set_vae_f16 / env CFB_VAE_F16; read when a handle is created (the packer asks
+// cfb_get_vae_f16 at the same moment).  Default 1.
+int g_vae_f16 = getenv("CFB_VAE_F16") ? atoi(getenv("CFB_VAE_F16")) : 1;
 int init_gemm_tc_kernels();
 int init_attention_kernels();
 }
@@ -32,10 +39,20 @@ struct cfb_vae {
   std::vector<cfb_vae_layer> layers[2];
   std::vector<cfb_vae_enc_layer> enc_layers[2];
   int d, L, H, ff, prec;
+  int f16 = 0;     // 16-bit handle whose weights were packed as fp16 (g_vae_f16 at creation)
   VaeBuf h, a, qkv, q, kv, mem, f, cat, skip[2], lens;
 };
 
 namespace {
+
+// T = __half is the fp16 form of the 16-bit handle: same buffers, fp16 payloads, fp16 x fp16 GEMMs / attention
+template <typename T> constexpr int is_h() { return std::is_same<T, __half>::value ? 1 : 0; }
+template <typename T>
+int ln16(const float* x, const float* g, const float* b, T* out, int rows, int d, cudaStream_t st) {
+  if constexpr (std::is_same<T, __half>::value)
+    return ln_rows<bf16>(x, g, b, nullptr, nullptr, 0, reinterpret_cast<bf16*>(out), rows, d, st, 3);
+  else return ln_rows<T>(x, g, b, nullptr, nullptr, 0, out, rows, d, st);
+}
 
 template <typename T>
 int vae_layer(cfb_vae* v, const cfb_vae_layer& w, int n_clips, int n_frames, int n_chunks, cudaStream_t st) {
@@ -45,25 +62,27 @@ int vae_layer(cfb_vae* v, const cfb_vae_layer& w, int n_clips, int n_frames, int
   T* a = v->a.as<T>();
   auto lin_T = [&](const void* A, int rows, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    ep.ab_f16 = ep.out_f16 = is_h<T>();
     return gemm(A, tb, K, W, tb, K, rows, N, K, 0, ep, st);
   };
   auto lin_res = [&](const void* A, int K, const void* W, const float* b) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = h; ep.ldo = d; ep.replicate = 1;
+    ep.ab_f16 = is_h<T>();
     return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
   };
   T* qkv = v->qkv.as<T>();
-  CFB_TRY(ln_rows<T>(h, w.ln1_g, w.ln1_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln16<T>(h, w.ln1_g, w.ln1_b, a, R, d, st));
   CFB_TRY(lin_T(a, R, d, w.w_in, w.b_in, qkv, 3 * d, 0));
   CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_clips, n_frames, n_frames, v->H, d / v->H,
                  v->lens.as<int>(), st));                      // tgt_key_padding_mask = ~mask (vae.py:326)
   CFB_TRY(lin_res(a, d, w.w_so, w.b_so));
-  CFB_TRY(ln_rows<T>(h, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln16<T>(h, w.ln2_g, w.ln2_b, a, R, d, st));
   CFB_TRY(lin_T(a, R, d, w.w_q, w.b_q, v->q.p, d, 0));
   CFB_TRY(lin_T(v->mem.p, Rm, d, w.w_kv, w.b_kv, v->kv.p, 2 * d, 0));
   T* kv = v->kv.as<T>();
   CFB_TRY(mha<T>(v->q.as<T>(), d, kv, kv + d, 2 * d, a, d, n_clips, n_frames, n_chunks, v->H, d / v->H, nullptr, st));
   CFB_TRY(lin_res(a, d, w.w_co, w.b_co));
-  CFB_TRY(ln_rows<T>(h, w.ln3_g, w.ln3_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln16<T>(h, w.ln3_g, w.ln3_b, a, R, d, st));
   CFB_TRY(lin_T(a, R, d, w.w_ff1, w.b_ff1, v->f.p, v->ff, CFB_ACT_GELU));
   return lin_res(v->f.p, v->ff, w.w_ff2, w.b_ff2);
 }
@@ -86,11 +105,13 @@ int vae_decode_part(cfb_vae* v, int part, const float* z_part, int n_clips, int 
   for (int i = 0; i < nb; ++i) {                                                          // :113-120
     CFB_TRY(concat2<T>(h, v->skip[nb - 1 - i].as<float>(), v->cat.as<T>(), R, d, st));
     Epilogue ep{}; ep.bias = dw.b_skip[i]; ep.bias_period = 1; ep.out = h; ep.ldo = d; ep.replicate = 1;
+    ep.ab_f16 = is_h<T>();
     CFB_TRY(gemm(v->cat.p, tb, 2 * d, dw.w_skip[i], tb, 2 * d, R, d, 2 * d, 0, ep, st));
     CFB_TRY(vae_layer<T>(v, v->layers[part][li++], n_clips, n_frames, n_chunks, st));
   }
-  CFB_TRY(ln_rows<T>(h, dw.lnf_g, dw.lnf_b, nullptr, nullptr, 0, v->a.as<T>(), R, d, st));   // :122-123
+  CFB_TRY(ln16<T>(h, dw.lnf_g, dw.lnf_b, v->a.as<T>(), R, d, st));   // :122-123
   Epilogue ep{}; ep.bias = dw.b_final; ep.bias_period = 1; ep.out = out + col_off; ep.ldo = out_ld; ep.replicate = 1;
+  ep.ab_f16 = is_h<T>();
   return gemm(v->a.p, tb, d, dw.w_final, tb, d, R, dw.n_out, d, 0, ep, st);               // vae.py:352-353
 }
 
@@ -103,17 +124,19 @@ int vae_enc_layer(cfb_vae* v, const cfb_vae_enc_layer& w, int n, int L, cudaStre
   T* qkv = v->qkv.as<T>();
   auto lin_T = [&](const void* A, int K, const void* W, const float* b, void* out, int N, int act) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.act = act; ep.out_bf16 = tb; ep.out = out; ep.ldo = N; ep.replicate = 1;
+    ep.ab_f16 = ep.out_f16 = is_h<T>();
     return gemm(A, tb, K, W, tb, K, R, N, K, 0, ep, st);
   };
   auto lin_res = [&](const void* A, int K, const void* W, const float* b) {
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = h; ep.ldo = d; ep.replicate = 1;
+    ep.ab_f16 = is_h<T>();
     return gemm(A, tb, K, W, tb, K, R, d, K, 0, ep, st);
   };
-  CFB_TRY(ln_rows<T>(h, w.ln1_g, w.ln1_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln16<T>(h, w.ln1_g, w.ln1_b, a, R, d, st));
   CFB_TRY(lin_T(a, d, w.w_in, w.b_in, qkv, 3 * d, 0));
   CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n, L, L, v->H, d / v->H, v->lens.as<int>(), st));
   CFB_TRY(lin_res(a, d, w.w_so, w.b_so));
-  CFB_TRY(ln_rows<T>(h, w.ln2_g, w.ln2_b, nullptr, nullptr, 0, a, R, d, st));
+  CFB_TRY(ln16<T>(h, w.ln2_g, w.ln2_b, a, R, d, st));
   CFB_TRY(lin_T(a, d, w.w_ff1, w.b_ff1, v->f.p, v->ff, CFB_ACT_GELU));
   return lin_res(v->f.p, v->ff, w.w_ff2, w.b_ff2);
 }
@@ -139,6 +162,7 @@ int vae_encode_part(cfb_vae* v, int part, const float* feats, int n_feat, int n,
   for (int i = 0; i < nb; ++i) {                                                         // :56-60
     CFB_TRY(concat2<T>(h, v->skip[nb - 1 - i].as<float>(), v->cat.as<T>(), R, d, st));
     Epilogue ep{}; ep.bias = ew.b_skip[i]; ep.bias_period = 1; ep.out = h; ep.ldo = d; ep.replicate = 1;
+    ep.ab_f16 = is_h<T>();
     CFB_TRY(gemm(v->cat.p, tb, 2 * d, ew.w_skip[i], tb, 2 * d, R, d, 2 * d, 0, ep, st));
     CFB_TRY(vae_enc_layer<T>(v, v->enc_layers[part][li++], n, L, st));
   }
@@ -173,12 +197,19 @@ int cfb_vae_create(const cfb_vae_weights* w, cfb_vae** out) {
     }
   }
   v->d = w->d_model; v->L = w->n_layers; v->H = w->n_heads; v->ff = w->ff_size; v->prec = w->precision;
+  v->f16 = (w->precision == CFB_BF16 && g_vae_f16) ? 1 : 0;
   int rc = init_gemm_tc_kernels();
   if (rc == CFB_OK) rc = init_attention_kernels();
   if (rc != CFB_OK) { delete v; return rc; }
   *out = v;
   return CFB_OK;
 }
+
+int cfb_set_vae_f16(int enabled) {
+  g_vae_f16 = enabled ? 1 : 0;
+  return CFB_OK;
+}
+int cfb_get_vae_f16(void) { return g_vae_f16; }
 
 void cfb_vae_destroy(cfb_vae* v) {
   if (!v) return;
@@ -213,7 +244,8 @@ int cfb_vae_decode(cfb_vae* v, const float* z, int n_clips, int n_chunks, int n_
   int col = 0;
   for (int p = 0; p < 2; ++p) {
     const float* zp = z + (size_t)p * Rm * d;     // torch.chunk(z, 2, dim=0), vae.py:279
-    if (v->prec == CFB_BF16) CFB_TRY(vae_decode_part<bf16>(v, p, zp, n_clips, n_chunks, n_frames, out, n_out, col, st));
+    if (v->prec == CFB_BF16 && v->f16) CFB_TRY(vae_decode_part<__half>(v, p, zp, n_clips, n_chunks, n_frames, out, n_out, col, st));
+    else if (v->prec == CFB_BF16) CFB_TRY(vae_decode_part<bf16>(v, p, zp, n_clips, n_chunks, n_frames, out, n_out, col, st));
     else CFB_TRY(vae_decode_part<float>(v, p, zp, n_clips, n_chunks, n_frames, out, n_out, col, st));
     col += v->w.part[p].n_out;
   }
@@ -255,7 +287,8 @@ int cfb_vae_encode(cfb_vae* v, const float* features, int n_clips, int n_frames,
   for (int p = 0; p < 2; ++p) {
     float* mu = mu_out + (size_t)p * n * d;        // torch.cat((b_mu, h_mu), axis=0), vae.py:254-255
     float* sd = std_out + (size_t)p * n * d;
-    if (v->prec == CFB_BF16) CFB_TRY(vae_encode_part<bf16>(v, p, feats_out, n_feat, n, mu, sd, st));
+    if (v->prec == CFB_BF16 && v->f16) CFB_TRY(vae_encode_part<__half>(v, p, feats_out, n_feat, n, mu, sd, st));
+    else if (v->prec == CFB_BF16) CFB_TRY(vae_encode_part<bf16>(v, p, feats_out, n_feat, n, mu, sd, st));
     else CFB_TRY(vae_encode_part<float>(v, p, feats_out, n_feat, n, mu, sd, st));
   }
   return CFB_OK;

@@ -25,11 +25,12 @@ STREAMS = ("spkemb", "alsn", "tlsn", "apb", "lsnemb")
 
 
 class _Packer:
-    def __init__(self, device, precision):
-        self.device, self.precision, self.keep = device, precision, []
+    def __init__(self, device, precision, f16: bool = False):
+        self.device, self.precision, self.keep, self.f16 = device, precision, [], f16
 
     def mat(self, t: Tensor) -> int:
-        dt = torch.bfloat16 if self.precision == _lib.BF16 else torch.float32
+        # 16-bit handles: bf16, or fp16 where the handle's kernels take fp16 operands (the VAE, cfb_get_vae_f16)
+        dt = (torch.float16 if self.f16 else torch.bfloat16) if self.precision == _lib.BF16 else torch.float32
         t = t.detach().to(dtype=dt).contiguous().to(self.device)
         self.keep.append(t)
         return t.data_ptr()
@@ -120,7 +121,8 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
 
 def pack_vae(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: int, ff: int, precision: int, device) -> dict:
     p = prefix
-    pk = _Packer(device, precision)
+    # the handle created right after this call reads the same switch (cfb_vae_create)
+    pk = _Packer(device, precision, f16=bool(_lib.lib().cfb_get_vae_f16()))
     d = sd[p + "body_final_layer.weight"].shape[1]
     nb = (n_layers - 1) // 2
     w = _lib.VaeWeights()

@@ -286,6 +286,13 @@ typedef struct {
 
 typedef struct cfb_vae cfb_vae;
 int cfb_vae_create(const cfb_vae_weights *w, cfb_vae **out);
+/* 16-bit VAE handles (precision = CFB_BF16): 1 (default, also env CFB_VAE_F16) = weights and activations are fp16
+ * instead of bf16 -- the host packs the matrices as fp16 (ask cfb_get_vae_f16 when packing), GEMMs run tcgen05.mma
+ * kind::f16 on f16 operands, the attention kernels their f16 mma.sync form; 11 instead of 8 significant bits at the
+ * same bytes and speed (decode max-relative error 6.6e-3 -> see DESIGN.md section 2).  The VAE has no guidance
+ * amplification, so here the weight format matters as much as the activations'.  Read when a handle is created. */
+int cfb_set_vae_f16(int enabled);
+int cfb_get_vae_f16(void);
 void cfb_vae_destroy(cfb_vae *h);
 /* z [2, B, n_chunks, d] float; lengths host [B]; out [B, n_frames, n_out_body+n_out_hands]. */
 int cfb_vae_decode(cfb_vae *h, const float *z, int n_clips, int n_chunks, int n_frames,
