@@ -94,6 +94,7 @@ PROTOTYPES = {
     "cfb_launch_count": (C.c_ulonglong, []),
     "cfb_denoiser_create": (C.c_int, [C.POINTER(DenoiserWeights), C.POINTER(_P)]),
     "cfb_denoiser_destroy": (None, [_P]),
+    "cfb_denoiser_attach_f16_weights": (C.c_int, [_P, C.POINTER(DenoiserWeights)]),
     "cfb_denoiser_set_chains": (C.c_int, [_P, C.c_int]),
     "cfb_denoiser_forward": (C.c_int, [_P, _P, _I, _LL, C.POINTER(Memory), _P, C.POINTER(_P), _P]),
     "cfb_denoiser_weg_forward": (C.c_int, [_P, _P, _I, _LL, C.POINTER(Memory), _I, _P, _P]),

@@ -877,17 +877,17 @@ int init_attention_kernels() {
   return CFB_OK;
 }
 
-// Self-attention on fp16 q / k / v (the denoiser's 16 x 16, head_dim 128 case on the mma.sync kernel); bf16 output.
+// Self-attention on fp16 q / k / v (the denoiser's 16 x 16, head_dim 128 case on the mma.sync kernel); bf16 or fp16 output.
 bool mha_f16_supported(int Lk, int head_dim) {
   return head_dim == 128 && Lk <= 16 && g_gemm_backend != CFB_GEMM_SIMT && !g_mha_simt;
 }
 int mha_f16(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
-            int n_heads, int head_dim, cudaStream_t st) {
+            int n_heads, int head_dim, cudaStream_t st, int out_f16) {
   if (n <= 0 || debug_skip(2)) return CFB_OK;
   const bool aligned = ldq % 8 == 0 && ldk % 8 == 0 && ldo % 2 == 0 && ((uintptr_t)q % 16 == 0) &&
                        ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ((uintptr_t)out % 4 == 0);
   CFB_CHECK(aligned && mha_f16_supported(Lk, head_dim), "mha_f16: unsupported (Lk=%d head_dim=%d)", Lk, head_dim);
-  return launch_mha_mma<128, 1, true>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, nullptr, st);
+  return launch_mha_mma<128, 1, true>(q, ldq, k, v, ldk, out, ldo, n, Lq, Lk, n_heads, nullptr, st, out_f16);
 }
 
 template <typename T>

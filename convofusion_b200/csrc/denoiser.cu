@@ -114,7 +114,7 @@ struct cfb_denoiser {
   size_t split_row_bytes = 0, split_a_bytes = 0, split_w_bytes = 0;
   bool fp32_tc = false;
   int act_f16 = 0;        // bf16: operand groups kept as fp16 (g_bf16_act_f16 at the last reserve_rows)
-  struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1, *w_fu, *w_qx; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
+  struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1, *w_fu, *w_qx, *w_so, *w_ff2; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
   std::vector<W16> l16;
   const bf16* w_out16 = nullptr;
   const bf16 *w_zx16[CFB_N_STREAMS] = {}, *w_yx16[CFB_N_STREAMS] = {};   // memory-side pre-projections [L d, d]
@@ -439,7 +439,9 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   const int uc_f16 = ((fm & 2) && !g_cross_tc) ? 1 : 0;
   const int pv_f16 = (fm & 2) ? 1 : 0;                                   // shared-slot probabilities x per-step values
   const int self_f16 = ((fm & 8) && mha_f16_supported(h->ntok, d / h->H)) ? 1 : 0;   // q / k / v of the self-attention
-  const int F16_SITES = ((fm & 1) ? (1 | 2 | 8 | 16) : 0) | ((fm & 4) ? 4 : 0) | (uc_f16 ? 128 : 0);
+  // 32 = the self-attention output feeding out_proj (fp16 when its kernel runs in fp16), 64 = the GELU output feeding
+  // linear2: nothing measurable as activations, but their GEMMs then meet the fp16 weights too
+  const int F16_SITES = ((fm & 1) ? (1 | 2 | 8 | 16 | 64) : 0) | ((fm & 4) ? 4 : 0) | (uc_f16 ? 128 : 0) | (self_f16 ? 32 : 0);
   const int pr_f16 = tb ? pair_f16(h) : 0;                                 // queries / memory of the per-pair attention
   ca.out_f16 = uc_f16; ca.in_f16 = pr_f16;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
@@ -449,7 +451,9 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   T* a = a_abs + (size_t)row0 * d;
   T* a2 = sites ? h->a2.as<T>() + (size_t)row0 * 2 * d : nullptr;
   auto ln_to = [&](int site, const float* ln_g, const float* ln_b, const float* mod) {   // LayerNorm for consumer `site`
-    return (sites & site) ? ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a2, R, d, st, 2)
+    // (two-term sites take fp16 terms and the fp16 weights when their group is on: 22 significant bits)
+    return (sites & site) ? ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a2, R, d, st,
+                                       (site & F16_SITES) ? 4 : 2)
                           : ln_rows<T>(hres, ln_g, ln_b, mod, mod ? step_ptr : nullptr, mod_stride, a, R, d, st,
                                        (site & F16_SITES) ? 3 : 1);
   };
@@ -476,7 +480,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     ep.out_f16 = out_f16;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = site;
     const int at = (sites & site) ? 2 : 1;
-    ep.a_terms = at; ep.ab_f16 = (at == 1 && (site & F16_SITES)) ? 1 : 0;
+    ep.a_terms = at; ep.ab_f16 = (site & F16_SITES) ? 1 : 0;
     if (ep.ab_f16) W = W16;
     return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * K, W, tb, K, R, N, K, 0, ep, st);
   };
@@ -490,7 +494,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     Epilogue ep{}; ep.bias = b; ep.bias_period = 1; ep.accumulate = 1; ep.out = hres; ep.ldo = d; ep.replicate = 1;
     ep.split = scm; ep.w_static = 1; ep.a_from_ln = a_site;
     const int at = (a_site && (sites & a_site)) ? 2 : 1;
-    ep.a_terms = at; ep.ab_f16 = (at == 1 && (a_site & F16_SITES)) ? 1 : 0;
+    ep.a_terms = at; ep.ab_f16 = (a_site & F16_SITES) ? 1 : 0;
     if (ep.ab_f16) W = W16;
     CFB_TRY(gemm(at == 2 ? (const void*)a2 : A, tb, at * K, W, tb, K, R, d, K, 0, ep, st));
     CFB_TRY(ln_to(next_site, ln_g, ln_b, mod));
@@ -506,14 +510,14 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     CFB_TRY(lin_T(d, w.w_in, w16.w_in, w.b_in, qkv, 3 * d, 0, 1, self_f16));
     if (self_f16) {
       if constexpr (tb)
-        CFB_TRY(mha_f16(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, st));
+        CFB_TRY(mha_f16(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, st, 1));
     } else {
       CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
     }
     if (rb & 1) {   // out_proj -> time_block1 -> norm2 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 0, row0, R, R_total, step_ptr, st));
     } else {
-      CFB_TRY(lin_res_ln(a, d, w.w_so, nullptr, w.b_so, w.tb1_g, w.tb1_b, mod1, 32, 2));              // + time_block1 prologue (:575)
+      CFB_TRY(lin_res_ln(a, d, w.w_so, w16.w_so, w.b_so, w.tb1_g, w.tb1_b, mod1, 32, 2));              // + time_block1 prologue (:575)
       CFB_TRY(lin_res_ln(a, d, w.w_tb1, w16.w_tb1, w.b_tb1, w.ln2_g, w.ln2_b, nullptr, 2, 4));       // + norm2 (:578)
     }
     // five cross-attentions + att_fuser (:578-652), folded; a = norm2(h)
@@ -628,12 +632,12 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     }
     if (!rb2_done) CFB_TRY(lin_res_ln(a, d, w.w_tb2, w16.w_tb2, w.b_tb2, w.ln3_g, w.ln3_b, nullptr, 2, 8));   // + norm3 (:659)
     // feed-forward (:659-661); the update carries the next layer's norm1 (or the final decoder.norm)
-    CFB_TRY(lin_T(d, w.w_ff1, w16.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU, 8));
+    CFB_TRY(lin_T(d, w.w_ff1, w16.w_ff1, w.b_ff1, f, h->ff, CFB_ACT_GELU, 8, (F16_SITES & 64) ? 1 : 0));
     const bool last = l + 1 == h->L;
     if ((rb & 4) && !(last && (sites & 16))) {   // linear2 -> next norm1 on resident rows (rowblock.cu)
       CFB_TRY(rowblock_run(h, l, 2, row0, R, R_total, step_ptr, st));
     } else {
-      CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, nullptr, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
+      CFB_TRY(lin_res_ln(f, h->ff, w.w_ff2, w16.w_ff2, w.b_ff2, last ? h->w.lnf_g : h->layers[l + 1].ln1_g,
                          last ? h->w.lnf_b : h->layers[l + 1].ln1_b, nullptr, 64, last ? 16 : 1));
     }
   }
@@ -641,7 +645,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   Epilogue ep{}; ep.bias = h->w.b_out; ep.bias_period = 1; ep.out = eps_out; ep.ldo = h->lat; ep.replicate = 1;
   ep.split = scm; ep.w_static = 1; ep.a_from_ln = 16;
   const int at = (sites & 16) ? 2 : 1;
-  ep.a_terms = at; ep.ab_f16 = (at == 1 && (F16_SITES & 16)) ? 1 : 0;
+  ep.a_terms = at; ep.ab_f16 = (F16_SITES & 16) ? 1 : 0;
   return gemm(at == 2 ? (const void*)a2 : (const void*)a, tb, at * d, ep.ab_f16 ? (const void*)h->w_out16 : h->w.w_out, tb, d,
               R, h->lat, d, 0, ep, st);
 }
@@ -885,7 +889,7 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
   // fp16 copies of the weights fed by LayerNorm outputs (g_bf16_act_f16): qkv, TimeBlock linears, linear1, latent_proj
   if (rc == CFB_OK && h->prec == CFB_BF16) {
     auto make16 = [&]() -> int {
-      const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = (5 + 2 * CFB_N_STREAMS) * d2 + ffd;
+      const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = (6 + 2 * CFB_N_STREAMS) * d2 + 2 * ffd;
       const size_t outn = (size_t)h->lat * h->d;
       const size_t pre = (size_t)h->L * d2;
       CFB_TRY(h->w16.reserve((per * h->L + outn + 2 * CFB_N_STREAMS * pre) * 2, nullptr));
@@ -903,6 +907,8 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
         CFB_TRY(conv(h->layers[l].w_ff1, ffd, &h->l16[l].w_ff1));
         CFB_TRY(conv(h->layers[l].w_fu, CFB_N_STREAMS * d2, &h->l16[l].w_fu));
         CFB_TRY(conv(h->layers[l].w_qx, CFB_N_STREAMS * d2, &h->l16[l].w_qx));
+        CFB_TRY(conv(h->layers[l].w_so, d2, &h->l16[l].w_so));
+        CFB_TRY(conv(h->layers[l].w_ff2, ffd, &h->l16[l].w_ff2));
       }
       CFB_TRY(conv(h->w.w_out, outn, &h->w_out16));
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
@@ -962,6 +968,31 @@ int cfb_set_fp32_tensor_cores(int mode) {
 int cfb_set_bf16_activation_terms(int terms) {   // 2: every site, 1: none
   CFB_CHECK(terms == 1 || terms == 2, "cfb_set_bf16_activation_terms: %d (1 or 2)", terms);
   g_bf16_act_sites = terms == 2 ? 27 : 0;
+  return CFB_OK;
+}
+
+int cfb_denoiser_attach_f16_weights(cfb_denoiser* h, const cfb_denoiser_weights* w16) {
+  CFB_CHECK(h && w16 && w16->layers, "cfb_denoiser_attach_f16_weights: null argument");
+  CFB_CHECK(h->prec == CFB_BF16, "cfb_denoiser_attach_f16_weights: the handle is not a 16-bit handle");
+  CFB_CHECK(w16->n_layers == h->L && w16->d_model == h->d && w16->ff_size == h->ff && w16->latent_dim == h->lat,
+            "cfb_denoiser_attach_f16_weights: shape mismatch");
+  h->l16.resize(h->L);
+  for (int l = 0; l < h->L; ++l) {
+    const cfb_denoiser_layer& s = w16->layers[l];
+    CFB_CHECK(s.w_in && s.w_so && s.w_tb1 && s.w_tb2 && s.w_qx && s.w_fu && s.w_ff1 && s.w_ff2,
+              "cfb_denoiser_attach_f16_weights: layer %d lacks a matrix", l);
+    h->l16[l] = cfb_denoiser::W16{(const bf16*)s.w_in, (const bf16*)s.w_tb1, (const bf16*)s.w_tb2, (const bf16*)s.w_ff1,
+                                  (const bf16*)s.w_fu, (const bf16*)s.w_qx, (const bf16*)s.w_so, (const bf16*)s.w_ff2};
+  }
+  CFB_CHECK(w16->w_out, "cfb_denoiser_attach_f16_weights: latent_proj missing");
+  h->w_out16 = (const bf16*)w16->w_out;
+  for (int x = 0; x < CFB_N_STREAMS; ++x) {
+    CFB_CHECK(w16->w_zx[x] && w16->w_yx[x], "cfb_denoiser_attach_f16_weights: pre-projection %d missing", x);
+    h->w_zx16[x] = (const bf16*)w16->w_zx[x]; h->w_yx16[x] = (const bf16*)w16->w_yx[x];
+  }
+  h->w16.release();   // (cudaFree synchronises: the conversions of cfb_denoiser_create have long finished)
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured pointers are stale
+  h->graph_valid = false;
   return CFB_OK;
 }
 

@@ -32,10 +32,10 @@ int enc_dist(const float* y, float* mu, float* sd, int n, int L, int d, cudaStre
 template <typename T>
 int mha(const T* q, int ldq, const T* k, const T* v, int ldk, T* out, int ldo, int n, int Lq, int Lk, int n_heads,
         int head_dim, const int* kv_len, cudaStream_t st);
-// bf16 handles with fp16 activations: q / k / v hold fp16, output bf16 (attention.cu)
+// bf16 handles with fp16 activations: q / k / v hold fp16, output bf16 or fp16 (attention.cu)
 bool mha_f16_supported(int Lk, int head_dim);
 int mha_f16(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldk, bf16* out, int ldo, int n, int Lq, int Lk,
-            int n_heads, int head_dim, cudaStream_t st);
+            int n_heads, int head_dim, cudaStream_t st, int out_f16 = 0);
 
 // The denoiser's five folded single-head cross-attentions for every (batch entry, stream):
 //   P = softmax(qx[bs, x] . mem_hat[slot]^T + mask),  u[bs, x] = P . mem_hat[slot]

@@ -12,7 +12,7 @@ namespace cfb {
 namespace {
 
 // out = LN(x) * g + b  [ * (1 + scale) + shift -> SiLU ]           (cross_attention.py:437-438)
-// OUT: 1 = T, 2 = two bf16 terms [hi | lo] (LN_OUT_SPLIT), 3 = fp16 in the bf16 buffer (LN_OUT_F16)
+// OUT: 1 = T, 2 = two bf16 terms [hi | lo], 3 = fp16 in the bf16 buffer, 4 = two fp16 terms [hi | lo]
 template <typename T, int D, int OUT = 1>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       const float* __restrict__ b, const float* __restrict__ mod,
@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   RowVec<D> r;
   r.load(x + (size_t)row * D, lane);
   ln_row_finish<D, sizeof(T) == 2>(r, g, b, mod ? mod + (step_ptr ? (size_t)(*step_ptr) * mod_step_stride : 0) : nullptr, lane);
-  if constexpr (OUT == 2 && sizeof(T) == 2) r.store_split(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
+  if constexpr (OUT == 2 && sizeof(T) == 2) r.template store_split<false>(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
+  else if constexpr (OUT == 4 && sizeof(T) == 2) r.template store_split<true>(reinterpret_cast<bf16*>(out) + (size_t)row * 2 * D, lane);
   else if constexpr (OUT == 3 && sizeof(T) == 2) r.store_f16(reinterpret_cast<bf16*>(out) + (size_t)row * D, lane);
   else r.store(out + (size_t)row * D, lane);
 }
@@ -221,9 +222,10 @@ int ln_rows(const float* x, const float* g, const float* b, const float* mod, co
             long long mod_step_stride, T* out, int rows, int d, cudaStream_t st, int terms) {
   if (rows <= 0 || debug_skip(1)) return CFB_OK;
   dim3 grid(ceil_div(rows, 8));
-  if (terms == 2) {      // [hi | lo] per 64 columns, row stride 2 d (bf16 outputs of the denoiser only)
-    CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: two-term output needs bf16 and d = 512");
-    launch_k(ln_rows_kernel<T, 512, 2>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+  if (terms == 2 || terms == 4) {      // [hi | lo] per 64 columns, row stride 2 d (16-bit outputs of the denoiser only); 4: fp16 terms
+    CFB_CHECK(sizeof(T) == 2 && d == 512, "ln_rows: two-term output needs a 16-bit buffer and d = 512");
+    if (terms == 2) launch_k(ln_rows_kernel<T, 512, 2>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
+    else launch_k(ln_rows_kernel<T, 512, 4>, grid, 256, 0, st, x, g, b, mod, step_ptr, mod_step_stride, out, rows);
     CFB_LAUNCH_CHECK();
     return CFB_OK;
   }

@@ -88,18 +88,31 @@ struct RowVec {
   }
   // Two bf16 terms per value (hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits), laid out [hi(64) | lo(64)] per 64
   // columns with a row stride of 2 D -- the A operand of the tcgen05 GEMM's two-term mode (gemm_tc.cu, A2).
+  // F16: both terms are fp16 (hi = fp16(v), lo = fp16(v - hi): 22 significant bits) for an all-f16 GEMM.
+  template <bool F16 = false>
   __device__ __forceinline__ void store_split(bf16* __restrict__ row, int lane) const {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 128 + lane * 4;
       bf16* dst = row + (c >> 6) * 128 + (c & 63);
       uint2 hi, lo;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 4], v[i * 4 + 1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 4 + 2], v[i * 4 + 3]);
-      __nv_bfloat162 l0 = __floats2bfloat162_rn(v[i * 4] - __low2float(h0), v[i * 4 + 1] - __high2float(h0));
-      __nv_bfloat162 l1 = __floats2bfloat162_rn(v[i * 4 + 2] - __low2float(h1), v[i * 4 + 3] - __high2float(h1));
-      hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
-      lo.x = *reinterpret_cast<uint32_t*>(&l0); lo.y = *reinterpret_cast<uint32_t*>(&l1);
+      if constexpr (F16) {
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = fminf(fmaxf(v[i * 4 + j], -65504.f), 65504.f);
+        const __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
+        const __half2 l0 = __floats2half2_rn(w[0] - __low2float(h0), w[1] - __high2float(h0));
+        const __half2 l1 = __floats2half2_rn(w[2] - __low2float(h1), w[3] - __high2float(h1));
+        hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+      } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 4], v[i * 4 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 4 + 2], v[i * 4 + 3]);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v[i * 4] - __low2float(h0), v[i * 4 + 1] - __high2float(h0));
+        __nv_bfloat162 l1 = __floats2bfloat162_rn(v[i * 4 + 2] - __low2float(h1), v[i * 4 + 3] - __high2float(h1));
+        hi.x = *reinterpret_cast<uint32_t*>(&h0); hi.y = *reinterpret_cast<uint32_t*>(&h1);
+        lo.x = *reinterpret_cast<uint32_t*>(&l0); lo.y = *reinterpret_cast<uint32_t*>(&l1);
+      }
       *reinterpret_cast<uint2*>(dst) = hi;
       *reinterpret_cast<uint2*>(dst + 64) = lo;
     }

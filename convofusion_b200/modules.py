@@ -274,6 +274,12 @@ class Denoiser(_CudaModule):
     def _create(self, packed):
         h = C.c_void_p()
         _lib.check(_lib.lib().cfb_denoiser_create(C.byref(packed["struct"]), C.byref(h)))
+        if "struct16" in packed:      # 16-bit handles: fp16 matrices packed from the fp32 parameters (pack.py)
+            try:
+                _lib.check(_lib.lib().cfb_denoiser_attach_f16_weights(h, C.byref(packed["struct16"])))
+            except Exception:
+                _lib.lib().cfb_denoiser_destroy(h)
+                raise
         return h
 
     def pack(self):

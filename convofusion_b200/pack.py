@@ -67,6 +67,15 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
                   device) -> dict:
     p = prefix
     pk = _Packer(device, precision)
+    # 16-bit handles: every matrix is packed twice from the fp32 state_dict -- bf16 (the handle's own weights) and fp16
+    # (cfb_denoiser_attach_f16_weights: the operand of the fp16 x fp16 products, 11 instead of 8 significant bits)
+    pk16 = _Packer(device, precision, f16=True) if precision == _lib.BF16 else None
+    layers16 = (_lib.DenoiserLayer * n_layers)() if pk16 else None
+
+    def mat2(t, obj16, field):
+        if pk16 is not None:
+            setattr(obj16, field, pk16.mat(t))
+        return pk.mat(t)
     d, lat = sd[p + "latent_embd.weight"].shape
     ff = sd[p + "decoder.layers.0.linear1.weight"].shape[0]
     layers = (_lib.DenoiserLayer * n_layers)()
@@ -75,29 +84,31 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
     for l in range(n_layers):
         lp = f"{p}decoder.layers.{l}."
         L = layers[l]
+        L16 = layers16[l] if pk16 else None
         L.ln1_g, L.ln1_b = pk.vec(sd[lp + "norm1.weight"]), pk.vec(sd[lp + "norm1.bias"])
-        L.w_in, L.b_in = pk.mat(sd[lp + "self_attn.in_proj_weight"]), pk.vec(sd[lp + "self_attn.in_proj_bias"])
-        L.w_so, L.b_so = pk.mat(sd[lp + "self_attn.out_proj.weight"]), pk.vec(sd[lp + "self_attn.out_proj.bias"])
+        L.w_in, L.b_in = mat2(sd[lp + "self_attn.in_proj_weight"], L16, "w_in"), pk.vec(sd[lp + "self_attn.in_proj_bias"])
+        L.w_so, L.b_so = mat2(sd[lp + "self_attn.out_proj.weight"], L16, "w_so"), pk.vec(sd[lp + "self_attn.out_proj.bias"])
         L.tb1_g, L.tb1_b = pk.vec(sd[lp + "time_block1.norm.weight"]), pk.vec(sd[lp + "time_block1.norm.bias"])
-        L.w_tb1 = pk.mat(sd[lp + "time_block1.out_layers.2.weight"])
+        L.w_tb1 = mat2(sd[lp + "time_block1.out_layers.2.weight"], L16, "w_tb1")
         L.b_tb1 = pk.vec(sd[lp + "time_block1.out_layers.2.bias"])
         L.ln2_g, L.ln2_b = pk.vec(sd[lp + "norm2.weight"]), pk.vec(sd[lp + "norm2.bias"])
         w_qx, b_qx, w_fu, b_fu = fold_cross_attention(sd, lp, d)
-        L.w_qx, L.b_qx, L.w_fu, L.b_fu = pk.mat(w_qx), pk.vec(b_qx), pk.mat(w_fu), pk.vec(b_fu)
+        L.w_qx, L.b_qx, L.w_fu, L.b_fu = mat2(w_qx, L16, "w_qx"), pk.vec(b_qx), mat2(w_fu, L16, "w_fu"), pk.vec(b_fu)
         for x in range(len(STREAMS)):
             zx[x].append(w_qx[x * d:(x + 1) * d].T)          # A_x^T: memory row -> key in query space
             az[x].append(b_qx[x * d:(x + 1) * d][None, :])
             yx[x].append(w_fu[:, x * d:(x + 1) * d])         # G_x: memory row -> its residual contribution
         L.tb2_g, L.tb2_b = pk.vec(sd[lp + "time_block2.norm.weight"]), pk.vec(sd[lp + "time_block2.norm.bias"])
-        L.w_tb2 = pk.mat(sd[lp + "time_block2.out_layers.2.weight"])
+        L.w_tb2 = mat2(sd[lp + "time_block2.out_layers.2.weight"], L16, "w_tb2")
         L.b_tb2 = pk.vec(sd[lp + "time_block2.out_layers.2.bias"])
         L.ln3_g, L.ln3_b = pk.vec(sd[lp + "norm3.weight"]), pk.vec(sd[lp + "norm3.bias"])
-        L.w_ff1, L.b_ff1 = pk.mat(sd[lp + "linear1.weight"]), pk.vec(sd[lp + "linear1.bias"])
-        L.w_ff2, L.b_ff2 = pk.mat(sd[lp + "linear2.weight"]), pk.vec(sd[lp + "linear2.bias"])
+        L.w_ff1, L.b_ff1 = mat2(sd[lp + "linear1.weight"], L16, "w_ff1"), pk.vec(sd[lp + "linear1.bias"])
+        L.w_ff2, L.b_ff2 = mat2(sd[lp + "linear2.weight"], L16, "w_ff2"), pk.vec(sd[lp + "linear2.bias"])
         for tb in ("time_block1", "time_block2"):
             tbw.append(sd[lp + f"{tb}.emb_layers.1.weight"].detach().float().cpu())
             tbb.append(sd[lp + f"{tb}.emb_layers.1.bias"].detach().float().cpu())
     w = _lib.DenoiserWeights()
+    w16 = _lib.DenoiserWeights() if pk16 else None
     pe_q = sd[p + "query_pos.pe"].detach().float().cpu()[:, 0]
     pe_m = sd[p + "mem_pos.pe"].detach().float().cpu()[:, 0]
     bh = sd[p + "bh_embedding.weight"].detach().float().cpu()
@@ -112,11 +123,20 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
     w.w_tbmod, w.b_tbmod = pk.vec(torch.cat(tbw, 0)), pk.vec(torch.cat(tbb, 0))
     w.stream_emb, w.pe_mem = pk.vec(sd[p + "condition_embedding.weight"]), pk.vec(pe_m)
     w.lnf_g, w.lnf_b = pk.vec(sd[p + "decoder.norm.weight"]), pk.vec(sd[p + "decoder.norm.bias"])
-    w.w_out, w.b_out = pk.mat(sd[p + "latent_proj.weight"]), pk.vec(sd[p + "latent_proj.bias"])
+    w.w_out, w.b_out = mat2(sd[p + "latent_proj.weight"], w16, "w_out"), pk.vec(sd[p + "latent_proj.bias"])
     for x in range(len(STREAMS)):
-        w.w_zx[x], w.a_zx[x], w.w_yx[x] = pk.mat(torch.cat(zx[x], 0)), pk.vec(torch.cat(az[x], 0)), pk.mat(torch.cat(yx[x], 0))
+        zcat, ycat = torch.cat(zx[x], 0), torch.cat(yx[x], 0)
+        w.w_zx[x], w.a_zx[x], w.w_yx[x] = pk.mat(zcat), pk.vec(torch.cat(az[x], 0)), pk.mat(ycat)
+        if pk16 is not None:
+            w16.w_zx[x], w16.w_yx[x] = pk16.mat(zcat), pk16.mat(ycat)
     w.layers = C.cast(layers, C.POINTER(_lib.DenoiserLayer))
-    return {"struct": w, "layers": layers, "keep": pk.keep}
+    out = {"struct": w, "layers": layers, "keep": pk.keep}
+    if pk16 is not None:
+        w16.d_model, w16.latent_dim, w16.n_tokens, w16.n_layers, w16.n_heads, w16.ff_size = d, lat, n_tokens, n_layers, n_heads, ff
+        w16.precision, w16.pe_len = precision, pe_m.shape[0]
+        w16.layers = C.cast(layers16, C.POINTER(_lib.DenoiserLayer))
+        out.update({"struct16": w16, "layers16": layers16, "keep16": pk16.keep})
+    return out
 
 
 def pack_vae(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: int, ff: int, precision: int, device) -> dict:

@@ -165,6 +165,12 @@ typedef struct {
 typedef struct cfb_denoiser cfb_denoiser;
 
 int cfb_denoiser_create(const cfb_denoiser_weights *w, cfb_denoiser **out);
+/* 16-bit handles: a second copy of the weight matrices in fp16, packed by the host FROM THE FP32 state_dict (same
+ * struct, `precision` ignored, only the matrix pointers are read: layers[].w_in / w_so / w_tb1 / w_tb2 / w_qx / w_fu /
+ * w_ff1 / w_ff2, w_out, w_zx[], w_yx[]; the tensors must outlive the handle).  The fp16 x fp16 products of
+ * cfb_set_bf16_activation_f16 then meet weights with 11 significant bits; without this call the handle uses fp16
+ * conversions of its bf16 weights (8 bits).  Invalidates the handle's captured graph. */
+int cfb_denoiser_attach_f16_weights(cfb_denoiser *h, const cfb_denoiser_weights *w16);
 void cfb_denoiser_destroy(cfb_denoiser *h);
 
 /* Concurrent chains of one captured sampling step: the guidance batch is cut into n_chains independent

@@ -17,18 +17,20 @@ from helpers import SCHED_KW, frac_within, golden, max_rel, oracle_batch, oracle
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# bf16 mode: operands of every GEMM and the attention memory are 16-bit -- bf16 weights, and since late round 2 fp16
-# (11 instead of 8 significant bits, same bytes) for every activation operand (cfb_set_bf16_activation_f16, default all
-# groups) plus a second bf16 term for latent_proj's input (cfb_set_bf16_activation_sites, default 16); residual
-# stream, LayerNorm statistics, softmax, guidance combine and scheduler stay fp32.  Measured on the B200 (round 2,
-# profiles/r02_pytest_gpu_full.log): one denoiser evaluation 2.6-3.0e-3 relative L2 (weight rounding, common to all
-# branches); the -36.5/+7.5 guidance weights amplify branch-differential rounding and random-init weights make the
-# trajectory chaotic, so over 50 DDIM steps the latents drift to 0.017 relative L2 (0.005 after the first step; 0.195 /
-# 0.060 with bf16 activations, the round-1 state) with every element within 5e-2 of the tensor scale at every step,
-# and the decoded joints land within 3.4e-3 max-relative (the 16-bit VAE is fp16 throughout, cfb_set_vae_f16: 7.7e-4 on
-# its own; 6.6e-3 in its bf16 form).  Every entry is at most ~2x its measured value.
-BF16_TOL = {"eps_l2": 6e-3, "latent_frac_tol": 5e-2, "latent_frac": 0.98, "latent_l2": 0.035, "joints": 7e-3,
-            "latent_frac90_tol": 0.3}
+# bf16 mode (the 16-bit mode): operands of every GEMM and the attention memory are 16-bit.  Since late round 2 the
+# activation operands are fp16 (11 instead of 8 significant bits, same bytes; cfb_set_bf16_activation_f16, default all
+# groups) and meet fp16 matrices packed from the fp32 state_dict (cfb_denoiser_attach_f16_weights); latent_proj's input
+# carries two fp16 terms (cfb_set_bf16_activation_sites, default 16); the bf16 weights remain for the few products that
+# still take bf16 operands.  Residual stream, LayerNorm statistics, softmax, guidance combine and scheduler are fp32.
+# Measured on the B200 (round 2, profiles/r02_pytest_gpu_full.log): one denoiser evaluation 4.9-5.3e-4 relative L2
+# (3.7e-3 with bf16 operands: the CUDA-core cross-check engines and the opt-in tcgen05 per-pair kernel still use them);
+# the -36.5/+7.5 guidance weights amplify branch-differential rounding and random-init weights make the trajectory
+# chaotic, so over 50 DDIM steps the latents drift to 0.017 relative L2 (0.005 after the first step; 0.195 / 0.060 in
+# round 1) with every element within 5e-2 of the tensor scale at every step, and the decoded joints land within
+# 2.3e-3 max-relative (the 16-bit VAE is fp16 throughout, cfb_set_vae_f16: 7.7e-4 on its own; 6.6e-3 in its bf16 form).
+# Every entry is at most ~2x its measured value.
+BF16_TOL = {"eps_l2": 1.2e-3, "eps_l2_bf16_operands": 8e-3, "latent_frac_tol": 5e-2, "latent_frac": 0.98,
+            "latent_l2": 0.035, "joints": 5e-3, "latent_frac90_tol": 0.3}
 
 _samplers = {}
 
@@ -103,7 +105,7 @@ def test_bf16_forward_tensor_core_engines_vs_cuda_core_engines():
     want, watt = oracle_denoise(x.cpu(), 500, o_enc, o_masks)
     e_tc, e_cc = rel_err(eps_tc.cpu(), want), rel_err(eps_cc.cpu(), want)
     print(f"bf16 eps L2 vs oracle: tensor-core {e_tc:.2e}, cuda-core {e_cc:.2e}; tc-vs-cc {rel_err(eps_tc, eps_cc):.2e}")
-    assert e_tc < BF16_TOL["eps_l2"] and e_cc < BF16_TOL["eps_l2"] and e_tc < 2 * e_cc + 1e-3
+    assert e_tc < BF16_TOL["eps_l2"] and e_cc < BF16_TOL["eps_l2_bf16_operands"]   # measured 4.9e-4 / 3.7e-3
     for i in range(5):
         # bf16 scores (|s| up to ~10, 0.4 % operand rounding) move individual probabilities by up to ~15 % in deep layers
         assert max_rel(att_tc[i].cpu(), watt[i]) < 0.3, i
@@ -145,7 +147,7 @@ def test_tcgen05_per_pair_attention_vs_oracle_and_mma_sync():
     print(f"bf16 eps L2 vs oracle: tcgen05 per-pair attention {e_tc:.2e}, mma.sync {e_mma:.2e}; tc-vs-mma "
           f"{rel_err(eps_tc, eps_mma):.2e}; launches {n_tc}; 3-step latents tc-vs-mma {rel_err(rec_tc[-1], rec_mma[-1]):.2e}")
     assert not torch.equal(eps_tc, eps_mma)                       # the switch selects another kernel
-    assert e_tc < BF16_TOL["eps_l2"] and e_tc < 1.5 * e_mma + 1e-3
+    assert e_tc < BF16_TOL["eps_l2_bf16_operands"] and e_tc < 1.5 * e_mma + 1e-3   # measured 2.2e-3 both
     for i in range(5):
         assert max_rel(att_tc[i].cpu(), watt[i]) < 0.3, i
         assert max_rel(att_tc[i].cpu(), att_mma[i].cpu()) < 0.1, i
