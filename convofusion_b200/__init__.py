@@ -33,7 +33,7 @@ def set_bf16_activation_sites(mask: int) -> None:
 
 def set_bf16_activation_f16(enabled) -> None:
     """bf16 handles: which 16-bit activation operands are kept as fp16 (11 significant bits) instead of bf16 (8) and fed
-    to fp16 x fp16 tensor-core products -- same bytes, same speed.  True (default) = every group, False = none (bf16
+    to fp16 x fp16 tensor-core products -- same bytes and instruction counts (1-3 % slower on power-capped GPUs).  True (default) = every group, False = none (bf16
     everywhere, the round-1 behaviour), or a bit mask: 1 LayerNorm outputs, 2 shared-slot probabilities / values and the
     per-pair attention output, 4 norm2 output / per-step keys, 8 self-attention q / k / v, 16 per-pair attention operands.
     Process-wide (cfb_set_bf16_activation_f16)."""

@@ -117,6 +117,7 @@ struct cfb_denoiser {
   struct W16 { const bf16 *w_in, *w_tb1, *w_tb2, *w_ff1, *w_fu, *w_qx, *w_so, *w_ff2; };   // fp16 copies (bf16-typed pointers: 16-bit payloads)
   std::vector<W16> l16;
   const bf16* w_out16 = nullptr;
+  const bf16* w_embed16 = nullptr;
   const bf16 *w_zx16[CFB_N_STREAMS] = {}, *w_yx16[CFB_N_STREAMS] = {};   // memory-side pre-projections [L d, d]
   DeviceBuf w16;
   int act_sites = 0;      // bf16: consumer sites whose LayerNorm input is kept as [hi | lo] in `a2` (g_bf16_act_sites)
@@ -223,9 +224,18 @@ int reserve_split(cfb_denoiser* h, int n_batch, const cfb_memory* mem, bool plan
 // Embedding of the batch entries [b0, b0 + nb) of the guidance batch (entry e = branch * n_clips + clip reads the
 // latents of `clip`): every chain embeds its own rows on its own stream instead of one replicated launch up front.
 // h->xin must hold the cast latents (embed_cast).
+// 16-bit handles: the input latents and latent_embd as fp16 (group 1 of g_bf16_act_f16)
+inline int embed_f16(const cfb_denoiser* h) {
+  return (h->prec == CFB_BF16 && (h->act_f16 & 1) && h->w_embed16 != nullptr) ? 1 : 0;
+}
+template <typename T>
+int cast_latents(cfb_denoiser* h, const float* latents, long long n, cudaStream_t st) {
+  if (embed_f16(h)) return cast_rows<__half>(latents, h->xin.as<__half>(), n, st);
+  return cast_rows<T>(latents, h->xin.as<T>(), n, st);
+}
 template <typename T>
 int embed_cast(cfb_denoiser* h, const float* latents, int n_clips, cudaStream_t st) {
-  return cast_rows<T>(latents, h->xin.as<T>(), (long long)n_clips * h->ntok * h->lat, st);
+  return cast_latents<T>(h, latents, (long long)n_clips * h->ntok * h->lat, st);
 }
 template <typename T>
 int embed_rows(cfb_denoiser* h, int b0, int nb, int n_clips, cudaStream_t st) {
@@ -235,9 +245,9 @@ int embed_rows(cfb_denoiser* h, int b0, int nb, int n_clips, cudaStream_t st) {
     const int run = (n_clips - clip < b0 + nb - e) ? n_clips - clip : b0 + nb - e;   // stay inside one branch
     Epilogue ep{};
     ep.bias = h->w.tok_bias; ep.bias_period = h->ntok; ep.out = h->h.as<float>() + (size_t)e * h->ntok * h->d;
-    ep.ldo = h->d; ep.replicate = 1;
-    CFB_TRY(gemm(h->xin.as<T>() + (size_t)clip * h->ntok * h->lat, tb, h->lat, h->w.w_embed, tb, h->lat, run * h->ntok,
-                 h->d, h->lat, 0, ep, st));
+    ep.ldo = h->d; ep.replicate = 1; ep.ab_f16 = embed_f16(h);
+    CFB_TRY(gemm(h->xin.as<T>() + (size_t)clip * h->ntok * h->lat, tb, h->lat,
+                 ep.ab_f16 ? (const void*)h->w_embed16 : h->w.w_embed, tb, h->lat, run * h->ntok, h->d, h->lat, 0, ep, st));
     e += run;
   }
   return CFB_OK;
@@ -247,11 +257,13 @@ template <typename T>
 int embed(cfb_denoiser* h, const float* latents, int n_in, int replicate, cudaStream_t st) {
   // denoiser.py:183-187,316-326: latent_embd + body/hand embedding + SineBH positional encoding
   const int rows = n_in * h->ntok;
-  CFB_TRY(cast_rows<T>(latents, h->xin.as<T>(), (long long)rows * h->lat, st));
+  CFB_TRY(cast_latents<T>(h, latents, (long long)rows * h->lat, st));
   Epilogue ep{};
   ep.bias = h->w.tok_bias; ep.bias_period = h->ntok; ep.out = h->h.p; ep.ldo = h->d;
   ep.replicate = replicate; ep.rep_stride = (long long)rows * h->d;
-  return gemm(h->xin.p, sizeof(T) == 2, h->lat, h->w.w_embed, sizeof(T) == 2, h->lat, rows, h->d, h->lat, 0, ep, st);
+  ep.ab_f16 = embed_f16(h);
+  return gemm(h->xin.p, sizeof(T) == 2, h->lat, ep.ab_f16 ? (const void*)h->w_embed16 : h->w.w_embed, sizeof(T) == 2, h->lat,
+              rows, h->d, h->lat, 0, ep, st);
 }
 
 // bf16 handles: queries and memory of the per-pair attention as fp16 (group 16 of g_bf16_act_f16; mma.sync kernel only)
@@ -892,7 +904,7 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
       const size_t d2 = (size_t)h->d * h->d, ffd = (size_t)h->ff * h->d, per = (6 + 2 * CFB_N_STREAMS) * d2 + 2 * ffd;
       const size_t outn = (size_t)h->lat * h->d;
       const size_t pre = (size_t)h->L * d2;
-      CFB_TRY(h->w16.reserve((per * h->L + outn + 2 * CFB_N_STREAMS * pre) * 2, nullptr));
+      CFB_TRY(h->w16.reserve((per * h->L + 2 * outn + 2 * CFB_N_STREAMS * pre) * 2, nullptr));
       bf16* p = h->w16.as<bf16>();
       auto conv = [&](const void* src, size_t n, const bf16** dst) -> int {
         CFB_TRY(bf16_to_f16((const bf16*)src, p, n, nullptr));
@@ -911,6 +923,7 @@ int cfb_denoiser_create(const cfb_denoiser_weights* w, cfb_denoiser** out) {
         CFB_TRY(conv(h->layers[l].w_ff2, ffd, &h->l16[l].w_ff2));
       }
       CFB_TRY(conv(h->w.w_out, outn, &h->w_out16));
+      CFB_TRY(conv(h->w.w_embed, outn, &h->w_embed16));
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
         CFB_TRY(conv(h->w.w_zx[x], pre, &h->w_zx16[x]));
         CFB_TRY(conv(h->w.w_yx[x], pre, &h->w_yx16[x]));
@@ -984,8 +997,9 @@ int cfb_denoiser_attach_f16_weights(cfb_denoiser* h, const cfb_denoiser_weights*
     h->l16[l] = cfb_denoiser::W16{(const bf16*)s.w_in, (const bf16*)s.w_tb1, (const bf16*)s.w_tb2, (const bf16*)s.w_ff1,
                                   (const bf16*)s.w_fu, (const bf16*)s.w_qx, (const bf16*)s.w_so, (const bf16*)s.w_ff2};
   }
-  CFB_CHECK(w16->w_out, "cfb_denoiser_attach_f16_weights: latent_proj missing");
+  CFB_CHECK(w16->w_out && w16->w_embed, "cfb_denoiser_attach_f16_weights: latent_proj / latent_embd missing");
   h->w_out16 = (const bf16*)w16->w_out;
+  h->w_embed16 = (const bf16*)w16->w_embed;
   for (int x = 0; x < CFB_N_STREAMS; ++x) {
     CFB_CHECK(w16->w_zx[x] && w16->w_yx[x], "cfb_denoiser_attach_f16_weights: pre-projection %d missing", x);
     h->w_zx16[x] = (const bf16*)w16->w_zx[x]; h->w_yx16[x] = (const bf16*)w16->w_yx[x];

@@ -289,6 +289,7 @@ int cast_rows(const float* in, T* out, long long n, cudaStream_t st) {
 }
 template int cast_rows<float>(const float*, float*, long long, cudaStream_t);
 template int cast_rows<bf16>(const float*, bf16*, long long, cudaStream_t);
+template int cast_rows<__half>(const float*, __half*, long long, cudaStream_t);
 
 template <typename T>
 int concat2(const float* a, const float* b, T* out, int rows, int d, cudaStream_t st) {

@@ -117,7 +117,7 @@ def pack_denoiser(sd: Dict[str, Tensor], prefix: str, n_layers: int, n_heads: in
     tok_bias = sd[p + "latent_embd.bias"].detach().float().cpu()[None, :] + bh[tok % 2] + pe_q[tok // 2]
     w.d_model, w.latent_dim, w.n_tokens, w.n_layers, w.n_heads, w.ff_size = d, lat, n_tokens, n_layers, n_heads, ff
     w.precision, w.pe_len = precision, pe_m.shape[0]
-    w.w_embed, w.tok_bias = pk.mat(sd[p + "latent_embd.weight"]), pk.vec(tok_bias)
+    w.w_embed, w.tok_bias = mat2(sd[p + "latent_embd.weight"], w16, "w_embed"), pk.vec(tok_bias)
     w.w_t1, w.b_t1 = pk.vec(sd[p + "time_embedding.linear_1.weight"]), pk.vec(sd[p + "time_embedding.linear_1.bias"])
     w.w_t2, w.b_t2 = pk.vec(sd[p + "time_embedding.linear_2.weight"]), pk.vec(sd[p + "time_embedding.linear_2.bias"])
     w.w_tbmod, w.b_tbmod = pk.vec(torch.cat(tbw, 0)), pk.vec(torch.cat(tbb, 0))

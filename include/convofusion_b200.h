@@ -81,7 +81,7 @@ int cfb_set_fp32_tensor_cores(int mode);
  *    8  q / k / v of the self-attention
  *   16  queries and normalised memory of the per-pair attention (and the memory-side pre-projections that read it)
  * DDIM-50 deviation from the fp32 reference (latent L2): 0.195 (mask 0) -> 0.084 (1) -> 0.049 (3) -> 0.028 (31) at
- * unchanged throughput.  0 = bf16 activations everywhere (round-1 behaviour).  Groups 2 (attention output) and 16 need
+ * the same instruction counts (-0.5 to -3 % throughput on power-capped boxes: the fp16 products draw more).  0 = bf16 activations everywhere (round-1 behaviour).  Groups 2 (attention output) and 16 need
  * the mma.sync per-pair kernel: they are off while cfb_set_cross_tc(1); everything is off with cfb_set_rowblock != 0
  * and on the CUDA-core GEMM backend.
  *
@@ -167,7 +167,7 @@ typedef struct cfb_denoiser cfb_denoiser;
 int cfb_denoiser_create(const cfb_denoiser_weights *w, cfb_denoiser **out);
 /* 16-bit handles: a second copy of the weight matrices in fp16, packed by the host FROM THE FP32 state_dict (same
  * struct, `precision` ignored, only the matrix pointers are read: layers[].w_in / w_so / w_tb1 / w_tb2 / w_qx / w_fu /
- * w_ff1 / w_ff2, w_out, w_zx[], w_yx[]; the tensors must outlive the handle).  The fp16 x fp16 products of
+ * w_ff1 / w_ff2, w_embed, w_out, w_zx[], w_yx[]; the tensors must outlive the handle).  The fp16 x fp16 products of
  * cfb_set_bf16_activation_f16 then meet weights with 11 significant bits; without this call the handle uses fp16
  * conversions of its bf16 weights (8 bits).  Invalidates the handle's captured graph. */
 int cfb_denoiser_attach_f16_weights(cfb_denoiser *h, const cfb_denoiser_weights *w16);
