@@ -97,13 +97,19 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
-template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// float -> fp16 with saturation to +-65504 in the conversion itself (cvt.rn.satfinite: one instruction, no min / max)
+__device__ __forceinline__ uint32_t f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) {
+  const uint32_t r = f16x2_sat(v, 0.f);
+  return __ushort_as_half((unsigned short)(r & 0xffffu));
+}
 // Two floats -> one 32-bit pair of 16-bit values: bf16, or fp16 (clamped to its range) when f16 is set.
 __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
-  if (f16) {
-    const __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<const uint32_t*>(&t);
-  }
+  if (f16) return f16x2_sat(a, b);
   const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&t);
 }

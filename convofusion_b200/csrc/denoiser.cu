@@ -78,6 +78,10 @@ bool gemm_tc_two_term_ok();   // gemm_tc.cu
 // and the per-pair attention output feeding the fuser, 4 norm2's output with the per-step keys (scores / conditional
 // queries), 8 q / k / v of the self-attention, 16 queries and memory of the per-pair attention.
 int g_bf16_act_f16 = getenv("CFB_BF16_ACT_F16") ? atoi(getenv("CFB_BF16_ACT_F16")) : 31;
+// Consumer sites taken back out of the fp16 form (they keep bf16 operands and the bf16 matrices): 1 qkv, 2 TimeBlock
+// linears, 4 scores / conditional queries, 8 linear1, 16 latent_proj, 32 out_proj, 64 linear2, 128 fuser.  Env
+// CFB_BF16_ACT_F16_EXCLUDE (power / accuracy experiments, profiles/r02_act_sites.txt).
+int g_bf16_act_f16_exclude = getenv("CFB_BF16_ACT_F16_EXCLUDE") ? atoi(getenv("CFB_BF16_ACT_F16_EXCLUDE")) : 0;
 int g_bf16_act_sites = getenv("CFB_BF16_ACT_SITES") ? atoi(getenv("CFB_BF16_ACT_SITES")) : 16;
 }
 
@@ -287,7 +291,7 @@ int shared_precompute(cfb_denoiser* h, const SharedPlan& sp, const MemLayout& ml
     const T* m0 = mh + (size_t)ml.row_base[x] * d;          // slot 0 of stream x: [len[x], d]
     if (which == 0) {
       Epilogue ez{}; ez.bias_period = 1; ez.out_bf16 = tb; ez.out = h->zall.as<T>() + (size_t)sp.s_off[x] * Ld; ez.ldo = Ld; ez.replicate = 1;
-      ez.out_f16 = tb && (h->act_f16 & 4) && !h->l16.empty();   // the scores GEMM runs on the fp16 norm2 output (run_layers)
+      ez.out_f16 = tb && (h->act_f16 & 4) && !(g_bf16_act_f16_exclude & 4) && !h->l16.empty();   // the scores GEMM runs on the fp16 norm2 output (run_layers)
       ez.ab_f16 = pair_f16(h);                                   // the memory is fp16 then (mem_hat)
       if constexpr (tb) CFB_TRY(gemm_tc(m0, d, ez.ab_f16 ? h->w_zx16[x] : (const bf16*)h->w.w_zx[x], d, len[x], Ld, d, ez, st));
       else { ez.split = scp; ez.w_static = 1; CFB_TRY(gemm(m0, 0, d, h->w.w_zx[x], 0, d, len[x], Ld, d, 0, ez, st)); }
@@ -448,12 +452,13 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // or the f16 mma.sync attention kernels.  F16_SITES: LayerNorm consumer sites whose `a` is fp16; 128 = the per-pair
   // attention output feeding the fuser (mma.sync kernel only).
   const int fm = (tb && !h->l16.empty()) ? h->act_f16 : 0;
-  const int uc_f16 = ((fm & 2) && !g_cross_tc) ? 1 : 0;
+  const int uc_f16 = ((fm & 2) && !g_cross_tc && !(g_bf16_act_f16_exclude & 128)) ? 1 : 0;
   const int pv_f16 = (fm & 2) ? 1 : 0;                                   // shared-slot probabilities x per-step values
   const int self_f16 = ((fm & 8) && mha_f16_supported(h->ntok, d / h->H)) ? 1 : 0;   // q / k / v of the self-attention
   // 32 = the self-attention output feeding out_proj (fp16 when its kernel runs in fp16), 64 = the GELU output feeding
   // linear2: nothing measurable as activations, but their GEMMs then meet the fp16 weights too
-  const int F16_SITES = ((fm & 1) ? (1 | 2 | 8 | 16 | 64) : 0) | ((fm & 4) ? 4 : 0) | (uc_f16 ? 128 : 0) | (self_f16 ? 32 : 0);
+  const int F16_SITES = (((fm & 1) ? (1 | 2 | 8 | 16 | 64) : 0) | ((fm & 4) ? 4 : 0) | (uc_f16 ? 128 : 0) | (self_f16 ? 32 : 0)) &
+                        ~g_bf16_act_f16_exclude;
   const int pr_f16 = tb ? pair_f16(h) : 0;                                 // queries / memory of the per-pair attention
   ca.out_f16 = uc_f16; ca.in_f16 = pr_f16;
   const long long mod_stride = (long long)h->L * 2 * 2 * d;
@@ -522,7 +527,8 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
     CFB_TRY(lin_T(d, w.w_in, w16.w_in, w.b_in, qkv, 3 * d, 0, 1, self_f16));
     if (self_f16) {
       if constexpr (tb)
-        CFB_TRY(mha_f16(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, st, 1));
+        CFB_TRY(mha_f16(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, st,
+                        (F16_SITES & 32) ? 1 : 0));
     } else {
       CFB_TRY(mha<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, a, d, n_batch, h->ntok, h->ntok, h->H, d / h->H, nullptr, st));
     }
@@ -562,9 +568,9 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
           CFB_CUDA(cudaStreamWaitEvent(sc, aux->ev_a, 0));
         }
         Epilogue eq{}; eq.bias_period = 1; eq.out_bf16 = tb; eq.ldo = CFB_N_STREAMS * d; eq.replicate = 1;
-        eq.ab_f16 = (fm & 4) ? 1 : 0; eq.out_f16 = pr_f16;
+        eq.ab_f16 = (F16_SITES & 4) ? 1 : 0; eq.out_f16 = pr_f16;
         if constexpr (sizeof(T) == 2) {
-          const bf16* wqx = (fm & 4) ? w16.w_qx : (const bf16*)w.w_qx;
+          const bf16* wqx = (F16_SITES & 4) ? w16.w_qx : (const bf16*)w.w_qx;
           TcGroup gq[TC_MAX_GROUPS];
           for (int z = 0; z < ng; ++z)
             gq[z] = TcGroup{a_abs, wqx + (size_t)grp[z].x * d * d, w.b_qx + grp[z].x * d, qx_abs + grp[z].x * d,
@@ -615,7 +621,7 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
       T* sP = h->sP.as<T>() + (size_t)row0 * sp->k_tot;
       Epilogue es{}; es.bias = h->z0all.as<float>() + (size_t)l * sp->n_tot; es.bias_period = 1; es.out = sS;
       es.ldo = sp->n_tot; es.replicate = 1; es.split = scm; es.a_from_ln = 4;   // keys Z change every step: this chain's W slot
-      es.ab_f16 = (fm & 4) ? 1 : 0;                                               // fp16 norm2 output x fp16 keys (shared_precompute)
+      es.ab_f16 = (F16_SITES & 4) ? 1 : 0;                                          // fp16 norm2 output x fp16 keys (shared_precompute)
       CFB_TRY(gemm(a, tb, d, h->zall.as<T>() + (size_t)l * d, tb, Ld, R, sp->n_tot, d, 0, es, st));
       SharedAttnArgs sa{};
       for (int x = 0; x < CFB_N_STREAMS; ++x) {
@@ -1359,7 +1365,7 @@ int cfb_sample(cfb_denoiser* h, const cfb_schedule* sched, const cfb_memory* mem
       key.att[x] = want_att ? att_out[x] : nullptr;
     }
     key.noise = step_noise; key.record = record;
-    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_sites + (h->act_f16 << 20); key.plan[1] = sp.on ? sp.n_groups : 0;
+    key.plan[0] = sp.on + 2 * h->n_chains + 64 * h->rb_mask + 512 * (h->fp32_tc ? 1 + h->split_scheme : 0) + 4096 * h->act_sites + (h->act_f16 << 20);   // (g_bf16_act_f16_exclude is an env-only, process-constant setting) key.plan[1] = sp.on ? sp.n_groups : 0;
     for (int z = 0; sp.on && z < sp.n_groups; ++z) {
       key.plan[2 + 3 * z] = sp.g_stream[z]; key.plan[3 + 3 * z] = sp.g_row_start[z]; key.plan[4 + 3 * z] = sp.g_rows[z];
     }

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) bf16_to_f16_kernel(const bf16* __restrict__ in, __half* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
-    out[i] = __float2half_rn(fminf(fmaxf(__bfloat162float(in[i]), -65504.f), 65504.f));
+    out[i] = from_f32<__half>(__bfloat162float(in[i]));
 }
 
 // mem_c[row] = cond[row] + stream_emb[x] + pe[pos]          (denoiser.py:332-353, time-independent part)

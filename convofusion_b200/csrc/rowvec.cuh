@@ -77,12 +77,9 @@ struct RowVec {
   __device__ __forceinline__ void store_f16(bf16* __restrict__ row, int lane) const {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      float c[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[j] = fminf(fmaxf(v[i * 4 + j], -65504.f), 65504.f);
-      __half2 a = __floats2half2_rn(c[0], c[1]);
-      __half2 b = __floats2half2_rn(c[2], c[3]);
-      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+      uint2 pk;
+      pk.x = f16x2_sat(v[i * 4], v[i * 4 + 1]);
+      pk.y = f16x2_sat(v[i * 4 + 2], v[i * 4 + 3]);
       *reinterpret_cast<uint2*>(row + i * 128 + lane * 4) = pk;
     }
   }
@@ -97,14 +94,11 @@ struct RowVec {
       bf16* dst = row + (c >> 6) * 128 + (c & 63);
       uint2 hi, lo;
       if constexpr (F16) {
-        float w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = fminf(fmaxf(v[i * 4 + j], -65504.f), 65504.f);
-        const __half2 h0 = __floats2half2_rn(w[0], w[1]), h1 = __floats2half2_rn(w[2], w[3]);
-        const __half2 l0 = __floats2half2_rn(w[0] - __low2float(h0), w[1] - __high2float(h0));
-        const __half2 l1 = __floats2half2_rn(w[2] - __low2float(h1), w[3] - __high2float(h1));
-        hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
-        lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+        hi.x = f16x2_sat(v[i * 4], v[i * 4 + 1]); hi.y = f16x2_sat(v[i * 4 + 2], v[i * 4 + 3]);
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&hi.x), h1 = *reinterpret_cast<const __half2*>(&hi.y);
+        // (a value beyond the fp16 range saturates in hi; its remainder saturates in lo: still finite)
+        lo.x = f16x2_sat(v[i * 4] - __low2float(h0), v[i * 4 + 1] - __high2float(h0));
+        lo.y = f16x2_sat(v[i * 4 + 2] - __low2float(h1), v[i * 4 + 3] - __high2float(h1));
       } else {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i * 4], v[i * 4 + 1]);
         __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i * 4 + 2], v[i * 4 + 3]);
