@@ -177,6 +177,46 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in _lib.lib().cfb_last_error()
 
 
+def test_precision_switches_and_packed_formats():
+    """The process-wide precision switches validate their arguments without a device, and the packer writes what the
+    handles expect: bf16 + fp16 matrices for a 16-bit denoiser (cfb_denoiser_attach_f16_weights), fp16 or bf16 matrices
+    for a 16-bit VAE depending on cfb_get_vae_f16, fp32 everywhere for fp32 handles."""
+    from convofusion_b200.pack import pack_denoiser, pack_vae
+    lib = _lib.lib()
+    assert lib.cfb_set_bf16_activation_f16(32) != 0 and lib.cfb_set_bf16_activation_f16(-1) != 0
+    assert lib.cfb_set_bf16_activation_sites(4) != 0 and lib.cfb_set_bf16_activation_sites(64) != 0
+    assert lib.cfb_set_bf16_activation_terms(3) != 0
+    for fn, good in ((lib.cfb_set_bf16_activation_f16, (0, 1, 19, 31)), (lib.cfb_set_bf16_activation_sites, (0, 2, 18, 27, 16))):
+        for v in good:
+            assert fn(v) == 0
+    cf.set_bf16_activation_f16(True)
+    cf.set_bf16_activation_sites(cf.ACT_SITE_LATENT_PROJ)
+    sd = state_dict()
+    den = {k[len("denoiser."):]: v for k, v in sd.items() if k.startswith("denoiser.")}
+    vae = {k[len("vae."):]: v for k, v in sd.items() if k.startswith("vae.")}
+    pk = pack_denoiser(den, "", 9, 4, 16, _lib.BF16, "cpu")
+    assert {t.dtype for t in pk["keep"]} == {torch.bfloat16, torch.float32}
+    assert {t.dtype for t in pk["keep16"]} == {torch.float16}
+    w, w16 = pk["struct"], pk["struct16"]
+    assert w16.n_layers == w.n_layers == 9 and w16.w_out and w16.w_embed and all(w16.w_zx[x] and w16.w_yx[x] for x in range(5))
+    for l in range(9):
+        for f in ("w_in", "w_so", "w_tb1", "w_tb2", "w_qx", "w_fu", "w_ff1", "w_ff2"):
+            assert getattr(pk["layers16"][l], f) and getattr(pk["layers16"][l], f) != getattr(pk["layers"][l], f)
+    # the fp16 matrices are roundings of the fp32 parameters, not of their bf16 forms
+    w_in = den["decoder.layers.0.self_attn.in_proj_weight"]
+    t16 = next(t for t in pk["keep16"] if t.shape == w_in.shape)
+    assert torch.equal(t16, w_in.to(torch.float16)) and not torch.equal(t16, w_in.to(torch.bfloat16).to(torch.float16))
+    assert "struct16" not in pack_denoiser(den, "", 9, 4, 16, _lib.F32, "cpu")
+    try:
+        for f16, want in ((1, torch.float16), (0, torch.bfloat16)):
+            assert lib.cfb_set_vae_f16(f16) == 0 and lib.cfb_get_vae_f16() == f16
+            mats = {t.dtype for t in pack_vae(vae, "", 5, 2, 1024, _lib.BF16, "cpu")["keep"]}
+            assert mats == {want, torch.float32}
+        assert {t.dtype for t in pack_vae(vae, "", 5, 2, 1024, _lib.F32, "cpu")["keep"]} == {torch.float32}
+    finally:
+        cf.set_vae_f16(True)
+
+
 def test_lane_context_and_pool_host_logic():
     """modules.lane is a per-thread, re-entrant selector; SamplerPool validates its arguments and, like every other
     entry point, refuses to run without a GPU."""
