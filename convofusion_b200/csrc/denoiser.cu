@@ -482,10 +482,10 @@ int run_layers(cfb_denoiser* h, int n_batch, CrossArgs ca, float* const att_base
   // row-block kernel for the residual chains: whole 128-row blocks of a plan-driven bf16 step only
   const int rb = (sizeof(T) == 2 && use_rb && row0 % 128 == 0 && R % 128 == 0) ? h->rb_mask : 0;
   // fp32 handles with tensor cores enabled: every GEMM below runs as a three-way bf16 split (gemm_split.cu); the
-  // contexts name this chain's scratch (main stream / side stream) and the handle's cache of split weights
-  const SplitCtx sc_main = split_ctx(h, row0, chain, false), sc_side = split_ctx(h, row0, chain, true);
+  // context names this chain's main-stream scratch and the handle's cache of split weights (the side-stream GEMMs of the
+  // conditional groups take their own rows of the arena, split_ctx(h, group row, chain, side))
+  const SplitCtx sc_main = split_ctx(h, row0, chain, false);
   const SplitCtx* scm = (!tb && h->fp32_tc) ? &sc_main : nullptr;
-  const SplitCtx* scs = (!tb && h->fp32_tc) ? &sc_side : nullptr;
   // a_from_ln carries a site bit for the precision study (gemm_split scheme 3 + CFB_SPLIT_SITES): 1 qkv, 2 TimeBlock
   // linears, 4 scores / conditional queries, 8 linear1, 16 latent_proj; operands that are not LayerNorm outputs:
   // 32 out_proj (self-attention output), 64 linear2 (GELU output), 128 fuser (per-pair attention output), 256 shared
